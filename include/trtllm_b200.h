@@ -1,0 +1,106 @@
+/*
+ * trtllm_b200.h — C ABI of the B200-native LLaMA decoder hot path (libtrtllm_llama_b200.so).
+ *
+ * Plain pointers and sizes only (device pointers unless a parameter says "host"); every call is
+ * asynchronous on `stream` and returns 0 on success, a negative code for a rejected argument, or a
+ * positive cudaError_t.  There is no CPU fallback: every entry point launches sm_100a kernels.
+ *
+ * Each group cites the reference interface it replaces
+ * (T/ = tensorrt_llm_july-release-v1, K/ = T/cpp/tensorrt_llm/kernels, P/ = T/cpp/tensorrt_llm/plugins).
+ * The plugin-level (IPluginV2DynamicExt) and engine-level entry points are in trtllm_b200_plugin.h /
+ * trtllm_b200_runtime.h and sit on top of these.
+ */
+#ifndef TRTLLM_B200_H
+#define TRTLLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* tb_stream_t; /* == cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* tb_version(void);
+/* 0 iff a CUDA device of compute capability 10.x is current. */
+int tb_check_device(void);
+
+/* ---- RMSNorm / LayerNorm (+ residual add) (+ int8 quantisation) ------------------------------
+ * replaces K/layernormKernels.cu:233-264 invokeGeneralLayerNorm (+quant args) and the TRT-native
+ * rms_norm T/tensorrt_llm/functional.py:3195-3219.
+ * x, residual, sum_out, gamma, beta, out: fp16.  If residual != NULL, h = x + residual is
+ * normalised and (if sum_out != NULL) h is written to sum_out.                                  */
+int tb_rmsnorm(void* out, const void* x, const void* residual, void* sum_out, const void* gamma, float eps,
+               int rows, int hidden, tb_stream_t stream);
+/* dynamic != 0: per-token scales written to scale_out[rows]; else static scale *scale_in.
+ * layernorm != 0 selects the reference's mean-subtracting LayerNorm (beta may be NULL).         */
+int tb_rmsnorm_quant(int8_t* out_q, float* scale_out, const void* x, const void* residual, void* sum_out,
+                     const void* gamma, const void* beta, const float* scale_in, float eps, int rows, int hidden,
+                     int dynamic, int layernorm, tb_stream_t stream);
+
+/* ---- quantisers: replace K/quantization.cu:67-84 invokeQuantization, :119-130 invokePerTokenQuantization */
+int tb_quantize_per_token(int8_t* dst, float* scales, const void* src, int rows, int cols, int src_is_fp32,
+                          tb_stream_t stream);
+int tb_quantize_tensor(int8_t* dst, const void* src, int64_t size, const float* scale, int src_is_fp32,
+                       tb_stream_t stream);
+
+/* ---- decode-shape GEMV (M <= 4) ---------------------------------------------------------------
+ * kind: 0 fp16 weights [N,K]; 1 int8 weight-only [N,K] + fp16 scales[N]; 2 int4 weight-only [N,K/2];
+ *       3 W8A8 SmoothQuant (x int8 [M,K], w int8 [N,K], sc per-channel, sr per-token fp32).
+ * replaces K/weightOnlyMatrixVectorMultiplication.cu:371-378 weight_only_gemv_launcher and the M<=4
+ * calls of CutlassInt8GemmRunner::gemm / cuBLAS GemmPlugin.
+ * swiglu != 0: w holds [N = 2*inter, K] (gate rows then up rows), y is [M, inter] = silu(gate)*up.
+ * y_f32 != NULL writes fp32 instead of fp16 (lm_head logits).                                   */
+int tb_gemv(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
+            const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
+            int swiglu, tb_stream_t stream);
+
+/* ---- tcgen05 GEMM (any M) ---------------------------------------------------------------------
+ * kind as tb_gemv.  out_type: 0 fp16, 1 fp32, 2 int32 (SmoothQuantGemm type_id half/float/int32).
+ * replaces CutlassInt8GemmRunner<T>::gemm (K/cutlass_kernels/int8_gemm/int8_gemm.h:108-110),
+ * CutlassFpAIntBGemmRunner<T,W>::gemm (K/cutlass_kernels/fpA_intB_gemm/fpA_intB_gemm.h:75-76) and
+ * the cuBLASLt GemmPlugin (P/gemmPlugin/gemmPlugin.cpp:121-230).
+ * workspace: tb_gemm_tc_workspace_bytes(M,N,K) bytes, zero-initialised once (split-K counters).
+ * force_splits / force_nt: 0 = automatic (test hooks).                                          */
+size_t tb_gemm_tc_workspace_bytes(int M, int N, int K);
+int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, const void* w_scale, const float* sc,
+               const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
+               void* workspace, size_t workspace_bytes, int force_splits, int force_nt, tb_stream_t stream);
+
+/* ---- attention --------------------------------------------------------------------------------
+ * decode step: replaces masked_multihead_attention(params, kvbuf, stream)
+ * (K/decoderMaskedMultiheadAttention.h:184-199) as driven by
+ * GPTAttentionPluginCommon::enqueueGeneration (P/gptAttentionCommon/gptAttentionCommon.cpp:649-780).
+ * kv_cache [B,2,H,S_max,Dh] int8|fp16 updated in place at position seq_lens[b] (or past_len).
+ * len_cap: host upper bound on any seq_lens[b] (sizes shared memory; == past_len when the host
+ * knows it).  workspace: tb_mmha_workspace_bytes(), zero-initialised once.                       */
+size_t tb_mmha_workspace_bytes(int batch, int num_heads, int max_splits);
+int tb_mmha_num_splits(int batch, int num_heads, int len_hint, int max_splits);
+int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
+                   const int* masked_tokens, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
+                   void* workspace, int batch, int num_heads, int head_size, int max_seq_len, int past_len,
+                   int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv, int nsplit,
+                   tb_stream_t stream);
+/* context phase: replaces GPTAttentionPluginCommon::enqueueContext (gptAttentionCommon.cpp:361-620).
+ * qkv [B,S,3*H*Dh] fp16 is rotated in place (q,k), out [B,S,H*Dh].                               */
+int tb_context_attention(void* out, void* qkv, void* kv_cache, const int* input_lengths,
+                         const float* kv_scale_orig_quant, int batch, int seq_len, int num_heads, int head_size,
+                         int max_seq_len, int rotary_dim, float q_scaling, int int8_kv, tb_stream_t stream);
+
+/* ---- glue (TRT-native ops in the reference, k14) ---------------------------------------------- */
+int tb_embedding(void* out, const void* table, const int* ids, int tokens, int hidden, int vocab, tb_stream_t s);
+int tb_swiglu(void* out, const void* gate, const void* up, int rows, int inter, int in_stride, tb_stream_t s);
+int tb_add(void* out, const void* a, const void* b, int64_t n, tb_stream_t s);
+int tb_gather_last_token(void* out, const void* in, const int* last_ids, int batch, int seq, int hidden,
+                         tb_stream_t s);
+int tb_argmax(int* out, const float* logits, int rows, int vocab, int vocab_stride, tb_stream_t s);
+int tb_advance_step(const int* new_ids, int* input_ids, int* output_ids, int* seq_lens, int* step_pos, int batch,
+                    int out_stride, tb_stream_t s);
+int tb_half_to_float(float* out, const void* in, int64_t n, tb_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRTLLM_B200_H */

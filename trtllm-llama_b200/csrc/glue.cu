@@ -1,0 +1,181 @@
+// Small element-wise / gather kernels that TensorRT generated natively in the reference (k14, no
+// source in the reference tree; semantics from the Python graph):
+//   embedding gather           T/tensorrt_llm/layers/embedding.py, LQ/llama_model.py:159-170
+//   silu(fc(x)) * gate(x)      T/tensorrt_llm/layers/mlp.py:68-73, T/tensorrt_llm/functional.py:521-551
+//   residual add               LQ/llama_model.py:100-119
+//   last-token gather          T/tensorrt_llm/functional.py:3316- (gather_last_token_logits)
+//   greedy argmax              DynamicDecodeOp top_k = 1 (T/tensorrt_llm/runtime/generation.py:943-961)
+// All HBM-bound, 16-byte vector accesses.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tb {
+
+__global__ void embedding_kernel(__half* out, const __half* table, const int* ids, int hidden, int vocab) {
+  const int tok = blockIdx.x;
+  int id = ids[tok];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const uint4* src = reinterpret_cast<const uint4*>(table + (size_t) id * hidden);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t) tok * hidden);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// in: [rows, 2*inter] (gate | up) or two separate pointers; out [rows, inter]
+__global__ void swiglu_kernel(__half* out, const __half* gate, const __half* up, int inter, int in_stride, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n8; i += (int64_t) gridDim.x * blockDim.x) {
+    const int64_t row = i / (inter / 8);
+    const int c8 = (int) (i % (inter / 8));
+    uint4 g4 = *reinterpret_cast<const uint4*>(gate + row * in_stride + c8 * 8);
+    uint4 u4 = *reinterpret_cast<const uint4*>(up + row * in_stride + c8 * 8);
+    const __half2* g = reinterpret_cast<const __half2*>(&g4);
+    const __half2* u = reinterpret_cast<const __half2*>(&u4);
+    uint4 o4;
+    __half2* o = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 gf = __half22float2(g[j]), uf = __half22float2(u[j]);
+      // act output rounded to fp16 (TRT fp16 activation layer), then fp16 multiply
+      __half2 a = __floats2half2_rn(gf.x / (1.f + __expf(-gf.x)), gf.y / (1.f + __expf(-gf.y)));
+      float2 af = __half22float2(a);
+      o[j] = __floats2half2_rn(af.x * uf.x, af.y * uf.y);
+    }
+    *reinterpret_cast<uint4*>(out + row * inter + c8 * 8) = o4;
+  }
+}
+
+__global__ void add_kernel(__half* out, const __half* a, const __half* b, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n8; i += (int64_t) gridDim.x * blockDim.x) {
+    uint4 a4 = reinterpret_cast<const uint4*>(a)[i], b4 = reinterpret_cast<const uint4*>(b)[i], o4;
+    const __half2* x = reinterpret_cast<const __half2*>(&a4);
+    const __half2* y = reinterpret_cast<const __half2*>(&b4);
+    __half2* o = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 xf = __half22float2(x[j]), yf = __half22float2(y[j]);
+      o[j] = __floats2half2_rn(xf.x + yf.x, xf.y + yf.y);
+    }
+    reinterpret_cast<uint4*>(out)[i] = o4;
+  }
+}
+
+// rows of [B, S, hidden] at index last_ids[b] - 1 -> [B, hidden]
+__global__ void gather_last_kernel(__half* out, const __half* in, const int* last_ids, int S, int hidden) {
+  const int b = blockIdx.x;
+  int s = last_ids[b] - 1;
+  s = s < 0 ? 0 : (s >= S ? S - 1 : s);
+  const uint4* src = reinterpret_cast<const uint4*>(in + ((size_t) b * S + s) * hidden);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t) b * hidden);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// argmax over fp32 logits [B, V]; lowest index wins ties.  One CTA per row.
+__global__ void __launch_bounds__(1024) argmax_kernel(int* out, const float* logits, int vocab, int vocab_stride) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const float* row = logits + (size_t) blockIdx.x * vocab_stride;
+  float bv = -3.4e38f;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+    const float v = row[i];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    bv = lane < (blockDim.x >> 5) ? sv[lane] : -3.4e38f;
+    bi = lane < (blockDim.x >> 5) ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) out[blockIdx.x] = bi;
+  }
+}
+
+// decode-loop bookkeeping kept on the device so a captured CUDA graph can be replayed:
+// appends the new token to output_ids[b, *step_pos], sets next input ids, advances the lengths.
+__global__ void advance_step_kernel(const int* new_ids, int* input_ids, int* output_ids, int* seq_lens, int* step_pos,
+                                    int batch, int out_stride) {
+  const int b = threadIdx.x;
+  const int pos = *step_pos;
+  if (b < batch) {
+    const int id = new_ids[b];
+    input_ids[b] = id;
+    if (output_ids && pos < out_stride) output_ids[(size_t) b * out_stride + pos] = id;
+    if (seq_lens) seq_lens[b] += 1;
+  }
+  __syncthreads();
+  if (b == 0) *step_pos = pos + 1;
+}
+
+__global__ void half_to_float_kernel(float* out, const __half* in, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
+    out[i] = __half2float(in[i]);
+}
+
+static inline int grid_for(int64_t work, int threads) {
+  int64_t b = (work + threads - 1) / threads;
+  const int64_t cap = (int64_t) kNumSMs * 16;
+  return (int) (b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int tb_embedding(void* out, const void* table, const int* ids, int tokens, int hidden, int vocab, cudaStream_t s) {
+  if (hidden % 8) return -1;
+  embedding_kernel<<<tokens, 128, 0, s>>>((__half*) out, (const __half*) table, ids, hidden, vocab);
+  return (int) cudaGetLastError();
+}
+
+int tb_swiglu(void* out, const void* gate, const void* up, int rows, int inter, int in_stride, cudaStream_t s) {
+  if (inter % 8 || in_stride % 8) return -1;
+  const int64_t n8 = (int64_t) rows * (inter / 8);
+  swiglu_kernel<<<grid_for(n8, 256), 256, 0, s>>>((__half*) out, (const __half*) gate, (const __half*) up, inter,
+                                                  in_stride, n8);
+  return (int) cudaGetLastError();
+}
+
+int tb_add(void* out, const void* a, const void* b, int64_t n, cudaStream_t s) {
+  if (n % 8) return -1;
+  add_kernel<<<grid_for(n / 8, 256), 256, 0, s>>>((__half*) out, (const __half*) a, (const __half*) b, n / 8);
+  return (int) cudaGetLastError();
+}
+
+int tb_gather_last_token(void* out, const void* in, const int* last_ids, int batch, int seq, int hidden,
+                         cudaStream_t s) {
+  if (hidden % 8) return -1;
+  gather_last_kernel<<<batch, 128, 0, s>>>((__half*) out, (const __half*) in, last_ids, seq, hidden);
+  return (int) cudaGetLastError();
+}
+
+int tb_argmax(int* out, const float* logits, int rows, int vocab, int vocab_stride, cudaStream_t s) {
+  argmax_kernel<<<rows, 1024, 0, s>>>(out, logits, vocab, vocab_stride);
+  return (int) cudaGetLastError();
+}
+
+int tb_advance_step(const int* new_ids, int* input_ids, int* output_ids, int* seq_lens, int* step_pos, int batch,
+                    int out_stride, cudaStream_t s) {
+  if (batch > 1024) return -1;
+  advance_step_kernel<<<1, ((batch + 31) / 32) * 32, 0, s>>>(new_ids, input_ids, output_ids, seq_lens, step_pos, batch,
+                                                             out_stride);
+  return (int) cudaGetLastError();
+}
+
+int tb_half_to_float(float* out, const void* in, int64_t n, cudaStream_t s) {
+  half_to_float_kernel<<<grid_for(n, 256), 256, 0, s>>>(out, (const __half*) in, n);
+  return (int) cudaGetLastError();
+}
+}

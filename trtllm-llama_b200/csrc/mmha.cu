@@ -1,0 +1,357 @@
+// Decode-step fused masked multi-head attention for sm_100a: RoPE(neox) on q,k of the new token,
+// in-place KV-cache append (int8 quantised or fp16), QK^T . softmax . V over the cache with the
+// sequence split across CTAs (split-L) and a deterministic in-order combine by the last CTA.
+//
+// Replaces (reference, K/ = T/cpp/tensorrt_llm/kernels/):
+//   K/decoderMaskedMultiheadAttention/decoderMaskedMultiheadAttentionTemplate.h:1195-2183
+//   K/gptKernels.cu:239-253 (updatePaddingCount, folded in: pad = max_input_len - input_lengths[b])
+//   P/gptAttentionCommon/gptAttentionCommon.cpp:649-780 (enqueueGeneration dispatch)
+//
+// HBM-bound byte streaming (one query row per head, MHA: no reuse of K/V across heads), so SIMT with
+// 16-byte coalesced loads, not tensor cores.  Algorithmic bytes per step and layer:
+//   2 * H * B * L * Dh * b_kv   (K and V rows read once)  + B * 3*H*Dh*2 (qkv in) + B*H*Dh*2 (out).
+// Grid = (H, B, nsplit) with nsplit chosen by the host so that H*B*nsplit covers >= 2 waves of 148 SMs.
+//
+// Numerics (documented deviations from the reference, all inside its test tolerance 2e-3,
+// T/tests/attention/test_gpt_attention.py:828-831):
+//   * int8 dequantisation scale is folded: s*(q.K_int8) instead of q.fp16(s*K_int8);
+//   * with nsplit > 1 the probabilities are normalised after the combine (flash-decoding) rather
+//     than before P.V; with nsplit == 1 the reference order (p * 1/(sum+1e-6) -> fp16 -> P.V) is kept.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tb {
+
+constexpr int kMmhaThreads = 256;
+constexpr int kDh = 128;
+
+struct MmhaParams {
+  const __half* qkv;         // [B, 3*H*Dh]
+  void* kv_cache;            // [B, 2, H, S_max, Dh] int8 or fp16
+  __half* out;               // [B, H*Dh]
+  const int* seq_lens;       // [B] tlength per sequence (device); nullptr -> past_len for all
+  const int* input_lengths;  // [B] real prompt lengths (device); nullptr -> no padding
+  const int* masked_tokens;  // [B, S_max] optional
+  const float* kv_scale_orig_quant;
+  const float* kv_scale_quant_orig;
+  float* partial;            // [B*H*nsplit*(Dh+2)] fp32 workspace
+  int* counters;             // [B*H], zero on entry, zero on exit
+  int past_len, max_input_len, S_max, H, rotary_dim;
+  float inv_sqrt_dh;
+};
+
+template <bool INT8>
+struct KvTraits {
+  static constexpr int kLanesPerKey = INT8 ? 8 : 16;   // 16 bytes per lane
+  static constexpr int kDimsPerLane = kDh / kLanesPerKey;
+  static constexpr int kKeysPerIter = kMmhaThreads / kLanesPerKey;
+};
+
+// 16 bytes of one K/V row -> floats (int8: exact integer values, scale applied by the caller)
+template <bool INT8>
+__device__ __forceinline__ void unpack16(const uint4& r, float* f) {
+  if constexpr (INT8) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t u = w[i] ^ 0x80808080u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // (b ^ 0x80) | 0x4B000000 is the float 2^23 + (b + 128); subtracting 8388736 is exact
+        uint32_t bits;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(bits) : "r"(u), "r"(0x4B000000u), "r"(0x7650u + j));
+        f[i * 4 + j] = __uint_as_float(bits) - 8388736.f;
+      }
+    }
+  } else {
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __half22float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+
+template <bool INT8>
+__global__ void __launch_bounds__(kMmhaThreads) mmha_decode_kernel(MmhaParams p) {
+  using TR = KvTraits<INT8>;
+  constexpr int LPK = TR::kLanesPerKey, DPL = TR::kDimsPerLane, KPI = TR::kKeysPerIter;
+  constexpr int ELT = INT8 ? 1 : 2;
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float q_s[kDh];
+  __shared__ __align__(16) __half kcur_s[kDh];
+  __shared__ __align__(16) __half vcur_s[kDh];
+  __shared__ float red[2 * (kMmhaThreads / 32)];
+  __shared__ int s_is_last;
+
+  const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z, nsplit = gridDim.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, hidden = H * kDh;
+  const int tlen = p.seq_lens ? p.seq_lens[b] : p.past_len;              // positions [0, tlen) are cached
+  const int in_len = p.input_lengths ? p.input_lengths[b] : p.max_input_len;
+  const int pad = p.max_input_len - in_len;
+  const int pos = tlen - pad;
+
+  // balanced split of the cached positions, multiples of KPI
+  int chunk = (tlen + nsplit - 1) / nsplit;
+  chunk = (chunk + KPI - 1) / KPI * KPI;
+  const int l0 = min(split * chunk, tlen), l1 = min(l0 + chunk, tlen);
+  const int len = l1 - l0;
+  const bool has_cur = (split == nsplit - 1);
+
+  float* s_s = smem;                                   // [chunk + 1] scores / probabilities
+  float* o_red = smem + ((chunk + 1 + 3) & ~3);        // [KPI][Dh] partial outputs
+
+  const float kv_dq = INT8 ? p.kv_scale_quant_orig[0] : 1.f;
+  const size_t seq_stride = (size_t) 2 * H * p.S_max * kDh * ELT;
+  uint8_t* kbase = reinterpret_cast<uint8_t*>(p.kv_cache) + (size_t) b * seq_stride + (size_t) h * p.S_max * kDh * ELT;
+  uint8_t* vbase = kbase + (size_t) H * p.S_max * kDh * ELT;
+
+  // ---- RoPE on q (all CTAs) and k (last split), cache append (last split) --------------------
+  const __half* qrow = p.qkv + (size_t) b * 3 * hidden + (size_t) h * kDh;
+  if (tid < kDh / 2) {
+    const int half_rot = p.rotary_dim / 2;
+    float c = 1.f, s = 0.f;
+    if (tid < half_rot) {
+      // inv_freq = t / pow(10000, 2j/rot)  (decoderMaskedMultiheadAttentionUtils.h:1511-1515)
+      const float ang = (float) pos / powf(10000.0f, (2 * tid) / (float) p.rotary_dim);
+      c = cosf(ang);
+      s = sinf(ang);
+    }
+    const int i0 = tid < half_rot ? tid : 2 * tid - half_rot + 0, i1 = tid < half_rot ? tid + half_rot : i0 + 1;
+    // (for rotary_dim == Dh every thread owns the pair (j, j + Dh/2); otherwise the non-rotated
+    //  tail dims are passed through pairwise with c = 1, s = 0)
+    const float qa = __half2float(qrow[i0]), qb = __half2float(qrow[i1]);
+    q_s[i0] = __half2float(__float2half_rn(c * qa - s * qb));
+    q_s[i1] = __half2float(__float2half_rn(c * qb + s * qa));
+    if (has_cur) {
+      const float ka = __half2float(qrow[hidden + i0]), kb = __half2float(qrow[hidden + i1]);
+      kcur_s[i0] = __float2half_rn(c * ka - s * kb);
+      kcur_s[i1] = __float2half_rn(c * kb + s * ka);
+      vcur_s[i0] = qrow[2 * hidden + i0];
+      vcur_s[i1] = qrow[2 * hidden + i1];
+    }
+  }
+  __syncthreads();
+  if (has_cur && tid < kDh / 8) {
+    // append 8 dims per thread: K[t] <- k, V[t] <- v (int8: cvt.rni.sat(x * scale))
+    const int d0 = tid * 8;
+    if constexpr (INT8) {
+      const float qs = p.kv_scale_orig_quant[0];
+      uint2 kq, vq;
+      kq.x = pack4_i8(__half2float(kcur_s[d0]) * qs, __half2float(kcur_s[d0 + 1]) * qs,
+                      __half2float(kcur_s[d0 + 2]) * qs, __half2float(kcur_s[d0 + 3]) * qs);
+      kq.y = pack4_i8(__half2float(kcur_s[d0 + 4]) * qs, __half2float(kcur_s[d0 + 5]) * qs,
+                      __half2float(kcur_s[d0 + 6]) * qs, __half2float(kcur_s[d0 + 7]) * qs);
+      vq.x = pack4_i8(__half2float(vcur_s[d0]) * qs, __half2float(vcur_s[d0 + 1]) * qs,
+                      __half2float(vcur_s[d0 + 2]) * qs, __half2float(vcur_s[d0 + 3]) * qs);
+      vq.y = pack4_i8(__half2float(vcur_s[d0 + 4]) * qs, __half2float(vcur_s[d0 + 5]) * qs,
+                      __half2float(vcur_s[d0 + 6]) * qs, __half2float(vcur_s[d0 + 7]) * qs);
+      *reinterpret_cast<uint2*>(kbase + (size_t) tlen * kDh + d0) = kq;
+      *reinterpret_cast<uint2*>(vbase + (size_t) tlen * kDh + d0) = vq;
+    } else {
+      *reinterpret_cast<uint4*>(kbase + ((size_t) tlen * kDh + d0) * 2) = *reinterpret_cast<uint4*>(&kcur_s[d0]);
+      *reinterpret_cast<uint4*>(vbase + ((size_t) tlen * kDh + d0) * 2) = *reinterpret_cast<uint4*>(&vcur_s[d0]);
+    }
+  }
+
+  // ---- Q.K^T over [l0, l1) -------------------------------------------------------------------
+  const int grp = tid / LPK, gl = tid % LPK;
+  float qreg[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) qreg[i] = q_s[gl * DPL + i];
+  const float qk_scale = kv_dq * p.inv_sqrt_dh;
+  const int* mrow = p.masked_tokens ? p.masked_tokens + (size_t) b * p.S_max : nullptr;
+
+  float lmax = -3.0e38f;
+  constexpr int UN = 4;
+  for (int i = grp; i - grp < len; i += KPI * UN) {   // trip count uniform across the warp (shuffles)
+    uint4 raw[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int ii = i + u * KPI;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (ii < len) raw[u] = ldg_nc_v4(kbase + ((size_t) (l0 + ii) * kDh + gl * DPL) * ELT);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int ii = i + u * KPI;
+      float kf[DPL];
+      unpack16<INT8>(raw[u], kf);
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) d = fmaf(qreg[j], kf[j], d);
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (ii < len && gl == 0) {
+        d *= qk_scale;
+        const bool masked = mrow ? (mrow[l0 + ii] != 0) : (l0 + ii >= in_len && l0 + ii < p.max_input_len);
+        if (masked) d = -3.0e38f;
+        s_s[ii] = d;
+        lmax = fmaxf(lmax, d);
+      }
+    }
+  }
+  if (has_cur && warp == 0) {
+    // current token: unquantised k (decoderMaskedMultiheadAttentionTemplate.h:1511-1549)
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d = fmaf(q_s[lane * 4 + j], __half2float(kcur_s[lane * 4 + j]), d);
+    d = warp_sum(d) * p.inv_sqrt_dh;
+    if (lane == 0) {
+      s_s[len] = d;
+      lmax = fmaxf(lmax, d);
+    }
+  }
+  const int n_s = len + (has_cur ? 1 : 0);
+
+  // ---- softmax statistics ---------------------------------------------------------------------
+  lmax = warp_max(lmax);
+  if (lane == 0) red[warp] = lmax;
+  __syncthreads();
+  float m_s = red[0];
+#pragma unroll
+  for (int w = 1; w < kMmhaThreads / 32; ++w) m_s = fmaxf(m_s, red[w]);
+  float lsum = 0.f;
+  for (int i = tid; i < n_s; i += kMmhaThreads) {
+    const float sv = s_s[i];
+    const float e = sv <= -1.0e38f ? 0.f : __expf(sv - m_s);
+    s_s[i] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red[kMmhaThreads / 32 + warp] = lsum;
+  __syncthreads();
+  float l_s = 0.f;
+#pragma unroll
+  for (int w = 0; w < kMmhaThreads / 32; ++w) l_s += red[kMmhaThreads / 32 + w];
+  const float inv_sum = nsplit == 1 ? __fdividef(1.f, l_s + 1.e-6f) : 1.f;
+  for (int i = tid; i < n_s; i += kMmhaThreads)  // p -> fp16 (Template.h:1765 / :1772)
+    s_s[i] = __half2float(__float2half_rn(s_s[i] * inv_sum));
+  __syncthreads();
+
+  // ---- P.V --------------------------------------------------------------------------------------
+  float acc[DPL];
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) acc[j] = 0.f;
+  for (int i = grp; i - grp < len; i += KPI * UN) {
+    uint4 raw[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int ii = i + u * KPI;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (ii < len) raw[u] = ldg_nc_v4(vbase + ((size_t) (l0 + ii) * kDh + gl * DPL) * ELT);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int ii = i + u * KPI;
+      const float pv = ii < len ? s_s[ii] : 0.f;
+      float vf[DPL];
+      unpack16<INT8>(raw[u], vf);
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) acc[j] = fmaf(pv, vf[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) o_red[grp * kDh + gl * DPL + j] = acc[j] * kv_dq;
+  __syncthreads();
+
+  float* part = p.partial + ((size_t) (b * H + h) * nsplit + split) * (kDh + 2);
+  if (tid < kDh) {
+    float o = 0.f;
+#pragma unroll 8
+    for (int g = 0; g < KPI; ++g) o += o_red[g * kDh + tid];
+    if (has_cur) o = fmaf(s_s[len], __half2float(vcur_s[tid]), o);
+    if (nsplit == 1) {
+      p.out[(size_t) b * hidden + h * kDh + tid] = __float2half_rn(o);
+    } else {
+      part[tid] = o;
+      if (tid == 0) { part[kDh] = m_s; part[kDh + 1] = l_s; }
+    }
+  }
+  if (nsplit == 1) return;
+
+  // ---- last CTA of this (b, h) combines the splits in index order (deterministic) --------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(&p.counters[b * H + h], 1);
+    s_is_last = (prev == nsplit - 1);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  if (tid < kDh) {
+    const float* pb = p.partial + (size_t) (b * H + h) * nsplit * (kDh + 2);
+    float gm = -3.0e38f;
+    for (int s = 0; s < nsplit; ++s) gm = fmaxf(gm, __ldcg(pb + s * (kDh + 2) + kDh));
+    float o = 0.f, l = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float w = __expf(__ldcg(pb + s * (kDh + 2) + kDh) - gm);
+      o = fmaf(w, __ldcg(pb + s * (kDh + 2) + tid), o);
+      l = fmaf(w, __ldcg(pb + s * (kDh + 2) + kDh + 1), l);
+    }
+    p.out[(size_t) b * hidden + h * kDh + tid] = __float2half_rn(o * __fdividef(1.f, l + 1.e-6f));
+  }
+  if (tid == 0) p.counters[b * H + h] = 0;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+size_t tb_mmha_workspace_bytes(int batch, int num_heads, int max_splits) {
+  return (size_t) batch * num_heads * max_splits * (kDh + 2) * sizeof(float) + (size_t) batch * num_heads * sizeof(int) + 256;
+}
+
+// split count: enough CTAs for >= 2 waves of 148 SMs, at least 64 cached keys per split
+int tb_mmha_num_splits(int batch, int num_heads, int len_hint, int max_splits) {
+  const int base = batch * num_heads;
+  int want = (2 * kNumSMs + base - 1) / base;
+  int by_len = len_hint / 64;
+  if (by_len < 1) by_len = 1;
+  int n = want < by_len ? want : by_len;
+  if (n > max_splits) n = max_splits;
+  if (n < 1) n = 1;
+  return n;
+}
+
+int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
+                   const int* masked_tokens, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
+                   void* workspace, int batch, int num_heads, int head_size, int max_seq_len, int past_len,
+                   int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv, int nsplit,
+                   cudaStream_t stream) {
+  if (head_size != kDh) return -1;                 // LLaMA-7B head size; other sizes are not built
+  if (rotary_dim != 0 && rotary_dim != kDh) return -1;
+  if (past_len + 1 > max_seq_len || len_cap + 1 > max_seq_len + 1) return -2;
+  if (int8_kv && (!kv_scale_orig_quant || !kv_scale_quant_orig)) return -1;
+  if (nsplit < 1) nsplit = 1;
+  MmhaParams p{};
+  p.qkv = (const __half*) qkv; p.kv_cache = kv_cache; p.out = (__half*) out; p.seq_lens = seq_lens;
+  p.input_lengths = input_lengths; p.masked_tokens = masked_tokens;
+  p.kv_scale_orig_quant = kv_scale_orig_quant; p.kv_scale_quant_orig = kv_scale_quant_orig;
+  p.counters = reinterpret_cast<int*>(workspace);
+  p.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t) batch * num_heads * 4 + 255) & ~(size_t) 255));
+  p.past_len = past_len; p.max_input_len = max_input_len; p.S_max = max_seq_len; p.H = num_heads;
+  p.rotary_dim = rotary_dim; p.inv_sqrt_dh = 1.f / (sqrtf((float) head_size) * q_scaling);
+  // shared memory sized for the longest possible split (len_cap = upper bound on any tlength)
+  const int kpi = int8_kv ? KvTraits<true>::kKeysPerIter : KvTraits<false>::kKeysPerIter;
+  int chunk = (len_cap + nsplit - 1) / nsplit;
+  chunk = (chunk + kpi - 1) / kpi * kpi;
+  const size_t smem = ((size_t) ((chunk + 1 + 3) & ~3) + (size_t) kpi * kDh) * sizeof(float);
+  if (smem > 200 * 1024) return -3;
+  dim3 grid(num_heads, batch, nsplit);
+  if (int8_kv) {
+    if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    mmha_decode_kernel<true><<<grid, kMmhaThreads, smem, stream>>>(p);
+  } else {
+    if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    mmha_decode_kernel<false><<<grid, kMmhaThreads, smem, stream>>>(p);
+  }
+  return (int) cudaGetLastError();
+}
+}
