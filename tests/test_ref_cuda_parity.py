@@ -80,7 +80,10 @@ def test_mmha_reference_kernel(ref, ops, int8_kv, past):
     c_or = cache.copy()
     out_or = R.mmha_decode(qkv, c_or, past, in_lens, max_in, num_heads=H, head_size=Dh, kv_scale_orig_quant=s_q,
                            kv_scale_quant_orig=s_dq).astype(np.float32)
-    np.testing.assert_allclose(out_or, out_ref, atol=2e-3)
+    # T/tests/attention/test_gpt_attention.py:828-831: atol 2e-3 on outputs of magnitude <= 1; outputs here
+    # reach ~4, so the same bound is applied relative to the output scale (2 fp16 ulps at that scale)
+    tol = 2e-3 * max(1.0, float(np.abs(out_ref).max()))
+    np.testing.assert_allclose(out_or, out_ref, atol=tol)
     if int8_kv:
         assert np.abs(c_or.astype(np.int32) - cache_after_ref.astype(np.int32)).max() <= 1
     else:
@@ -92,7 +95,7 @@ def test_mmha_reference_kernel(ref, ops, int8_kv, past):
         kw = dict(kv_scale_orig_quant=d_sq, kv_scale_quant_orig=d_sdq) if int8_kv else {}
         out_my = ops.mmha_decode(d_qkv, c_my, past, num_heads=H, head_size=Dh, max_input_len=max_in, seq_lens=d_seq,
                                  input_lengths=d_in, masked_tokens=d_mask, nsplit=nsplit, **kw)
-        np.testing.assert_allclose(host(out_my).astype(np.float32), out_ref, atol=2e-3)
+        np.testing.assert_allclose(host(out_my).astype(np.float32), out_ref, atol=tol)
         if int8_kv:
             assert np.abs(host(c_my).astype(np.int32) - cache_after_ref.astype(np.int32)).max() <= 1
         else:

@@ -7,10 +7,10 @@
 // TMEM (double-buffered, 2*NT columns) and is read back with tcgen05.ld by four epilogue warps.
 //
 //   KIND 0  fp16 x fp16  -> kind::f16, fp32 accumulate        (GemmPlugin / lm_head)
-//   KIND 1  int8 x int8  -> kind::i8,  int32 accumulate, epilogue float(acc) * (sc[n]*sr[m])
+//   KIND 3  int8 x int8  -> kind::i8,  int32 accumulate, epilogue float(acc) * (sc[n]*sr[m])
 //           replaces CutlassInt8GemmRunner<T>::gemm, K/cutlass_kernels/int8_gemm/int8_gemm_template.h:56-172,
 //           epilogue CE/epilogue/threadblock/epilogue_per_row_per_col_scale.h:279-349
-//   KIND 2/3 fp16 x int8/int4 weight-only: raw weight bytes arrive by TMA, four converter warps expand
+//   KIND 1/2 fp16 x int8/int4 weight-only: raw weight bytes arrive by TMA, four converter warps expand
 //           them exactly to fp16 into the 128B-swizzled UMMA tile, per-channel scale in the epilogue
 //           replaces CutlassFpAIntBGemmRunner::gemm, K/cutlass_kernels/fpA_intB_gemm/fpA_intB_gemm_template.h:49-175
 //
@@ -29,7 +29,7 @@
 
 namespace tb {
 
-enum { kGF16 = 0, kGI8 = 1, kGW8 = 2, kGW4 = 3 };
+enum { kGF16 = 0, kGW8 = 1, kGW4 = 2, kGI8 = 3 };   // same numbering as tb_gemv
 
 struct GemmTcParams {
   void* c;                 // [M, N] fp16 / fp32 / int32

@@ -125,8 +125,10 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(GemvParams p) {
   constexpr int EPC = KTraits<KIND>::kElemsPer16B;   // k elements per 16-byte weight chunk
   const int K = p.K;
   const int x_bytes = p.M * K * (KIND == kA8W8 ? 1 : 2);
-  for (int i = threadIdx.x * 16; i < x_bytes; i += kGemvThreads * 16)
-    *reinterpret_cast<uint4*>(xs + i) = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + i);
+  const int xs_bytes = MB * K * (KIND == kA8W8 ? 1 : 2);    // rows [M, MB) are zero-filled
+  for (int i = threadIdx.x * 16; i < xs_bytes; i += kGemvThreads * 16)
+    *reinterpret_cast<uint4*>(xs + i) =
+        i < x_bytes ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + i) : make_uint4(0, 0, 0, 0);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(GemvParams p) {
 
 template <int KIND, int MB, bool SWIGLU>
 static int launch_gemv_t(const GemvParams& p, cudaStream_t stream) {
-  const size_t smem = (size_t) p.M * p.K * (KIND == kA8W8 ? 1 : 2);
+  const size_t smem = (size_t) MB * p.K * (KIND == kA8W8 ? 1 : 2);
   auto kern = gemv_kernel<KIND, MB, SWIGLU>;
   if (smem > 48 * 1024) {
     if (smem > 200 * 1024) return -2;
