@@ -62,12 +62,15 @@ int tb_gemv(int kind, void* y, float* y_f32, const void* x, const void* w, const
  * replaces CutlassInt8GemmRunner<T>::gemm (K/cutlass_kernels/int8_gemm/int8_gemm.h:108-110),
  * CutlassFpAIntBGemmRunner<T,W>::gemm (K/cutlass_kernels/fpA_intB_gemm/fpA_intB_gemm.h:75-76) and
  * the cuBLASLt GemmPlugin (P/gemmPlugin/gemmPlugin.cpp:121-230).
- * workspace: tb_gemm_tc_workspace_bytes(M,N,K) bytes, zero-initialised once (split-K counters).
- * force_splits / force_nt: 0 = automatic (test hooks).                                          */
+ * workspace: tb_gemm_tc_workspace_bytes(M,N,K) bytes of scratch (need not be initialised: a TensorRT
+ * workspace is fine).  counters: tb_gemm_tc_counter_bytes() bytes, zeroed ONCE by the owner; the
+ * split-K arrival counters reset themselves.  force_splits / force_nt: 0 = automatic (test hooks). */
 size_t tb_gemm_tc_workspace_bytes(int M, int N, int K);
+size_t tb_gemm_tc_counter_bytes(void);
 int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, const void* w_scale, const float* sc,
                const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
-               void* workspace, size_t workspace_bytes, int force_splits, int force_nt, tb_stream_t stream);
+               void* workspace, size_t workspace_bytes, int* counters, int force_splits, int force_nt,
+               tb_stream_t stream);
 
 /* ---- attention --------------------------------------------------------------------------------
  * decode step: replaces masked_multihead_attention(params, kvbuf, stream)
@@ -75,12 +78,15 @@ int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, co
  * GPTAttentionPluginCommon::enqueueGeneration (P/gptAttentionCommon/gptAttentionCommon.cpp:649-780).
  * kv_cache [B,2,H,S_max,Dh] int8|fp16 updated in place at position seq_lens[b] (or past_len).
  * len_cap: host upper bound on any seq_lens[b] (sizes shared memory; == past_len when the host
- * knows it).  workspace: tb_mmha_workspace_bytes(), zero-initialised once.                       */
+ * knows it).  workspace: tb_mmha_workspace_bytes() of scratch; counters: tb_mmha_counter_bytes(),
+ * zeroed ONCE by the owner (self-resetting split-L arrival counters).                            */
 size_t tb_mmha_workspace_bytes(int batch, int num_heads, int max_splits);
+size_t tb_mmha_counter_bytes(int batch, int num_heads);
 int tb_mmha_num_splits(int batch, int num_heads, int len_hint, int max_splits);
 int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
                    const int* masked_tokens, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
-                   void* workspace, int batch, int num_heads, int head_size, int max_seq_len, int past_len,
+                   void* workspace, int* counters, int batch, int num_heads, int head_size, int max_seq_len,
+                   int past_len,
                    int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv, int nsplit,
                    tb_stream_t stream);
 /* context phase: replaces GPTAttentionPluginCommon::enqueueContext (gptAttentionCommon.cpp:361-620).
@@ -99,6 +105,10 @@ int tb_argmax(int* out, const float* logits, int rows, int vocab, int vocab_stri
 int tb_advance_step(const int* new_ids, int* input_ids, int* output_ids, int* seq_lens, int* step_pos, int batch,
                     int out_stride, tb_stream_t s);
 int tb_half_to_float(float* out, const void* in, int64_t n, tb_stream_t s);
+int tb_fill_int(int* p, int value, int n, tb_stream_t s);
+int tb_copy(void* dst, const void* src, size_t bytes, tb_stream_t s); /* device-to-device */
+/* in [tp, rows, vocab_local] fp16 (all-gathered vocab-parallel lm_head) -> out [rows, tp*vocab_local] fp32 */
+int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int tp, tb_stream_t s);
 
 #ifdef __cplusplus
 }

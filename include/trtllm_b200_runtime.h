@@ -1,0 +1,79 @@
+/*
+ * trtllm_b200_runtime.h — engine-level C ABI: the C++ runtime that plays TensorRT's role for the LLaMA
+ * decoder (there is no TensorRT in this build).  It looks the plugin creators up in the
+ * registry, creates the operators, and runs the fixed layer schedule of
+ * LQ/llama_model.py:78-119,159-287 by calling IPluginV2DynamicExt::enqueue on each, with the
+ * TensorRT-native glue ops (RMSNorm, residual, SwiGLU, embedding, last-token gather, lm_head, argmax)
+ * fused into plugin epilogues or run as small kernels.  The decode step is captured in a CUDA graph.
+ *
+ * Replaces: the serialised TensorRT engine + IExecutionContext (T/tensorrt_llm/runtime/generation.py:61-100)
+ * and the step loop of GenerationSession.decode (generation.py:782-997) for greedy, contiguous-KV, beam 1.
+ */
+#ifndef TRTLLM_B200_RUNTIME_H
+#define TRTLLM_B200_RUNTIME_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "trtllm_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tbrt_engine tbrt_engine;
+
+enum { TBRT_MODE_FP16 = 0, TBRT_MODE_W8 = 1, TBRT_MODE_W4 = 2, TBRT_MODE_SQ = 3 };
+
+typedef struct {
+  int32_t hidden, heads, inter, layers, vocab, head_size; /* LQ/build.py:59-71 */
+  float rms_eps;
+  int32_t mode;          /* TBRT_MODE_*: use_weight_only (+int4) / use_smooth_quant per-token+per-channel (LQ/build.py:276-324) */
+  int32_t int8_kv;       /* --int8_kv_cache */
+  int32_t max_batch, max_input_len, max_output_len; /* builder limits (LQ/build.py:73-75) */
+  int32_t tp_size, tp_rank;   /* Mapping(world_size, rank) (T/tensorrt_llm/mapping.py) */
+  int32_t use_cuda_graph;
+} tbrt_config;
+
+tbrt_engine* tbrt_create(const tbrt_config* cfg);
+void tbrt_destroy(tbrt_engine* e);
+const char* tbrt_last_error(void);
+
+/* Bind one weight tensor (device pointer, not copied; the caller keeps it alive).  Names follow the
+ * reference's module tree (LQ/weight_quant.py:176-446):
+ *   vocab_embedding.weight [V, hidden] fp16     ln_f.weight [hidden] fp16     lm_head.weight [V/tp, hidden] fp16
+ *   layers.{i}.input_layernorm.weight, layers.{i}.post_layernorm.weight [hidden] fp16
+ *   layers.{i}.attention.qkv.weight    [3*hidden/tp, hidden]   layers.{i}.attention.dense.weight [hidden, hidden/tp]
+ *   layers.{i}.mlp.fc_gate.weight      [2*inter/tp, hidden] (fc = gate_proj rows, then gate = up_proj rows)
+ *   layers.{i}.mlp.proj.weight         [hidden, inter/tp]
+ *   weight dtype by mode: fp16 | int8 [N,K] | packed int4 [N,K/2] | int8 [N,K];
+ *   <linear>.per_channel_scale: fp16 [N] (weight-only) or fp32 [N] (SmoothQuant)
+ *   layers.{i}.attention.kv_orig_quant_scale / kv_quant_orig_scale fp32 [1] (int8 KV, LQ/weight_quant.py:439-446) */
+int tbrt_set_tensor(tbrt_engine* e, const char* name, const void* device_ptr, size_t bytes);
+/* Check that every tensor is bound, create plugins, allocate activations / KV caches / workspace. */
+int tbrt_finalize(tbrt_engine* e);
+size_t tbrt_device_bytes(const tbrt_engine* e);
+
+/* Context phase over a padded batch: ids [B,S] int32 and input_lengths [B] are DEVICE pointers. */
+int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_lengths, int batch, int seq, tb_stream_t s);
+/* One generation step for every sequence (token ids come from the previous step's argmax). */
+int tbrt_step(tbrt_engine* e, tb_stream_t s);
+/* fp32 logits [B, vocab] of the last context/step call (device pointer). */
+const float* tbrt_logits(const tbrt_engine* e);
+/* generated ids so far: device int32 [B, max_output_len] (column j = j-th new token). */
+const int32_t* tbrt_output_ids(const tbrt_engine* e);
+/* device pointer of layer i's KV cache [B,2,H/tp,S_max,Dh] (tests) */
+void* tbrt_kv_cache(const tbrt_engine* e, int layer);
+
+/* Whole request with HOST buffers (pinned for async copies): H2D ids/lengths, context, max_new-1
+ * steps, D2H of out_ids [B, max_new]; returns after the stream is synchronised.
+ * This is GenerationSession.decode (generation.py:782-997) for greedy sampling without early stop. */
+int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_lengths, int batch, int seq, int max_new,
+                  int32_t* host_out_ids, tb_stream_t s);
+/* kernels launched by the last tbrt_context / tbrt_step / tbrt_generate call */
+int64_t tbrt_last_launches(const tbrt_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRTLLM_B200_RUNTIME_H */

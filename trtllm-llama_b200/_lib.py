@@ -31,10 +31,12 @@ SIGNATURES = {
     "tb_quantize_tensor": (i32, [vp, vp, i64, vp, i32, vp]),
     "tb_gemv": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp]),
     "tb_gemm_tc_workspace_bytes": (sz, [i32, i32, i32]),
-    "tb_gemm_tc": (i32, [i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, vp, sz, i32, i32, vp]),
+    "tb_gemm_tc_counter_bytes": (sz, []),
+    "tb_gemm_tc": (i32, [i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, vp, sz, vp, i32, i32, vp]),
     "tb_mmha_workspace_bytes": (sz, [i32, i32, i32]),
     "tb_mmha_num_splits": (i32, [i32, i32, i32, i32]),
-    "tb_mmha_decode": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32,
+    "tb_mmha_counter_bytes": (sz, [i32, i32]),
+    "tb_mmha_decode": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32,
                              i32, vp]),
     "tb_context_attention": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp]),
     "tb_embedding": (i32, [vp, vp, vp, i32, i32, i32, vp]),
@@ -44,7 +46,78 @@ SIGNATURES = {
     "tb_argmax": (i32, [vp, vp, i32, i32, i32, vp]),
     "tb_advance_step": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
     "tb_half_to_float": (i32, [vp, vp, i64, vp]),
+    "tb_fill_int": (i32, [vp, i32, i32, vp]),
+    "tb_copy": (i32, [vp, vp, sz, vp]),
+    "tb_gather_logits": (i32, [vp, vp, i32, i32, i32, vp]),
 }
+
+
+
+class TbrtConfig(C.Structure):
+    """== tbrt_config (include/trtllm_b200_runtime.h)"""
+    _fields_ = [("hidden", i32), ("heads", i32), ("inter", i32), ("layers", i32), ("vocab", i32), ("head_size", i32),
+                ("rms_eps", f32), ("mode", i32), ("int8_kv", i32), ("max_batch", i32), ("max_input_len", i32),
+                ("max_output_len", i32), ("tp_size", i32), ("tp_rank", i32), ("use_cuda_graph", i32)]
+
+
+class TbpField(C.Structure):
+    """== tbp_field == nvinfer1::PluginField"""
+    _fields_ = [("name", C.c_char_p), ("data", vp), ("type", i32), ("length", i32)]
+
+
+class TbpDims(C.Structure):
+    """== tbp_dims == nvinfer1::Dims"""
+    _fields_ = [("nb_dims", i32), ("d", i32 * 8)]
+
+
+class TbpTensorDesc(C.Structure):
+    """== tbp_tensor_desc == nvinfer1::PluginTensorDesc"""
+    _fields_ = [("dims", TbpDims), ("type", i32), ("format", i32), ("scale", f32)]
+
+
+_P = C.POINTER
+SIGNATURES.update({
+    # include/trtllm_b200_plugin.h
+    "tbp_init": (i32, [C.c_char_p]),
+    "tbp_num_creators": (i32, []),
+    "tbp_creator_name": (C.c_char_p, [i32]),
+    "tbp_creator_fields": (i32, [C.c_char_p, _P(C.c_char_p), i32]),
+    "tbp_create": (vp, [C.c_char_p, C.c_char_p, C.c_char_p, _P(TbpField), i32]),
+    "tbp_deserialize": (vp, [C.c_char_p, C.c_char_p, C.c_char_p, vp, sz]),
+    "tbp_clone": (vp, [vp]),
+    "tbp_destroy": (None, [vp]),
+    "tbp_type": (C.c_char_p, [vp]),
+    "tbp_version": (C.c_char_p, [vp]),
+    "tbp_namespace": (C.c_char_p, [vp]),
+    "tbp_serialization_size": (sz, [vp]),
+    "tbp_serialize": (i32, [vp, vp]),
+    "tbp_nb_outputs": (i32, [vp]),
+    "tbp_output_dims": (i32, [vp, i32, _P(TbpDims), i32, _P(TbpDims)]),
+    "tbp_output_dtype": (i32, [vp, i32, _P(i32), i32]),
+    "tbp_supports_format": (i32, [vp, i32, _P(TbpTensorDesc), i32, i32]),
+    "tbp_workspace_size": (sz, [vp, _P(TbpTensorDesc), i32, _P(TbpTensorDesc), i32]),
+    "tbp_initialize": (i32, [vp]),
+    "tbp_enqueue": (i32, [vp, _P(TbpTensorDesc), _P(TbpTensorDesc), _P(vp), _P(vp), vp, vp]),
+    "tb_comm_unique_id": (i32, [vp]),
+    "tb_comm_init": (i32, [vp, _P(i32), i32, i32]),
+    "initLibNvInferPlugins": (C.c_bool, [vp, C.c_char_p]),
+    "getPluginRegistry": (vp, []),
+    "getInferLibVersion": (i32, []),
+    # include/trtllm_b200_runtime.h
+    "tbrt_create": (vp, [_P(TbrtConfig)]),
+    "tbrt_destroy": (None, [vp]),
+    "tbrt_last_error": (C.c_char_p, []),
+    "tbrt_set_tensor": (i32, [vp, C.c_char_p, vp, sz]),
+    "tbrt_finalize": (i32, [vp]),
+    "tbrt_device_bytes": (sz, [vp]),
+    "tbrt_context": (i32, [vp, vp, vp, i32, i32, vp]),
+    "tbrt_step": (i32, [vp, vp]),
+    "tbrt_logits": (vp, [vp]),
+    "tbrt_output_ids": (vp, [vp]),
+    "tbrt_kv_cache": (vp, [vp, i32]),
+    "tbrt_generate": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
+    "tbrt_last_launches": (i64, [vp]),
+})
 
 _lib = None
 

@@ -46,6 +46,7 @@ struct GemmTcParams {
 };
 
 constexpr int kTileN = 128;      // output channels per tile (UMMA_M)
+constexpr int kGemmMaxCounters = 4096;   // tiles that may be split (split-K only when tiles < #SMs)
 constexpr int kStageKBytes = 128; // bytes of K per row per stage (one 128B swizzle atom)
 
 template <int KIND, int NT>
@@ -356,7 +357,7 @@ static int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, i
 
 template <int KIND, int NT>
 static int launch_gemm_tc(GemmTcParams p, const void* x, const void* w, void* workspace, size_t workspace_bytes,
-                          int force_splits, cudaStream_t stream) {
+                          int* counters, int force_splits, cudaStream_t stream) {
   using Cfg = GemmCfg<KIND, NT>;
   CUtensorMap tw, tx;
   int rc;
@@ -397,11 +398,10 @@ static int launch_gemm_tc(GemmTcParams p, const void* x, const void* w, void* wo
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;   // no empty splits
   p.splits = splits;
   if (splits > 1) {
-    const size_t cnt_bytes = (((size_t) base_items * sizeof(int)) + 255) & ~(size_t) 255;
-    const size_t need = cnt_bytes + (size_t) base_items * splits * NT * kTileN * sizeof(float);
-    if (!workspace || workspace_bytes < need) return -12;
-    p.counters = reinterpret_cast<int*>(workspace);
-    p.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + cnt_bytes);
+    const size_t need = (size_t) base_items * splits * NT * kTileN * sizeof(float);
+    if (!workspace || workspace_bytes < need || !counters || base_items > kGemmMaxCounters) return -12;
+    p.counters = counters;
+    p.partial = reinterpret_cast<float*>(workspace);
   }
   const int items = base_items * splits;
   int grid = items < kNumSMs ? items : kNumSMs;
@@ -412,16 +412,16 @@ static int launch_gemm_tc(GemmTcParams p, const void* x, const void* w, void* wo
 }
 
 template <int KIND>
-static int dispatch_nt(const GemmTcParams& p, const void* x, const void* w, void* ws, size_t ws_bytes, int force_splits,
-                       int force_nt, cudaStream_t stream) {
+static int dispatch_nt(const GemmTcParams& p, const void* x, const void* w, void* ws, size_t ws_bytes, int* counters,
+                       int force_splits, int force_nt, cudaStream_t stream) {
   int nt = force_nt;
   if (nt <= 0) nt = p.M <= 16 ? 16 : (p.M <= 32 ? 32 : (p.M <= 64 ? 64 : (p.M <= 128 ? 128 : 256)));
   switch (nt) {
-    case 16:  return launch_gemm_tc<KIND, 16>(p, x, w, ws, ws_bytes, force_splits, stream);
-    case 32:  return launch_gemm_tc<KIND, 32>(p, x, w, ws, ws_bytes, force_splits, stream);
-    case 64:  return launch_gemm_tc<KIND, 64>(p, x, w, ws, ws_bytes, force_splits, stream);
-    case 128: return launch_gemm_tc<KIND, 128>(p, x, w, ws, ws_bytes, force_splits, stream);
-    case 256: return launch_gemm_tc<KIND, 256>(p, x, w, ws, ws_bytes, force_splits, stream);
+    case 16:  return launch_gemm_tc<KIND, 16>(p, x, w, ws, ws_bytes, counters, force_splits, stream);
+    case 32:  return launch_gemm_tc<KIND, 32>(p, x, w, ws, ws_bytes, counters, force_splits, stream);
+    case 64:  return launch_gemm_tc<KIND, 64>(p, x, w, ws, ws_bytes, counters, force_splits, stream);
+    case 128: return launch_gemm_tc<KIND, 128>(p, x, w, ws, ws_bytes, counters, force_splits, stream);
+    case 256: return launch_gemm_tc<KIND, 256>(p, x, w, ws, ws_bytes, counters, force_splits, stream);
   }
   return -1;
 }
@@ -440,12 +440,14 @@ size_t tb_gemm_tc_workspace_bytes(int M, int N, int K) {
   const int m_tiles = (M + nt - 1) / nt;
   const size_t base = (size_t) n_tiles * m_tiles;
   size_t splits = base < (size_t) kNumSMs ? (2 * kNumSMs + base - 1) / base : 1;
-  return ((base * sizeof(int) + 255) & ~(size_t) 255) + base * splits * nt * kTileN * sizeof(float) + 256;
+  return base * splits * nt * kTileN * sizeof(float) + 256;
 }
+size_t tb_gemm_tc_counter_bytes(void) { return (size_t) kGemmMaxCounters * sizeof(int); }
 
 int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, const void* w_scale, const float* sc,
                const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
-               void* workspace, size_t workspace_bytes, int force_splits, int force_nt, cudaStream_t stream) {
+               void* workspace, size_t workspace_bytes, int* counters, int force_splits, int force_nt,
+               cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return -1;
   if (kind == kGF16 || kind == kGW8) { if (K % 8) return -1; }   // TMA: 16-byte aligned row pitch
   if (kind == kGI8 && K % 16) return -1;
@@ -458,10 +460,10 @@ int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, co
   p.sc = sc; p.sr = sr; p.sc_per_channel = sc_per_channel; p.sr_per_token = sr_per_token;
   p.M = M; p.N = N; p.K = K;
   switch (kind) {
-    case kGF16: return dispatch_nt<kGF16>(p, x, w, workspace, workspace_bytes, force_splits, force_nt, stream);
-    case kGI8:  return dispatch_nt<kGI8>(p, x, w, workspace, workspace_bytes, force_splits, force_nt, stream);
-    case kGW8:  return dispatch_nt<kGW8>(p, x, w, workspace, workspace_bytes, force_splits, force_nt, stream);
-    case kGW4:  return dispatch_nt<kGW4>(p, x, w, workspace, workspace_bytes, force_splits, force_nt, stream);
+    case kGF16: return dispatch_nt<kGF16>(p, x, w, workspace, workspace_bytes, counters, force_splits, force_nt, stream);
+    case kGI8:  return dispatch_nt<kGI8>(p, x, w, workspace, workspace_bytes, counters, force_splits, force_nt, stream);
+    case kGW8:  return dispatch_nt<kGW8>(p, x, w, workspace, workspace_bytes, counters, force_splits, force_nt, stream);
+    case kGW4:  return dispatch_nt<kGW4>(p, x, w, workspace, workspace_bytes, counters, force_splits, force_nt, stream);
   }
   return -1;
 }

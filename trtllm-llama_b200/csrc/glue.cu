@@ -122,6 +122,22 @@ __global__ void half_to_float_kernel(float* out, const __half* in, int64_t n) {
     out[i] = __half2float(in[i]);
 }
 
+__global__ void fill_int_kernel(int* p, int v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// all-gathered vocab-parallel logits [tp, rows, Vl] fp16 -> [rows, tp*Vl] fp32
+// (the slice+concat after allgather in T/tensorrt_llm/layers/linear.py:78-97, plus the fp32 cast of LQ/llama_model.py:279)
+__global__ void gather_logits_kernel(float* out, const __half* in, int rows, int vl, int tp, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+    const int j = (int) (i % vl);
+    const int r = (int) ((i / vl) % rows);
+    const int t = (int) (i / ((int64_t) vl * rows));
+    out[(size_t) r * vl * tp + (size_t) t * vl + j] = __half2float(in[i]);
+  }
+}
+
 static inline int grid_for(int64_t work, int threads) {
   int64_t b = (work + threads - 1) / threads;
   const int64_t cap = (int64_t) kNumSMs * 16;
@@ -171,6 +187,21 @@ int tb_advance_step(const int* new_ids, int* input_ids, int* output_ids, int* se
   if (batch > 1024) return -1;
   advance_step_kernel<<<1, ((batch + 31) / 32) * 32, 0, s>>>(new_ids, input_ids, output_ids, seq_lens, step_pos, batch,
                                                              out_stride);
+  return (int) cudaGetLastError();
+}
+
+int tb_copy(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  return (int) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
+}
+
+int tb_fill_int(int* p, int value, int n, cudaStream_t s) {
+  fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, value, n);
+  return (int) cudaGetLastError();
+}
+
+int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int tp, cudaStream_t s) {
+  const int64_t n = (int64_t) rows * vocab_local * tp;
+  gather_logits_kernel<<<grid_for(n, 256), 256, 0, s>>>(out, (const __half*) in, rows, vocab_local, tp, n);
   return (int) cudaGetLastError();
 }
 

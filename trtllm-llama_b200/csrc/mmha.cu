@@ -305,8 +305,9 @@ using namespace tb;
 extern "C" {
 
 size_t tb_mmha_workspace_bytes(int batch, int num_heads, int max_splits) {
-  return (size_t) batch * num_heads * max_splits * (kDh + 2) * sizeof(float) + (size_t) batch * num_heads * sizeof(int) + 256;
+  return (size_t) batch * num_heads * max_splits * (kDh + 2) * sizeof(float) + 256;
 }
+size_t tb_mmha_counter_bytes(int batch, int num_heads) { return (size_t) batch * num_heads * sizeof(int); }
 
 // split count: enough CTAs for >= 2 waves of 148 SMs, at least 64 cached keys per split
 int tb_mmha_num_splits(int batch, int num_heads, int len_hint, int max_splits) {
@@ -322,7 +323,7 @@ int tb_mmha_num_splits(int batch, int num_heads, int len_hint, int max_splits) {
 
 int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
                    const int* masked_tokens, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
-                   void* workspace, int batch, int num_heads, int head_size, int max_seq_len, int past_len,
+                   void* workspace, int* counters, int batch, int num_heads, int head_size, int max_seq_len, int past_len,
                    int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv, int nsplit,
                    cudaStream_t stream) {
   if (head_size != kDh) return -1;                 // LLaMA-7B head size; other sizes are not built
@@ -330,12 +331,13 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
   if (past_len + 1 > max_seq_len || len_cap + 1 > max_seq_len + 1) return -2;
   if (int8_kv && (!kv_scale_orig_quant || !kv_scale_quant_orig)) return -1;
   if (nsplit < 1) nsplit = 1;
+  if (nsplit > 1 && (!workspace || !counters)) return -1;
   MmhaParams p{};
   p.qkv = (const __half*) qkv; p.kv_cache = kv_cache; p.out = (__half*) out; p.seq_lens = seq_lens;
   p.input_lengths = input_lengths; p.masked_tokens = masked_tokens;
   p.kv_scale_orig_quant = kv_scale_orig_quant; p.kv_scale_quant_orig = kv_scale_quant_orig;
-  p.counters = reinterpret_cast<int*>(workspace);
-  p.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + (((size_t) batch * num_heads * 4 + 255) & ~(size_t) 255));
+  p.counters = counters;
+  p.partial = reinterpret_cast<float*>(workspace);
   p.past_len = past_len; p.max_input_len = max_input_len; p.S_max = max_seq_len; p.H = num_heads;
   p.rotary_dim = rotary_dim; p.inv_sqrt_dh = 1.f / (sqrtf((float) head_size) * q_scaling);
   // shared memory sized for the longest possible split (len_cap = upper bound on any tlength)

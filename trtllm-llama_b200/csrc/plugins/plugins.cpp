@@ -1,0 +1,631 @@
+// The IPluginV2DynamicExt operators of the LLaMA decoder hot path, each a thin shape/type shim over the
+// sm_100a kernels behind the C ABI of include/trtllm_b200.h.  Names, versions ("1"), namespace
+// ("tensorrt_llm"), field names, input order, output shapes/types and serialisation order follow the
+// reference plugin of the same name (cited per class) so an engine builder that looks these creators up
+// finds drop-in replacements.  Fields marked [ext] are additions (absent => reference behaviour).
+#include <cmath>
+
+#include "pluginBase.h"
+
+using namespace nvinfer1;
+
+namespace tb {
+namespace plugins {
+
+namespace {
+using FT = PluginFieldType;
+
+DimsExprs with_last_dim(const DimsExprs& in, const IDimensionExpr* last) {
+  DimsExprs r = in;
+  r.d[r.nbDims - 1] = last;
+  return r;
+}
+bool linear(const PluginTensorDesc& d, DataType t) { return d.type == t && d.format == TensorFormat::kLINEAR; }
+}  // namespace
+
+// =====================================================================================================
+// GPTAttention v1 — P/gptAttentionPlugin/gptAttentionPlugin.{h,cpp}, P/gptAttentionCommon/gptAttentionCommon.{h,cpp}
+// inputs  0 qkv [B,S,3*H*Dh]  1 past_key_value [B,2,H,S_max,Dh]  2 sequence_length [B]  3 past_key_value_length [2] (HOST:
+//         {past_len, is_context})  4 masked_tokens [B,S_max]  5 input_lengths [B]  6 max_input_length [max_in] (shape only)
+//         7 cache_indirection [B,beam,S_max]  (8 kv_orig_quant_scale [1], 9 kv_quant_orig_scale [1] iff int8 KV)
+// outputs 0 context [B,S,H*Dh]   1 present_key_value (same buffer as input 1: updated in place)
+// =====================================================================================================
+class GPTAttentionPlugin : public BasePlugin {
+ public:
+  static const char* type_name() { return "GPTAttention"; }
+  static const std::vector<PluginField>& field_table() {
+    static const std::vector<PluginField> t = {
+        field_decl("num_heads", FT::kINT32), field_decl("head_size", FT::kINT32), field_decl("unidirectional", FT::kINT32),
+        field_decl("q_scaling", FT::kFLOAT32), field_decl("rotary_embedding_dim", FT::kINT32),
+        field_decl("neox_rotary_style", FT::kINT8), field_decl("context_fmha_type", FT::kINT8),
+        field_decl("multi_block_mode", FT::kINT8), field_decl("multi_query_mode", FT::kINT8),
+        field_decl("int8_kv_cache", FT::kINT32), field_decl("fp8_kv_cache", FT::kINT32),
+        field_decl("remove_input_padding", FT::kINT8), field_decl("mask_type", FT::kINT32),
+        field_decl("paged_kv_cache", FT::kINT32), field_decl("type_id", FT::kINT32),
+        field_decl("in_flight_batching", FT::kINT32), field_decl("device_lengths", FT::kINT32) /*[ext]*/};
+    return t;
+  }
+  explicit GPTAttentionPlugin(Fields& f) {
+    num_heads_ = f.required<int32_t>("num_heads");
+    head_size_ = f.required<int32_t>("head_size");
+    unidirectional_ = f.optional<int32_t>("unidirectional", 1);
+    q_scaling_ = f.optional<float>("q_scaling", 1.f);
+    rotary_dim_ = f.optional<int32_t>("rotary_embedding_dim", 0);
+    neox_ = f.optional<int32_t>("neox_rotary_style", 1) != 0;
+    context_fmha_ = f.optional<int32_t>("context_fmha_type", 0);
+    multi_block_ = f.optional<int32_t>("multi_block_mode", 0) != 0;
+    multi_query_ = f.optional<int32_t>("multi_query_mode", 0) != 0;
+    int8_kv_ = f.optional<int32_t>("int8_kv_cache", 0) != 0;
+    fp8_kv_ = f.optional<int32_t>("fp8_kv_cache", 0) != 0;
+    remove_padding_ = f.optional<int32_t>("remove_input_padding", 0) != 0;
+    mask_type_ = f.optional<int32_t>("mask_type", 1 /*causal*/);
+    paged_kv_ = f.optional<int32_t>("paged_kv_cache", 0) != 0;
+    type_ = f.optional<int32_t>("type_id", (int32_t) DataType::kHALF);
+    ifb_ = f.optional<int32_t>("in_flight_batching", 0) != 0;
+    device_lengths_ = f.optional<int32_t>("device_lengths", 0) != 0;
+    validate();
+  }
+  explicit GPTAttentionPlugin(Reader& r) {
+    // same member order as the reference blob (P/gptAttentionCommon/gptAttentionCommon.cpp:862-890,
+    // P/gptAttentionPlugin/gptAttentionPlugin.cpp:443-455), then this library's extension word
+    num_heads_ = r.get<int32_t>(); head_size_ = r.get<int32_t>(); unidirectional_ = r.get<int32_t>();
+    q_scaling_ = r.get<float>(); rotary_dim_ = r.get<int32_t>(); neox_ = r.get<bool>();
+    context_fmha_ = r.get<bool>(); (void) r.get<bool>() /*fmha fp32 acc*/; multi_block_ = r.get<bool>();
+    multi_query_ = r.get<bool>(); int8_kv_ = r.get<bool>(); fp8_kv_ = r.get<bool>(); remove_padding_ = r.get<bool>();
+    mask_type_ = r.get<int32_t>(); paged_kv_ = r.get<bool>(); type_ = r.get<int32_t>(); ifb_ = r.get<bool>();
+    device_lengths_ = r.get<bool>();
+    validate();
+  }
+  size_t getSerializationSize() const noexcept override {
+    return 4 * sizeof(int32_t) + sizeof(float) + 8 * sizeof(bool) + sizeof(int32_t) + sizeof(bool) + sizeof(int32_t) +
+           2 * sizeof(bool);
+  }
+  void serialize(void* buf) const noexcept override {
+    Writer w{static_cast<char*>(buf)};
+    w.put(num_heads_); w.put(head_size_); w.put(unidirectional_); w.put(q_scaling_); w.put(rotary_dim_); w.put(neox_);
+    w.put((bool) (context_fmha_ != 0)); w.put((bool) (context_fmha_ == 2)); w.put(multi_block_); w.put(multi_query_);
+    w.put(int8_kv_); w.put(fp8_kv_); w.put(remove_padding_); w.put(mask_type_); w.put(paged_kv_); w.put(type_);
+    w.put(ifb_); w.put(device_lengths_);
+  }
+  GPTAttentionPlugin* clone() const noexcept override {
+    auto* p = new GPTAttentionPlugin(*this);
+    p->counters_ = DeviceCounters();   // a clone owns its own counters (the reference clone re-initialises too)
+    return p;
+  }
+  const char* getPluginType() const noexcept override { return type_name(); }
+  int32_t getNbOutputs() const noexcept override { return 2; }
+  DimsExprs getOutputDimensions(int32_t idx, const DimsExprs* in, int32_t, IExprBuilder& eb) noexcept override {
+    if (idx == 0) return with_last_dim(in[0], eb.constant(num_heads_ * head_size_));
+    return in[1];
+  }
+  DataType getOutputDataType(int32_t idx, const DataType* in, int32_t) const noexcept override {
+    return idx == 0 ? in[0] : in[1];
+  }
+  bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nb_in, int32_t) noexcept override {
+    if (pos >= 2 && pos <= 7) return linear(io[pos], DataType::kINT32);
+    if (int8_kv_ && (pos == 8 || pos == 9)) return linear(io[pos], DataType::kFLOAT);
+    if (int8_kv_ && (pos == 1 || pos == nb_in + 1)) return linear(io[pos], DataType::kINT8);
+    return linear(io[pos], (DataType) type_);
+  }
+  size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+    // generation: split-L partials.  context: the fused causal kernel needs no scratch (the reference
+    // sizes ~6.4 GB of score buffers here, gptAttentionCommon.cpp:267-305).
+    return align128(tb_mmha_workspace_bytes(in[0].dims.d[0], num_heads_, kMaxSplits));
+  }
+  int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out,
+                  void* workspace, cudaStream_t stream) noexcept override {
+    return guarded("GPTAttention::enqueue", [&]() -> int {
+      const int B = id[0].dims.d[0], S = id[0].dims.d[1];
+      const int S_max = id[1].dims.d[3];
+      const int max_in = id[6].dims.d[0];
+      const int* host_len = static_cast<const int*>(in[3]);          // HOST tensor {past_len, is_context}
+      TBP_REQUIRE(host_len != nullptr, "past_key_value_length must be a host tensor");
+      const int past_len = host_len[0];
+      const bool is_context = host_len[1] != 0;
+      const float* s_oq = int8_kv_ ? static_cast<const float*>(in[8]) : nullptr;
+      const float* s_qo = int8_kv_ ? static_cast<const float*>(in[9]) : nullptr;
+      void* cache = out[1] ? out[1] : const_cast<void*>(in[1]);      // in-place: runtime binds one buffer to both
+      if (is_context) {
+        return tb_context_attention(out[0], const_cast<void*>(in[0]), cache, static_cast<const int*>(in[5]), s_oq, B, S,
+                                    num_heads_, head_size_, S_max, rotary_dim_, q_scaling_, int8_kv_, stream);
+      }
+      TBP_REQUIRE(S == 1, "generation phase expects one token per sequence");
+      // device_lengths [ext]: the step position is read from sequence_length on the device so one
+      // captured CUDA graph serves every step; shared memory is then sized for S_max.
+      const int cap = device_lengths_ ? S_max - 1 : past_len;
+      const int nsplit = tb_mmha_num_splits(B, num_heads_, cap, kMaxSplits);
+      int* cnt = counters_.get(tb_mmha_counter_bytes(B, num_heads_));
+      return tb_mmha_decode(out[0], in[0], cache, static_cast<const int*>(in[2]), static_cast<const int*>(in[5]),
+                            static_cast<const int*>(in[4]), s_oq, s_qo, workspace, cnt, B, num_heads_, head_size_, S_max,
+                            device_lengths_ ? 0 : past_len, max_in, cap, rotary_dim_, q_scaling_, int8_kv_, nsplit,
+                            stream);
+    });
+  }
+
+ private:
+  static constexpr int kMaxSplits = 32;
+  void validate() const {
+    TBP_REQUIRE(head_size_ == 128, "only head_size 128 (LLaMA-7B) is built");
+    TBP_REQUIRE(rotary_dim_ == 0 || rotary_dim_ == head_size_, "rotary_embedding_dim must be 0 or head_size");
+    TBP_REQUIRE(rotary_dim_ == 0 || neox_, "only neox-style rotary embedding is built");
+    TBP_REQUIRE(is_half(type_), "only type_id = half is built");
+    TBP_REQUIRE(!multi_query_ && !fp8_kv_ && !paged_kv_ && !ifb_ && !remove_padding_,
+                "multi-query / fp8 KV / paged KV / in-flight batching / packed input are out of scope (SURVEY 8f)");
+    TBP_REQUIRE(unidirectional_ == 1, "causal attention only");
+  }
+  int32_t num_heads_ = 0, head_size_ = 0, unidirectional_ = 1, rotary_dim_ = 0, context_fmha_ = 0, mask_type_ = 1;
+  int32_t type_ = (int32_t) DataType::kHALF;
+  float q_scaling_ = 1.f;
+  bool neox_ = true, multi_block_ = false, multi_query_ = false, int8_kv_ = false, fp8_kv_ = false;
+  bool remove_padding_ = false, paged_kv_ = false, ifb_ = false, device_lengths_ = false;
+  DeviceCounters counters_;
+};
+
+// =====================================================================================================
+// SmoothQuantGemm v1 — P/smoothQuantGemmPlugin/smoothQuantGemmPlugin.{h,cpp}
+// inputs 0 act int8 [..,K]  1 weight int8 [N,K] (declared fp32 [N,K/4])  2 scale_tokens fp32 [M,1]|[1,1]
+//        3 scale_channels fp32 [1,N]|[1,1]  (4 residual fp16 [..,N] iff fused_residual [ext])
+// output [..,N] type_id in {half, float, int32}
+// =====================================================================================================
+class SmoothQuantGemmPlugin : public BasePlugin {
+ public:
+  static const char* type_name() { return "SmoothQuantGemm"; }
+  static const std::vector<PluginField>& field_table() {
+    static const std::vector<PluginField> t = {field_decl("has_per_channel_scaling", FT::kINT32),
+                                               field_decl("has_per_token_scaling", FT::kINT32),
+                                               field_decl("type_id", FT::kINT32), field_decl("fused_swiglu", FT::kINT32),
+                                               field_decl("fused_residual", FT::kINT32)};
+    return t;
+  }
+  explicit SmoothQuantGemmPlugin(Fields& f) {
+    per_channel_ = f.optional<int32_t>("has_per_channel_scaling", 0) != 0;
+    per_token_ = f.optional<int32_t>("has_per_token_scaling", 0) != 0;
+    type_ = f.required<int32_t>("type_id");
+    swiglu_ = f.optional<int32_t>("fused_swiglu", 0) != 0;
+    residual_ = f.optional<int32_t>("fused_residual", 0) != 0;
+    validate();
+  }
+  explicit SmoothQuantGemmPlugin(Reader& r) {
+    // reference order perChannel, perToken, type (smoothQuantGemmPlugin.cpp:253-282); the reference's
+    // CUTLASS tactic table that follows is replaced by this library's two extension flags
+    per_channel_ = r.get<bool>(); per_token_ = r.get<bool>(); type_ = r.get<int32_t>();
+    swiglu_ = r.get<bool>(); residual_ = r.get<bool>();
+    validate();
+  }
+  size_t getSerializationSize() const noexcept override { return 4 * sizeof(bool) + sizeof(int32_t); }
+  void serialize(void* buf) const noexcept override {
+    Writer w{static_cast<char*>(buf)};
+    w.put(per_channel_); w.put(per_token_); w.put(type_); w.put(swiglu_); w.put(residual_);
+  }
+  SmoothQuantGemmPlugin* clone() const noexcept override {
+    auto* p = new SmoothQuantGemmPlugin(*this);
+    p->counters_ = DeviceCounters();
+    return p;
+  }
+  const char* getPluginType() const noexcept override { return type_name(); }
+  int32_t getNbOutputs() const noexcept override { return 1; }
+  DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& eb) noexcept override {
+    const IDimensionExpr* n = in[1].d[0];
+    if (swiglu_) n = eb.operation(DimensionOperation::kFLOOR_DIV, *n, *eb.constant(2));
+    return with_last_dim(in[0], n);
+  }
+  DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return (DataType) type_; }
+  bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nb_in, int32_t) noexcept override {
+    if (pos == 0) return linear(io[pos], DataType::kINT8);
+    if (pos == 1) return io[pos].format == TensorFormat::kLINEAR && (io[pos].type == DataType::kINT8 || io[pos].type == DataType::kFLOAT);
+    if (pos == 2 || pos == 3) return linear(io[pos], DataType::kFLOAT);
+    if (residual_ && pos == 4) return linear(io[pos], DataType::kHALF);
+    (void) nb_in;
+    return linear(io[pos], (DataType) type_);
+  }
+  size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+    return align128(tb_gemm_tc_workspace_bytes((int) rows_of(in[0].dims), in[1].dims.d[0], last_dim(in[0].dims)));
+  }
+  int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc* od, const void* const* in, void* const* out,
+                  void* workspace, cudaStream_t stream) noexcept override {
+    return guarded("SmoothQuantGemm::enqueue", [&]() -> int {
+      const int M = (int) rows_of(id[0].dims), N = id[1].dims.d[0], K = last_dim(id[0].dims);
+      const void* res = residual_ ? in[4] : nullptr;
+      const float* st = static_cast<const float*>(in[2]);
+      const float* sc = static_cast<const float*>(in[3]);
+      if (M <= 4 && is_half(type_))
+        return tb_gemv(3, out[0], nullptr, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K, swiglu_,
+                       stream);
+      TBP_REQUIRE(!swiglu_, "fused_swiglu is only available on the decode (M <= 4) path");
+      const int ot = is_half(type_) ? 0 : (type_ == (int32_t) DataType::kFLOAT ? 1 : 2);
+      (void) od;
+      return tb_gemm_tc(3, out[0], ot, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K, workspace,
+                        tb_gemm_tc_workspace_bytes(M, N, K), counters_.get(tb_gemm_tc_counter_bytes()), 0, 0, stream);
+    });
+  }
+
+ private:
+  void validate() const {
+    TBP_REQUIRE(is_half(type_) || type_ == (int32_t) DataType::kFLOAT || type_ == (int32_t) DataType::kINT32,
+                "type_id must be half, float or int32");
+    TBP_REQUIRE(!(swiglu_ || residual_) || is_half(type_), "fused epilogues need a half output");
+  }
+  bool per_channel_ = false, per_token_ = false, swiglu_ = false, residual_ = false;
+  int32_t type_ = (int32_t) DataType::kHALF;
+  DeviceCounters counters_;
+};
+
+// =====================================================================================================
+// WeightOnlyQuantMatmul v1 — P/weightOnlyQuantMatmulPlugin/weightOnlyQuantMatmulPlugin.{h,cpp}
+// inputs 0 act fp16 [..,K]  1 weight (declared fp32 [K, N/4] int8 | [K, N/8] int4; bytes hold this library's
+//        processed layout [N,K] int8 / [N,K/2] packed int4, see tb_preprocess_weights)  2 scales fp16 [N]
+//        (3 residual fp16 iff fused_residual [ext])
+// =====================================================================================================
+class WeightOnlyQuantMatmulPlugin : public BasePlugin {
+ public:
+  static const char* type_name() { return "WeightOnlyQuantMatmul"; }
+  static const std::vector<PluginField>& field_table() {
+    static const std::vector<PluginField> t = {field_decl("type_id", FT::kINT32), field_decl("weight_type_id", FT::kINT32),
+                                               field_decl("fused_swiglu", FT::kINT32),
+                                               field_decl("fused_residual", FT::kINT32)};
+    return t;
+  }
+  explicit WeightOnlyQuantMatmulPlugin(Fields& f) {
+    type_ = f.required<int32_t>("type_id");
+    weight_type_ = f.required<int32_t>("weight_type_id");
+    swiglu_ = f.optional<int32_t>("fused_swiglu", 0) != 0;
+    residual_ = f.optional<int32_t>("fused_residual", 0) != 0;
+    validate();
+  }
+  explicit WeightOnlyQuantMatmulPlugin(Reader& r) {
+    type_ = r.get<int32_t>(); weight_type_ = r.get<int32_t>();   // weightOnlyQuantMatmulPlugin.cpp:256-267
+    swiglu_ = r.get<bool>(); residual_ = r.get<bool>();
+    validate();
+  }
+  size_t getSerializationSize() const noexcept override { return 2 * sizeof(int32_t) + 2 * sizeof(bool); }
+  void serialize(void* buf) const noexcept override {
+    Writer w{static_cast<char*>(buf)};
+    w.put(type_); w.put(weight_type_); w.put(swiglu_); w.put(residual_);
+  }
+  WeightOnlyQuantMatmulPlugin* clone() const noexcept override {
+    auto* p = new WeightOnlyQuantMatmulPlugin(*this);
+    p->counters_ = DeviceCounters();
+    return p;
+  }
+  const char* getPluginType() const noexcept override { return type_name(); }
+  int32_t getNbOutputs() const noexcept override { return 1; }
+  int pack() const { return weight_type_ == 1 ? 4 : 8; }   // output channels per declared fp32 element
+  DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& eb) noexcept override {
+    const IDimensionExpr* n = eb.operation(DimensionOperation::kPROD, *in[1].d[1], *eb.constant(pack()));
+    if (swiglu_) n = eb.operation(DimensionOperation::kFLOOR_DIV, *n, *eb.constant(2));
+    return with_last_dim(in[0], n);
+  }
+  DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return (DataType) type_; }
+  bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t, int32_t) noexcept override {
+    if (pos == 1) return linear(io[pos], DataType::kFLOAT);
+    return linear(io[pos], (DataType) type_);
+  }
+  size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+    return align128(tb_gemm_tc_workspace_bytes((int) rows_of(in[0].dims), in[1].dims.d[1] * pack(), last_dim(in[0].dims)));
+  }
+  int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out,
+                  void* workspace, cudaStream_t stream) noexcept override {
+    return guarded("WeightOnlyQuantMatmul::enqueue", [&]() -> int {
+      const int M = (int) rows_of(id[0].dims), N = id[1].dims.d[1] * pack(), K = last_dim(id[0].dims);
+      TBP_REQUIRE(id[1].dims.d[0] == K, "weight rows must equal the activation's last dim");
+      const int kind = weight_type_ == 1 ? 1 : 2;
+      const void* res = residual_ ? in[3] : nullptr;
+      if (M <= 4) return tb_gemv(kind, out[0], nullptr, in[0], in[1], in[2], nullptr, nullptr, 0, 0, res, M, N, K, swiglu_, stream);
+      TBP_REQUIRE(!swiglu_, "fused_swiglu is only available on the decode (M <= 4) path");
+      return tb_gemm_tc(kind, out[0], 0, in[0], in[1], in[2], nullptr, nullptr, 0, 0, res, M, N, K, workspace,
+                        tb_gemm_tc_workspace_bytes(M, N, K), counters_.get(tb_gemm_tc_counter_bytes()), 0, 0, stream);
+    });
+  }
+
+ private:
+  void validate() const {
+    TBP_REQUIRE(is_half(type_), "only type_id = half is supported (as in the reference, weightOnlyQuantMatmulPlugin.cpp:47-63)");
+    TBP_REQUIRE(weight_type_ == 1 || weight_type_ == 2, "weight_type_id must be 1 (int8) or 2 (int4)");
+  }
+  int32_t type_ = (int32_t) DataType::kHALF, weight_type_ = 1;
+  bool swiglu_ = false, residual_ = false;
+  DeviceCounters counters_;
+};
+
+// =====================================================================================================
+// Gemm v1 — P/gemmPlugin/gemmPlugin.{h,cpp}: fp16 C = A . B^T, the only form the LLaMA graph uses
+// (T/tensorrt_llm/layers/linear.py:13-35: transa = 0, transb = 1).  inputs 0 A [..,K]  1 B [N,K]
+// (2 residual iff fused_residual [ext]).  out_fp32 [ext]: fp32 logits for lm_head.
+// =====================================================================================================
+class GemmPlugin : public BasePlugin {
+ public:
+  static const char* type_name() { return "Gemm"; }
+  static const std::vector<PluginField>& field_table() {
+    static const std::vector<PluginField> t = {field_decl("transa", FT::kINT32), field_decl("transb", FT::kINT32),
+                                               field_decl("type_id", FT::kINT32), field_decl("fused_swiglu", FT::kINT32),
+                                               field_decl("fused_residual", FT::kINT32), field_decl("out_fp32", FT::kINT32)};
+    return t;
+  }
+  explicit GemmPlugin(Fields& f) {
+    transa_ = f.optional<int32_t>("transa", 0);
+    transb_ = f.optional<int32_t>("transb", 1);
+    type_ = f.required<int32_t>("type_id");
+    swiglu_ = f.optional<int32_t>("fused_swiglu", 0) != 0;
+    residual_ = f.optional<int32_t>("fused_residual", 0) != 0;
+    out_fp32_ = f.optional<int32_t>("out_fp32", 0) != 0;
+    validate();
+  }
+  explicit GemmPlugin(Reader& r) {
+    transa_ = r.get<int32_t>(); transb_ = r.get<int32_t>(); type_ = r.get<int32_t>();
+    swiglu_ = r.get<bool>(); residual_ = r.get<bool>(); out_fp32_ = r.get<bool>();
+    validate();
+  }
+  size_t getSerializationSize() const noexcept override { return 3 * sizeof(int32_t) + 3 * sizeof(bool); }
+  void serialize(void* buf) const noexcept override {
+    Writer w{static_cast<char*>(buf)};
+    w.put(transa_); w.put(transb_); w.put(type_); w.put(swiglu_); w.put(residual_); w.put(out_fp32_);
+  }
+  GemmPlugin* clone() const noexcept override {
+    auto* p = new GemmPlugin(*this);
+    p->counters_ = DeviceCounters();
+    return p;
+  }
+  const char* getPluginType() const noexcept override { return type_name(); }
+  int32_t getNbOutputs() const noexcept override { return 1; }
+  DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& eb) noexcept override {
+    const IDimensionExpr* n = in[1].d[0];
+    if (swiglu_) n = eb.operation(DimensionOperation::kFLOOR_DIV, *n, *eb.constant(2));
+    return with_last_dim(in[0], n);
+  }
+  DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override {
+    return out_fp32_ ? DataType::kFLOAT : (DataType) type_;
+  }
+  bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nb_in, int32_t) noexcept override {
+    if (pos == nb_in && out_fp32_) return linear(io[pos], DataType::kFLOAT);
+    return linear(io[pos], (DataType) type_);
+  }
+  size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
+    return align128(tb_gemm_tc_workspace_bytes((int) rows_of(in[0].dims), in[1].dims.d[0], last_dim(in[0].dims)));
+  }
+  int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out,
+                  void* workspace, cudaStream_t stream) noexcept override {
+    return guarded("Gemm::enqueue", [&]() -> int {
+      const int M = (int) rows_of(id[0].dims), N = id[1].dims.d[0], K = last_dim(id[0].dims);
+      TBP_REQUIRE(id[1].dims.d[1] == K, "B must be [N, K]");
+      const void* res = residual_ ? in[2] : nullptr;
+      if (M <= 4)
+        return tb_gemv(0, out_fp32_ ? nullptr : out[0], out_fp32_ ? static_cast<float*>(out[0]) : nullptr, in[0], in[1],
+                       nullptr, nullptr, nullptr, 0, 0, res, M, N, K, swiglu_, stream);
+      TBP_REQUIRE(!swiglu_, "fused_swiglu is only available on the decode (M <= 4) path");
+      return tb_gemm_tc(0, out[0], out_fp32_ ? 1 : 0, in[0], in[1], nullptr, nullptr, nullptr, 0, 0, res, M, N, K,
+                        workspace, tb_gemm_tc_workspace_bytes(M, N, K), counters_.get(tb_gemm_tc_counter_bytes()), 0, 0,
+                        stream);
+    });
+  }
+
+ private:
+  void validate() const {
+    TBP_REQUIRE(is_half(type_), "only type_id = half is built");
+    TBP_REQUIRE(transa_ == 0 && transb_ == 1, "only C = A . B^T (transa=0, transb=1) is built");
+    TBP_REQUIRE(!(out_fp32_ && (residual_ || swiglu_)), "out_fp32 excludes the fused epilogues");
+  }
+  int32_t transa_ = 0, transb_ = 1, type_ = (int32_t) DataType::kHALF;
+  bool swiglu_ = false, residual_ = false, out_fp32_ = false;
+  DeviceCounters counters_;
+};
+
+// =====================================================================================================
+// RmsnormQuantization v1 (new) and LayernormQuantization v1 (the reference's,
+// P/layernormQuantizationPlugin/layernormQuantizationPlugin.{h,cpp}) share one implementation.
+// inputs 0 x [..,H]  1 weight [H]  2 bias [H]  3 scale_to_int fp32 [1]   (4 residual iff fused_residual [ext])
+// outputs 0 int8 [..,H]  (1 fp32 [..,1] iff dyn_act_scaling)  (+ fp16 [..,H] = x + residual iff fused_residual)
+// Field semantics follow the header (eps, use_diff_of_squares, dyn_act_scaling, type_id); the reference's
+// definition crosses the two flags — not reproduced.
+// =====================================================================================================
+template <bool RMS>
+class NormQuantizationPlugin : public BasePlugin {
+ public:
+  static const char* type_name() { return RMS ? "RmsnormQuantization" : "LayernormQuantization"; }
+  static const std::vector<PluginField>& field_table() {
+    static const std::vector<PluginField> t = {field_decl("eps", FT::kFLOAT32), field_decl("use_diff_of_squares", FT::kINT32),
+                                               field_decl("dyn_act_scaling", FT::kINT32), field_decl("type_id", FT::kINT32),
+                                               field_decl("fused_residual", FT::kINT32)};
+    return t;
+  }
+  explicit NormQuantizationPlugin(Fields& f) {
+    eps_ = f.optional<float>("eps", RMS ? 1e-6f : 1e-5f);
+    diff_of_squares_ = f.optional<int32_t>("use_diff_of_squares", 0) != 0;
+    dynamic_ = f.optional<int32_t>("dyn_act_scaling", 0) != 0;
+    type_ = f.required<int32_t>("type_id");
+    residual_ = f.optional<int32_t>("fused_residual", 0) != 0;
+    TBP_REQUIRE(is_half(type_), "only type_id = half is built");
+  }
+  explicit NormQuantizationPlugin(Reader& r) {
+    eps_ = r.get<float>(); diff_of_squares_ = r.get<bool>(); dynamic_ = r.get<bool>(); type_ = r.get<int32_t>();
+    residual_ = r.get<bool>();   // layernormQuantizationPlugin.cpp:206-219 order + extension
+    TBP_REQUIRE(is_half(type_), "only type_id = half is built");
+  }
+  size_t getSerializationSize() const noexcept override { return sizeof(float) + 3 * sizeof(bool) + sizeof(int32_t); }
+  void serialize(void* buf) const noexcept override {
+    Writer w{static_cast<char*>(buf)};
+    w.put(eps_); w.put(diff_of_squares_); w.put(dynamic_); w.put(type_); w.put(residual_);
+  }
+  NormQuantizationPlugin* clone() const noexcept override { return new NormQuantizationPlugin(*this); }
+  const char* getPluginType() const noexcept override { return type_name(); }
+  int32_t getNbOutputs() const noexcept override { return 1 + (dynamic_ ? 1 : 0) + (residual_ ? 1 : 0); }
+  DimsExprs getOutputDimensions(int32_t idx, const DimsExprs* in, int32_t, IExprBuilder& eb) noexcept override {
+    if (dynamic_ && idx == 1) return with_last_dim(in[0], eb.constant(1));
+    return in[0];
+  }
+  DataType getOutputDataType(int32_t idx, const DataType* in, int32_t) const noexcept override {
+    if (idx == 0) return DataType::kINT8;
+    if (dynamic_ && idx == 1) return DataType::kFLOAT;
+    return in[0];
+  }
+  bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nb_in, int32_t) noexcept override {
+    if (pos == 3) return linear(io[pos], DataType::kFLOAT);
+    if (pos == nb_in) return linear(io[pos], DataType::kINT8);
+    if (dynamic_ && pos == nb_in + 1) return linear(io[pos], DataType::kFLOAT);
+    return linear(io[pos], (DataType) type_);
+  }
+  int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out, void*,
+                  cudaStream_t stream) noexcept override {
+    return guarded(type_name(), [&]() -> int {
+      const int rows = (int) rows_of(id[0].dims), hidden = last_dim(id[0].dims);
+      float* dyn = dynamic_ ? static_cast<float*>(out[1]) : nullptr;
+      void* sum = residual_ ? out[1 + (dynamic_ ? 1 : 0)] : nullptr;
+      return tb_rmsnorm_quant(static_cast<int8_t*>(out[0]), dyn, in[0], residual_ ? in[4] : nullptr, sum, in[1], in[2],
+                              static_cast<const float*>(in[3]), eps_, rows, hidden, dynamic_, RMS ? 0 : 1, stream);
+    });
+  }
+
+ private:
+  float eps_ = 1e-6f;
+  bool diff_of_squares_ = false, dynamic_ = false, residual_ = false;
+  int32_t type_ = (int32_t) DataType::kHALF;
+};
+
+// =====================================================================================================
+// QuantizePerToken v1 / QuantizeTensor v1 — P/quantizePerTokenPlugin, P/quantizeTensorPlugin (no fields)
+// =====================================================================================================
+class QuantizePerTokenPlugin : public BasePlugin {
+ public:
+  static const char* type_name() { return "QuantizePerToken"; }
+  static const std::vector<PluginField>& field_table() { static const std::vector<PluginField> t; return t; }
+  explicit QuantizePerTokenPlugin(Fields&) {}
+  explicit QuantizePerTokenPlugin(Reader&) {}
+  size_t getSerializationSize() const noexcept override { return 0; }
+  void serialize(void*) const noexcept override {}
+  QuantizePerTokenPlugin* clone() const noexcept override { return new QuantizePerTokenPlugin(*this); }
+  const char* getPluginType() const noexcept override { return type_name(); }
+  int32_t getNbOutputs() const noexcept override { return 2; }
+  DimsExprs getOutputDimensions(int32_t idx, const DimsExprs* in, int32_t, IExprBuilder& eb) noexcept override {
+    return idx == 0 ? in[0] : with_last_dim(in[0], eb.constant(1));
+  }
+  DataType getOutputDataType(int32_t idx, const DataType*, int32_t) const noexcept override {
+    return idx == 0 ? DataType::kINT8 : DataType::kFLOAT;
+  }
+  bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t, int32_t) noexcept override {
+    if (pos == 0) return io[0].format == TensorFormat::kLINEAR && (io[0].type == DataType::kHALF || io[0].type == DataType::kFLOAT);
+    return linear(io[pos], pos == 1 ? DataType::kINT8 : DataType::kFLOAT);
+  }
+  int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out, void*,
+                  cudaStream_t stream) noexcept override {
+    return guarded(type_name(), [&]() -> int {
+      return tb_quantize_per_token(static_cast<int8_t*>(out[0]), static_cast<float*>(out[1]), in[0],
+                                   (int) rows_of(id[0].dims), last_dim(id[0].dims), id[0].type == DataType::kFLOAT, stream);
+    });
+  }
+};
+
+class QuantizeTensorPlugin : public BasePlugin {
+ public:
+  static const char* type_name() { return "QuantizeTensor"; }
+  static const std::vector<PluginField>& field_table() { static const std::vector<PluginField> t; return t; }
+  explicit QuantizeTensorPlugin(Fields&) {}
+  explicit QuantizeTensorPlugin(Reader&) {}
+  size_t getSerializationSize() const noexcept override { return 0; }
+  void serialize(void*) const noexcept override {}
+  QuantizeTensorPlugin* clone() const noexcept override { return new QuantizeTensorPlugin(*this); }
+  const char* getPluginType() const noexcept override { return type_name(); }
+  int32_t getNbOutputs() const noexcept override { return 1; }
+  DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder&) noexcept override { return in[0]; }
+  DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return DataType::kINT8; }
+  bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t, int32_t) noexcept override {
+    if (pos == 0) return io[0].format == TensorFormat::kLINEAR && (io[0].type == DataType::kHALF || io[0].type == DataType::kFLOAT);
+    return linear(io[pos], pos == 1 ? DataType::kFLOAT : DataType::kINT8);
+  }
+  int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out, void*,
+                  cudaStream_t stream) noexcept override {
+    return guarded(type_name(), [&]() -> int {
+      return tb_quantize_tensor(static_cast<int8_t*>(out[0]), in[0], volume(id[0].dims), static_cast<const float*>(in[1]),
+                                id[0].type == DataType::kFLOAT, stream);
+    });
+  }
+};
+
+// =====================================================================================================
+// AllReduce v1 / AllGather v1 — P/ncclPlugin/allreducePlugin.{h,cpp}, allgatherPlugin.{h,cpp}
+// fields group:i32[n], type_id:i32.  The communicator for `group` must have been registered with
+// tb_comm_init (the reference bootstraps over MPI, allreducePlugin.cpp:128-167; there is no MPI here).
+// Both are no-ops while IS_BUILDING=1 (P/common/plugin.h:145-157).
+// AllReduce [ext] fused_residual: inputs (x, residual) -> out = allreduce(x) + residual.
+// =====================================================================================================
+template <bool GATHER>
+class NcclPlugin : public BasePlugin {
+ public:
+  static const char* type_name() { return GATHER ? "AllGather" : "AllReduce"; }
+  static const std::vector<PluginField>& field_table() {
+    static const std::vector<PluginField> t = {PluginField("group", nullptr, FT::kINT32, 1), field_decl("type_id", FT::kINT32)};
+    return t;
+  }
+  explicit NcclPlugin(Fields& f) {
+    group_ = f.int_list("group");
+    type_ = f.required<int32_t>("type_id");
+    TBP_REQUIRE(!group_.empty(), "group must list at least one rank");
+    TBP_REQUIRE(is_half(type_), "only type_id = half is built");
+  }
+  explicit NcclPlugin(Reader& r) {
+    type_ = r.get<int32_t>();                                   // allreducePlugin.cpp:170-183: type, then the group
+    while (r.p < r.end) group_.push_back(r.get<int32_t>());
+    TBP_REQUIRE(!group_.empty() && is_half(type_), "bad serialised NCCL plugin");
+  }
+  size_t getSerializationSize() const noexcept override { return sizeof(int32_t) * (1 + group_.size()); }
+  void serialize(void* buf) const noexcept override {
+    Writer w{static_cast<char*>(buf)};
+    w.put(type_);
+    for (int32_t g : group_) w.put(g);
+  }
+  NcclPlugin* clone() const noexcept override { return new NcclPlugin(*this); }
+  const char* getPluginType() const noexcept override { return type_name(); }
+  int32_t getNbOutputs() const noexcept override { return 1; }
+  DimsExprs getOutputDimensions(int32_t, const DimsExprs* in, int32_t, IExprBuilder& eb) noexcept override {
+    DimsExprs r = in[0];
+    if (GATHER) r.d[0] = eb.operation(DimensionOperation::kPROD, *in[0].d[0], *eb.constant((int32_t) group_.size()));
+    return r;
+  }
+  DataType getOutputDataType(int32_t, const DataType* in, int32_t) const noexcept override { return in[0]; }
+  bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t, int32_t) noexcept override {
+    return linear(io[pos], (DataType) type_);
+  }
+  int32_t initialize() noexcept override {
+    const char* building = std::getenv("IS_BUILDING");
+    if (building && building[0] == '1') return 0;
+    comm_ = find_comm(group_);
+    if (!comm_) {
+      log_msg(ILogger::Severity::kERROR, "%s: no communicator registered for this group (call tb_comm_init first)", type_name());
+      return -1;
+    }
+    return 0;
+  }
+  int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out, void*,
+                  cudaStream_t stream) noexcept override {
+    return guarded(type_name(), [&]() -> int {
+      const char* building = std::getenv("IS_BUILDING");
+      if (building && building[0] == '1') return 0;
+      if (!comm_) comm_ = find_comm(group_);
+      TBP_REQUIRE(comm_ != nullptr, "communicator not initialised");
+      const size_t n = (size_t) volume(id[0].dims);
+      return GATHER ? comm_allgather_half(comm_, in[0], out[0], n, stream) : comm_allreduce_half(comm_, in[0], out[0], n, stream);
+    });
+  }
+
+ private:
+  std::vector<int32_t> group_;
+  int32_t type_ = (int32_t) DataType::kHALF;
+  CommHandle* comm_ = nullptr;
+};
+
+// ---- creator instances (registered by initLibNvInferPlugins, registry.cpp) ------------------------------------
+std::vector<IPluginCreator*>& all_creators() {
+  static Creator<GPTAttentionPlugin> c0;
+  static Creator<SmoothQuantGemmPlugin> c1;
+  static Creator<WeightOnlyQuantMatmulPlugin> c2;
+  static Creator<NormQuantizationPlugin<true>> c3;
+  static Creator<NormQuantizationPlugin<false>> c4;
+  static Creator<QuantizePerTokenPlugin> c5;
+  static Creator<QuantizeTensorPlugin> c6;
+  static Creator<NcclPlugin<false>> c7;
+  static Creator<NcclPlugin<true>> c8;
+  static Creator<GemmPlugin> c9;
+  static std::vector<IPluginCreator*> v = {&c0, &c1, &c2, &c3, &c4, &c5, &c6, &c7, &c8, &c9};
+  return v;
+}
+
+}  // namespace plugins
+}  // namespace tb

@@ -1,0 +1,609 @@
+// The C++ runtime that stands where TensorRT stands in the reference: it owns no math.  It looks plugin
+// creators up in the registry by (name, "1", "tensorrt_llm"), creates the operators from
+// PluginFieldCollections exactly as T/tensorrt_llm/functional.py:2828-2928 and
+// T/tensorrt_llm/quantization/functional.py:12-212 do, and per step calls
+// IPluginV2DynamicExt::enqueue(inputDesc, outputDesc, inputs, outputs, workspace, stream) in the order
+// of LQ/llama_model.py:78-119,159-287.  Glue ops that TensorRT generates natively in the reference
+//  are either fused into a plugin epilogue ([ext] fields) or one small kernel each.
+//
+// Device-resident step state (token ids, sequence lengths, output position) lets one captured CUDA
+// graph serve every decode step; the reference's loop rebuilds host shape buffers and calls .item()
+// every token (T/tensorrt_llm/runtime/generation.py:852-963).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/trtllm_b200_runtime.h"
+#include "../plugins/pluginBase.h"
+
+using namespace nvinfer1;
+using tb::plugins::kNamespace;
+using tb::plugins::kVersion;
+
+extern "C" bool initLibNvInferPlugins(void* logger, const char* libNamespace);
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return -1; }
+
+#define RT_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+#define RT_CALL(expr)                                                         \
+  do {                                                                        \
+    const int rc_ = (expr);                                                   \
+    if (rc_ != 0) return fail(std::string(#expr) + " failed with code " + std::to_string(rc_)); \
+  } while (0)
+
+struct Tensor { const void* ptr = nullptr; size_t bytes = 0; };
+
+PluginTensorDesc desc(std::initializer_list<int> dims, DataType t) {
+  PluginTensorDesc d{};
+  d.dims.nbDims = (int32_t) dims.size();
+  int i = 0;
+  for (int v : dims) d.dims.d[i++] = v;
+  d.type = t;
+  d.format = TensorFormat::kLINEAR;
+  d.scale = 1.f;
+  return d;
+}
+
+struct PluginDeleter { void operator()(IPluginV2DynamicExt* p) const { if (p) p->destroy(); } };
+using PluginPtr = std::unique_ptr<IPluginV2DynamicExt, PluginDeleter>;
+
+struct FieldList {
+  std::vector<PluginField> f;
+  std::vector<std::unique_ptr<char[]>> store;
+  template <class T> void add(const char* name, PluginFieldType t, T v) {
+    store.emplace_back(new char[sizeof(T)]);
+    std::memcpy(store.back().get(), &v, sizeof(T));
+    f.emplace_back(name, store.back().get(), t, 1);
+  }
+  void add_list(const char* name, const std::vector<int32_t>& v) {
+    store.emplace_back(new char[sizeof(int32_t) * v.size()]);
+    std::memcpy(store.back().get(), v.data(), sizeof(int32_t) * v.size());
+    f.emplace_back(name, store.back().get(), PluginFieldType::kINT32, (int32_t) v.size());
+  }
+};
+
+PluginPtr make_plugin(const char* name, FieldList& fl) {
+  IPluginCreator* c = getPluginRegistry()->getPluginCreator(name, kVersion, kNamespace);
+  if (!c) { g_err = std::string("plugin creator not registered: ") + name; return nullptr; }
+  PluginFieldCollection fc{(int32_t) fl.f.size(), fl.f.data()};
+  auto* p = static_cast<IPluginV2DynamicExt*>(c->createPlugin(name, &fc));
+  if (!p) { g_err = std::string("createPlugin failed: ") + name; return nullptr; }
+  if (p->initialize() != 0) { p->destroy(); g_err = std::string("plugin initialize failed: ") + name; return nullptr; }
+  return PluginPtr(p);
+}
+
+struct LinearW { const void* w = nullptr; const void* scale = nullptr; int N = 0, K = 0; };
+struct LayerW {
+  const void *ln_in = nullptr, *ln_post = nullptr;
+  LinearW qkv, dense, fc_gate, proj;
+  const float *kv_oq = nullptr, *kv_qo = nullptr;
+};
+
+}  // namespace
+
+struct tbrt_engine {
+  tbrt_config c{};
+  std::map<std::string, Tensor> tensors;
+  std::vector<LayerW> L;
+  const void *emb = nullptr, *ln_f = nullptr, *lm_head = nullptr;
+  int Hl = 0, hid_l = 0, inter_l = 0, vocab_l = 0, S_max = 0;
+  bool finalized = false;
+
+  // plugins (one instance per distinct configuration, shared by all layers)
+  PluginPtr lin, lin_res, lin_swiglu, lm, attn, normq, qpt, allreduce, allgather;
+
+  // device memory
+  std::vector<void*> allocs;
+  size_t dev_bytes = 0;
+  __half *h = nullptr, *h2 = nullptr, *x = nullptr, *qkv = nullptr, *att = nullptr, *gu = nullptr, *act = nullptr,
+         *o = nullptr, *hl = nullptr;
+  int8_t* xq = nullptr;
+  float *xs = nullptr, *logits = nullptr;
+  __half* logits_h = nullptr;
+  std::vector<void*> kv;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+  int *d_ids = nullptr, *d_in_lens = nullptr, *d_seq_lens = nullptr, *d_step_pos = nullptr, *d_next = nullptr,
+      *d_out_ids = nullptr, *d_prompt = nullptr;
+  float* d_dummy_scale = nullptr;
+
+  // session state
+  int B = 0, S_in = 0, steps_done = 0;
+  int64_t launches = 0;
+  std::map<int, cudaGraphExec_t> graphs;
+  std::map<int, int64_t> graph_nodes;
+  std::map<int, int> eager_steps;
+  cudaStream_t cap_stream = nullptr;
+
+  template <class T> int alloc(T*& p, size_t bytes) {
+    void* q = nullptr;
+    RT_CUDA(cudaMalloc(&q, bytes ? bytes : 16));
+    allocs.push_back(q);
+    dev_bytes += bytes;
+    p = static_cast<T*>(q);
+    return 0;
+  }
+  ~tbrt_engine() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    for (void* p : allocs) cudaFree(p);
+  }
+
+  int bind();
+  int build_plugins();
+  int linear(IPluginV2DynamicExt* p, const LinearW& w, const void* in, const float* in_scales, void* out,
+             const void* residual, int M, DataType out_t, cudaStream_t s);
+  int layers_forward(int M, int S, bool context, cudaStream_t s);
+  int head(int rows, cudaStream_t s);
+  int step_body(cudaStream_t s);
+};
+
+// ---------------------------------------------------------------------------------------------------------
+int tbrt_engine::bind() {
+  auto get = [&](const std::string& n, size_t want, const void*& out) -> int {
+    auto it = tensors.find(n);
+    if (it == tensors.end()) return fail("tensor not bound: " + n);
+    if (want && it->second.bytes != want)
+      return fail("tensor " + n + " has " + std::to_string(it->second.bytes) + " bytes, expected " + std::to_string(want));
+    out = it->second.ptr;
+    return 0;
+  };
+  const int hid = c.hidden, tp = c.tp_size;
+  Hl = c.heads / tp; hid_l = Hl * c.head_size; inter_l = c.inter / tp; vocab_l = c.vocab / tp;
+  S_max = c.max_input_len + c.max_output_len;
+  if (c.heads % tp || c.inter % tp || c.vocab % tp) return fail("heads, inter and vocab must divide by tp_size");
+  if (c.hidden != c.heads * c.head_size) return fail("hidden must equal heads * head_size");
+  auto wbytes = [&](int N, int K) -> size_t {
+    switch (c.mode) {
+      case TBRT_MODE_FP16: return (size_t) N * K * 2;
+      case TBRT_MODE_W4: return (size_t) N * K / 2;
+      default: return (size_t) N * K;
+    }
+  };
+  auto bind_linear = [&](const std::string& base, int N, int K, LinearW& w) -> int {
+    w.N = N; w.K = K;
+    if (get(base + ".weight", wbytes(N, K), w.w)) return -1;
+    if (c.mode == TBRT_MODE_W8 || c.mode == TBRT_MODE_W4) return get(base + ".per_channel_scale", (size_t) N * 2, w.scale);
+    if (c.mode == TBRT_MODE_SQ) return get(base + ".per_channel_scale", (size_t) N * 4, w.scale);
+    return 0;
+  };
+  if (get("vocab_embedding.weight", (size_t) c.vocab * hid * 2, emb)) return -1;
+  if (get("ln_f.weight", (size_t) hid * 2, ln_f)) return -1;
+  if (get("lm_head.weight", (size_t) vocab_l * hid * 2, lm_head)) return -1;
+  L.resize(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    const std::string p = "layers." + std::to_string(i);
+    LayerW& l = L[i];
+    if (get(p + ".input_layernorm.weight", (size_t) hid * 2, l.ln_in)) return -1;
+    if (get(p + ".post_layernorm.weight", (size_t) hid * 2, l.ln_post)) return -1;
+    if (bind_linear(p + ".attention.qkv", 3 * hid_l, hid, l.qkv)) return -1;
+    if (bind_linear(p + ".attention.dense", hid, hid_l, l.dense)) return -1;
+    if (bind_linear(p + ".mlp.fc_gate", 2 * inter_l, hid, l.fc_gate)) return -1;
+    if (bind_linear(p + ".mlp.proj", hid, inter_l, l.proj)) return -1;
+    if (c.int8_kv) {
+      const void *a = nullptr, *b = nullptr;
+      if (get(p + ".attention.kv_orig_quant_scale", 4, a)) return -1;
+      if (get(p + ".attention.kv_quant_orig_scale", 4, b)) return -1;
+      l.kv_oq = static_cast<const float*>(a);
+      l.kv_qo = static_cast<const float*>(b);
+    }
+  }
+  return 0;
+}
+
+int tbrt_engine::build_plugins() {
+  initLibNvInferPlugins(nullptr, kNamespace);
+  const int32_t half_t = (int32_t) DataType::kHALF;
+  auto make_linear = [&](bool swiglu, bool residual) -> PluginPtr {
+    FieldList fl;
+    const char* name = nullptr;
+    if (c.mode == TBRT_MODE_FP16) {
+      name = "Gemm";
+      fl.add<int32_t>("transa", PluginFieldType::kINT32, 0);
+      fl.add<int32_t>("transb", PluginFieldType::kINT32, 1);
+      fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+    } else if (c.mode == TBRT_MODE_SQ) {
+      name = "SmoothQuantGemm";
+      fl.add<int32_t>("has_per_channel_scaling", PluginFieldType::kINT32, 1);
+      fl.add<int32_t>("has_per_token_scaling", PluginFieldType::kINT32, 1);
+      fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+    } else {
+      name = "WeightOnlyQuantMatmul";
+      fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+      fl.add<int32_t>("weight_type_id", PluginFieldType::kINT32, c.mode == TBRT_MODE_W8 ? 1 : 2);
+    }
+    if (swiglu) fl.add<int32_t>("fused_swiglu", PluginFieldType::kINT32, 1);
+    if (residual) fl.add<int32_t>("fused_residual", PluginFieldType::kINT32, 1);
+    return make_plugin(name, fl);
+  };
+  if (!(lin = make_linear(false, false))) return -1;
+  if (!(lin_res = make_linear(false, true))) return -1;
+  if (!(lin_swiglu = make_linear(true, false))) return -1;
+  {
+    FieldList fl;
+    fl.add<int32_t>("transa", PluginFieldType::kINT32, 0);
+    fl.add<int32_t>("transb", PluginFieldType::kINT32, 1);
+    fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+    fl.add<int32_t>("out_fp32", PluginFieldType::kINT32, c.tp_size == 1 ? 1 : 0);
+    if (!(lm = make_plugin("Gemm", fl))) return -1;
+  }
+  {
+    // the fields T/tensorrt_llm/functional.py:2833-2891 passes for a LLaMA layer
+    FieldList fl;
+    fl.add<int32_t>("num_heads", PluginFieldType::kINT32, Hl);
+    fl.add<int32_t>("head_size", PluginFieldType::kINT32, c.head_size);
+    fl.add<int32_t>("unidirectional", PluginFieldType::kINT32, 1);
+    fl.add<float>("q_scaling", PluginFieldType::kFLOAT32, 1.f);
+    fl.add<int32_t>("rotary_embedding_dim", PluginFieldType::kINT32, c.head_size);
+    fl.add<int8_t>("neox_rotary_style", PluginFieldType::kINT8, 1);
+    fl.add<int8_t>("context_fmha_type", PluginFieldType::kINT8, 1);
+    fl.add<int8_t>("multi_block_mode", PluginFieldType::kINT8, 1);
+    fl.add<int8_t>("multi_query_mode", PluginFieldType::kINT8, 0);
+    fl.add<int32_t>("int8_kv_cache", PluginFieldType::kINT32, c.int8_kv);
+    fl.add<int32_t>("fp8_kv_cache", PluginFieldType::kINT32, 0);
+    fl.add<int8_t>("remove_input_padding", PluginFieldType::kINT8, 0);
+    fl.add<int32_t>("mask_type", PluginFieldType::kINT32, 1);
+    fl.add<int32_t>("paged_kv_cache", PluginFieldType::kINT32, 0);
+    fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+    fl.add<int32_t>("in_flight_batching", PluginFieldType::kINT32, 0);
+    fl.add<int32_t>("device_lengths", PluginFieldType::kINT32, 1);
+    if (!(attn = make_plugin("GPTAttention", fl))) return -1;
+  }
+  if (c.mode == TBRT_MODE_SQ) {
+    FieldList fl;
+    fl.add<float>("eps", PluginFieldType::kFLOAT32, c.rms_eps);
+    fl.add<int32_t>("use_diff_of_squares", PluginFieldType::kINT32, 0);
+    fl.add<int32_t>("dyn_act_scaling", PluginFieldType::kINT32, 1);
+    fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+    if (!(normq = make_plugin("RmsnormQuantization", fl))) return -1;
+    FieldList none;
+    if (!(qpt = make_plugin("QuantizePerToken", none))) return -1;
+  }
+  if (c.tp_size > 1) {
+    std::vector<int32_t> group;
+    for (int r = 0; r < c.tp_size; ++r) group.push_back(r);
+    FieldList a, g;
+    a.add_list("group", group);
+    a.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+    g.add_list("group", group);
+    g.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+    if (!(allreduce = make_plugin("AllReduce", a))) return -1;
+    if (!(allgather = make_plugin("AllGather", g))) return -1;
+  }
+  return 0;
+}
+
+// one projection through its plugin: fp16 / weight-only take (x, w[, scales][, residual]); SmoothQuant
+// takes (x int8, w, scale_tokens, scale_channels[, residual]) — same input order as the reference plugins
+int tbrt_engine::linear(IPluginV2DynamicExt* p, const LinearW& w, const void* in, const float* in_scales, void* out,
+                        const void* residual, int M, DataType out_t, cudaStream_t s) {
+  PluginTensorDesc id[5], od[1];
+  const void* inputs[5];
+  void* outputs[1] = {out};
+  int n = 0;
+  if (c.mode == TBRT_MODE_SQ && p != lm.get()) {
+    id[n] = desc({M, w.K}, DataType::kINT8); inputs[n++] = in;
+    id[n] = desc({w.N, w.K / 4}, DataType::kFLOAT); inputs[n++] = w.w;
+    id[n] = desc({M, 1}, DataType::kFLOAT); inputs[n++] = in_scales;
+    id[n] = desc({1, w.N}, DataType::kFLOAT); inputs[n++] = w.scale;
+  } else if ((c.mode == TBRT_MODE_W8 || c.mode == TBRT_MODE_W4) && p != lm.get()) {
+    const int pack = c.mode == TBRT_MODE_W8 ? 4 : 8;
+    id[n] = desc({M, w.K}, DataType::kHALF); inputs[n++] = in;
+    id[n] = desc({w.K, w.N / pack}, DataType::kFLOAT); inputs[n++] = w.w;
+    id[n] = desc({w.N}, DataType::kHALF); inputs[n++] = w.scale;
+  } else {
+    id[n] = desc({M, w.K}, DataType::kHALF); inputs[n++] = in;
+    id[n] = desc({w.N, w.K}, DataType::kHALF); inputs[n++] = w.w;
+  }
+  if (residual) { id[n] = desc({M, w.N}, DataType::kHALF); inputs[n++] = residual; }
+  od[0] = desc({M, w.N}, out_t);
+  ++launches;
+  return p->enqueue(id, od, inputs, outputs, workspace, s);
+}
+
+int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
+  const int hid = c.hidden, Bq = context ? M / S : M;
+  const bool sq = c.mode == TBRT_MODE_SQ, tp = c.tp_size > 1;
+  const bool fuse_swiglu = M <= 4;
+  int host_len[2] = {context ? 0 : c.max_input_len, context ? 1 : 0};   // device_lengths [ext]: step position is on the device
+
+  auto norm = [&](const __half* src, const void* gamma, const __half* residual, __half* sum_out) -> int {
+    launches += 1;
+    if (sq) {
+      PluginTensorDesc id[4] = {desc({M, hid}, DataType::kHALF), desc({hid}, DataType::kHALF), desc({hid}, DataType::kHALF),
+                                desc({1}, DataType::kFLOAT)};
+      PluginTensorDesc od[2] = {desc({M, hid}, DataType::kINT8), desc({M, 1}, DataType::kFLOAT)};
+      if (residual) {   // x + residual first (no fused-residual form requested from the plugin here)
+        RT_CALL(tb_add(sum_out, src, residual, (int64_t) M * hid, s));
+        launches += 1;
+        src = sum_out;
+      }
+      const void* in[4] = {src, gamma, nullptr, d_dummy_scale};
+      void* out[2] = {xq, xs};
+      return normq->enqueue(id, od, in, out, workspace, s);
+    }
+    return tb_rmsnorm(x, src, residual, sum_out, gamma, c.rms_eps, M, hid, s);
+  };
+  auto quant = [&](const __half* src, int cols) -> int {
+    PluginTensorDesc id[1] = {desc({M, cols}, DataType::kHALF)};
+    PluginTensorDesc od[2] = {desc({M, cols}, DataType::kINT8), desc({M, 1}, DataType::kFLOAT)};
+    const void* in[1] = {src};
+    void* out[2] = {xq, xs};
+    launches += 1;
+    return qpt->enqueue(id, od, in, out, workspace, s);
+  };
+  const void* lin_in = sq ? static_cast<const void*>(xq) : static_cast<const void*>(x);
+
+  __half* cur = h;   // residual stream
+  __half* nxt = h2;
+  RT_CALL(norm(cur, L[0].ln_in, nullptr, nullptr));
+  for (int li = 0; li < c.layers; ++li) {
+    const LayerW& l = L[li];
+    RT_CALL(linear(lin.get(), l.qkv, lin_in, xs, qkv, nullptr, M, DataType::kHALF, s));
+    {
+      const DataType kvt = c.int8_kv ? DataType::kINT8 : DataType::kHALF;
+      PluginTensorDesc id[10] = {desc({Bq, context ? S : 1, 3 * hid_l}, DataType::kHALF),
+                                 desc({Bq, 2, Hl, S_max, c.head_size}, kvt),
+                                 desc({Bq}, DataType::kINT32), desc({2}, DataType::kINT32),
+                                 desc({Bq, S_max}, DataType::kINT32), desc({Bq}, DataType::kINT32),
+                                 desc({S_in}, DataType::kINT32), desc({Bq, 1, S_max}, DataType::kINT32),
+                                 desc({1}, DataType::kFLOAT), desc({1}, DataType::kFLOAT)};
+      PluginTensorDesc od[2] = {desc({Bq, context ? S : 1, hid_l}, DataType::kHALF), id[1]};
+      // masked_tokens = NULL: derived from input_lengths / max_input_length on the device ([ext])
+      const void* in[10] = {qkv, kv[li], d_seq_lens, host_len, nullptr, d_in_lens, nullptr, nullptr, l.kv_oq, l.kv_qo};
+      void* out[2] = {att, kv[li]};
+      launches += context ? 2 : 1;
+      RT_CALL(attn->enqueue(id, od, in, out, workspace, s));
+    }
+    const void* dense_in = att;
+    if (sq) { RT_CALL(quant(att, hid_l)); dense_in = xq; }
+    if (!tp) {
+      RT_CALL(linear(lin_res.get(), l.dense, dense_in, xs, nxt, cur, M, DataType::kHALF, s));   // nxt = cur + dense(att)
+      RT_CALL(norm(nxt, l.ln_post, nullptr, nullptr));
+    } else {
+      RT_CALL(linear(lin.get(), l.dense, dense_in, xs, o, nullptr, M, DataType::kHALF, s));
+      PluginTensorDesc d1[1] = {desc({M, hid}, DataType::kHALF)};
+      const void* in[1] = {o};
+      void* out[1] = {o};
+      launches += 1;
+      RT_CALL(allreduce->enqueue(d1, d1, in, out, workspace, s));
+      RT_CALL(norm(o, l.ln_post, cur, nxt));                                                    // nxt = o + cur, x = norm(nxt)
+    }
+    std::swap(cur, nxt);
+    if (fuse_swiglu) {
+      RT_CALL(linear(lin_swiglu.get(), l.fc_gate, lin_in, xs, act, nullptr, M, DataType::kHALF, s));
+    } else {
+      RT_CALL(linear(lin.get(), l.fc_gate, lin_in, xs, gu, nullptr, M, DataType::kHALF, s));
+      launches += 1;
+      RT_CALL(tb_swiglu(act, gu, gu + inter_l, M, inter_l, 2 * inter_l, s));
+    }
+    const void* proj_in = act;
+    if (sq) { RT_CALL(quant(act, inter_l)); proj_in = xq; }
+    const void* next_gamma = li + 1 < c.layers ? L[li + 1].ln_in : nullptr;
+    if (!tp) {
+      RT_CALL(linear(lin_res.get(), l.proj, proj_in, xs, nxt, cur, M, DataType::kHALF, s));
+      std::swap(cur, nxt);
+      if (next_gamma) RT_CALL(norm(cur, next_gamma, nullptr, nullptr));
+    } else {
+      RT_CALL(linear(lin.get(), l.proj, proj_in, xs, o, nullptr, M, DataType::kHALF, s));
+      PluginTensorDesc d1[1] = {desc({M, hid}, DataType::kHALF)};
+      const void* in[1] = {o};
+      void* out[1] = {o};
+      launches += 1;
+      RT_CALL(allreduce->enqueue(d1, d1, in, out, workspace, s));
+      if (next_gamma) {
+        RT_CALL(norm(o, next_gamma, cur, nxt));
+      } else {
+        launches += 1;
+        RT_CALL(tb_add(nxt, o, cur, (int64_t) M * hid, s));
+      }
+      std::swap(cur, nxt);
+    }
+  }
+  if (cur != h) {   // keep the final residual stream in `h` (layer count is even in practice; copy otherwise)
+    RT_CUDA(cudaMemcpyAsync(h, cur, (size_t) M * hid * 2, cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+// ln_f -> lm_head (fp32 logits) -> greedy argmax -> device-side bookkeeping
+int tbrt_engine::head(int rows, cudaStream_t s) {
+  LinearW w;
+  w.w = lm_head; w.N = vocab_l; w.K = c.hidden;
+  launches += 3;
+  RT_CALL(tb_rmsnorm(x, hl, nullptr, nullptr, ln_f, c.rms_eps, rows, c.hidden, s));
+  if (c.tp_size == 1) {
+    RT_CALL(linear(lm.get(), w, x, nullptr, logits, nullptr, rows, DataType::kFLOAT, s));
+  } else {
+    // vocab-parallel lm_head + all-gather (T/tensorrt_llm/layers/linear.py:78-97 gather_output)
+    RT_CALL(linear(lm.get(), w, x, nullptr, logits_h, nullptr, rows, DataType::kHALF, s));
+    PluginTensorDesc id[1] = {desc({rows, vocab_l}, DataType::kHALF)};
+    PluginTensorDesc od[1] = {desc({rows * c.tp_size, vocab_l}, DataType::kHALF)};
+    const void* in[1] = {logits_h};
+    void* out[1] = {logits_h + (size_t) rows * vocab_l};
+    launches += 2;
+    RT_CALL(allgather->enqueue(id, od, in, out, workspace, s));
+    RT_CALL(tb_gather_logits(logits, logits_h + (size_t) rows * vocab_l, rows, vocab_l, c.tp_size, s));
+  }
+  RT_CALL(tb_argmax(d_next, logits, rows, c.vocab, c.vocab, s));
+  RT_CALL(tb_advance_step(d_next, d_ids, d_out_ids, d_seq_lens, d_step_pos, rows, c.max_output_len, s));
+  return 0;
+}
+
+int tbrt_engine::step_body(cudaStream_t s) {
+  launches += 1;
+  RT_CALL(tb_embedding(h, emb, d_ids, B, c.hidden, c.vocab, s));
+  if (layers_forward(B, 1, false, s)) return -1;
+  RT_CUDA(cudaMemcpyAsync(hl, h, (size_t) B * c.hidden * 2, cudaMemcpyDeviceToDevice, s));
+  return head(B, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* tbrt_last_error(void) { return g_err.c_str(); }
+
+tbrt_engine* tbrt_create(const tbrt_config* cfg) {
+  if (!cfg || cfg->head_size != 128 || cfg->tp_size < 1 || cfg->mode < 0 || cfg->mode > 3) {
+    g_err = "bad tbrt_config";
+    return nullptr;
+  }
+  if (tb_check_device() != 0) {
+    g_err = "no sm_100 device is current: this runtime has no CPU or other-architecture fallback";
+    return nullptr;
+  }
+  auto* e = new tbrt_engine();
+  e->c = *cfg;
+  return e;
+}
+void tbrt_destroy(tbrt_engine* e) { delete e; }
+
+int tbrt_set_tensor(tbrt_engine* e, const char* name, const void* ptr, size_t bytes) {
+  if (!e || !name || !ptr) return fail("tbrt_set_tensor: null argument");
+  if (e->finalized) return fail("engine already finalized");
+  e->tensors[name] = Tensor{ptr, bytes};
+  return 0;
+}
+
+int tbrt_finalize(tbrt_engine* e) {
+  if (e->finalized) return 0;
+  if (e->bind()) return -1;
+  if (e->build_plugins()) return -1;
+  const tbrt_config& c = e->c;
+  const size_t Mmax = (size_t) c.max_batch * c.max_input_len, hid = c.hidden;
+  if (e->alloc(e->h, Mmax * hid * 2) || e->alloc(e->h2, Mmax * hid * 2) || e->alloc(e->x, Mmax * hid * 2) ||
+      e->alloc(e->qkv, Mmax * 3 * e->hid_l * 2) || e->alloc(e->att, Mmax * e->hid_l * 2) ||
+      e->alloc(e->gu, Mmax * 2 * e->inter_l * 2) || e->alloc(e->act, Mmax * e->inter_l * 2) ||
+      e->alloc(e->o, Mmax * hid * 2) || e->alloc(e->hl, (size_t) c.max_batch * hid * 2))
+    return -1;
+  if (c.mode == TBRT_MODE_SQ) {
+    const size_t widest = (size_t) (e->inter_l > c.hidden ? e->inter_l : c.hidden);
+    if (e->alloc(e->xq, Mmax * widest) || e->alloc(e->xs, Mmax * 4)) return -1;
+  }
+  if (e->alloc(e->logits, (size_t) c.max_batch * c.vocab * 4)) return -1;
+  if (c.tp_size > 1 && e->alloc(e->logits_h, (size_t) c.max_batch * e->vocab_l * 2 * (1 + c.tp_size))) return -1;
+  e->kv.resize(c.layers);
+  const size_t kv_bytes = (size_t) c.max_batch * 2 * e->Hl * e->S_max * c.head_size * (c.int8_kv ? 1 : 2);
+  for (int i = 0; i < c.layers; ++i) {
+    if (e->alloc(e->kv[i], kv_bytes)) return -1;
+    RT_CUDA(cudaMemset(e->kv[i], 0, kv_bytes));
+  }
+  // workspace: the maximum any plugin asks for over the shapes this engine runs (TensorRT does the same)
+  size_t ws = tb_mmha_workspace_bytes(c.max_batch, e->Hl, 32);
+  const int Ns[4] = {3 * e->hid_l, c.hidden, 2 * e->inter_l, e->vocab_l};
+  const int Ks[4] = {c.hidden, e->inter_l, c.hidden, c.hidden};
+  const int Ms[2] = {c.max_batch, (int) Mmax};
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const size_t w = tb_gemm_tc_workspace_bytes(Ms[b], Ns[a], Ks[a]);
+      if (w > ws) ws = w;
+    }
+  {
+    const size_t w = tb_gemm_tc_workspace_bytes(c.max_batch, c.hidden, e->hid_l);
+    if (w > ws) ws = w;
+  }
+  e->workspace_bytes = ws + 1024;
+  if (e->alloc(e->workspace, e->workspace_bytes)) return -1;
+  if (e->alloc(e->d_ids, (size_t) c.max_batch * 4) || e->alloc(e->d_in_lens, (size_t) c.max_batch * 4) ||
+      e->alloc(e->d_seq_lens, (size_t) c.max_batch * 4) || e->alloc(e->d_step_pos, 4) ||
+      e->alloc(e->d_next, (size_t) c.max_batch * 4) || e->alloc(e->d_out_ids, (size_t) c.max_batch * c.max_output_len * 4) ||
+      e->alloc(e->d_prompt, Mmax * 4) || e->alloc(e->d_dummy_scale, 4))
+    return -1;
+  RT_CUDA(cudaMemset(e->d_dummy_scale, 0, 4));
+  RT_CUDA(cudaDeviceSynchronize());
+  e->finalized = true;
+  return 0;
+}
+
+size_t tbrt_device_bytes(const tbrt_engine* e) { return e->dev_bytes; }
+const float* tbrt_logits(const tbrt_engine* e) { return e->logits; }
+const int32_t* tbrt_output_ids(const tbrt_engine* e) { return e->d_out_ids; }
+void* tbrt_kv_cache(const tbrt_engine* e, int layer) { return (layer >= 0 && layer < (int) e->kv.size()) ? e->kv[layer] : nullptr; }
+int64_t tbrt_last_launches(const tbrt_engine* e) { return e->launches; }
+
+int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_lengths, int batch, int seq, tb_stream_t st) {
+  if (!e->finalized) return fail("engine not finalized");
+  if (batch < 1 || batch > e->c.max_batch || seq < 1 || seq > e->c.max_input_len) return fail("batch / seq outside the engine limits");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
+  e->B = batch; e->S_in = seq; e->steps_done = 0; e->launches = 0;
+  const int M = batch * seq;
+  // step state: the first generated token lands in column 0; every sequence of the padded batch sits at
+  // position seq afterwards (sequence_length = max_input_len + step, generation.py:686-687)
+  RT_CUDA(cudaMemsetAsync(e->d_step_pos, 0, 4, s));
+  RT_CALL(tb_fill_int(e->d_seq_lens, seq - 1, batch, s));
+  RT_CUDA(cudaMemcpyAsync(e->d_in_lens, input_lengths, (size_t) batch * 4, cudaMemcpyDeviceToDevice, s));
+  e->launches += 1;
+  RT_CALL(tb_embedding(e->h, e->emb, ids, M, e->c.hidden, e->c.vocab, s));
+  if (e->layers_forward(M, seq, true, s)) return -1;
+  e->launches += 1;
+  RT_CALL(tb_gather_last_token(e->hl, e->h, e->d_in_lens, batch, seq, e->c.hidden, s));
+  return e->head(batch, s);
+}
+
+int tbrt_step(tbrt_engine* e, tb_stream_t st) {
+  if (!e->finalized || e->B == 0) return fail("tbrt_step before tbrt_context");
+  if (e->S_in + e->steps_done + 1 >= e->S_max) return fail("KV cache is full");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
+  e->steps_done += 1;
+  if (!e->c.use_cuda_graph) { e->launches = 0; return e->step_body(s); }
+  auto it = e->graphs.find(e->B);
+  if (it == e->graphs.end()) {
+    // the first step at a batch size runs eagerly (plugins allocate their counters, kernels set their
+    // attributes); the second is captured; every later one replays the graph
+    if (e->eager_steps[e->B]++ == 0) { e->launches = 0; return e->step_body(s); }
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
+    // nothing executes during capture, the instantiated graph is then launched on the caller's stream
+    cudaGraph_t g = nullptr;
+    if (!e->cap_stream) RT_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    RT_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    e->launches = 0;
+    const int rc = e->step_body(e->cap_stream);
+    cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &g);
+    if (rc != 0) { if (g) cudaGraphDestroy(g); return -1; }
+    RT_CUDA(ce);
+    size_t nodes = 0;
+    RT_CUDA(cudaGraphGetNodes(g, nullptr, &nodes));
+    cudaGraphExec_t ge = nullptr;
+    RT_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    RT_CUDA(cudaGraphDestroy(g));
+    e->graphs[e->B] = ge;
+    e->graph_nodes[e->B] = (int64_t) nodes;
+    it = e->graphs.find(e->B);
+  }
+  e->launches = e->graph_nodes[e->B];
+  RT_CUDA(cudaGraphLaunch(it->second, s));
+  return 0;
+}
+
+int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_lengths, int batch, int seq, int max_new,
+                  int32_t* host_out_ids, tb_stream_t st) {
+  if (!e->finalized) return fail("engine not finalized");
+  if (max_new < 1 || max_new > e->c.max_output_len) return fail("max_new outside the engine limits");
+  if (batch < 1 || batch > e->c.max_batch || seq < 1 || seq > e->c.max_input_len) return fail("batch / seq outside the engine limits");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
+  RT_CUDA(cudaMemcpyAsync(e->d_prompt, host_ids, (size_t) batch * seq * 4, cudaMemcpyHostToDevice, s));
+  RT_CUDA(cudaMemcpyAsync(e->d_next, host_lengths, (size_t) batch * 4, cudaMemcpyHostToDevice, s));
+  if (tbrt_context(e, e->d_prompt, e->d_next, batch, seq, st)) return -1;
+  int64_t total = e->launches;
+  for (int i = 1; i < max_new; ++i) {
+    if (tbrt_step(e, st)) return -1;
+    total += e->launches;
+  }
+  RT_CUDA(cudaMemcpy2DAsync(host_out_ids, (size_t) max_new * 4, e->d_out_ids, (size_t) e->c.max_output_len * 4,
+                            (size_t) max_new * 4, batch, cudaMemcpyDeviceToHost, s));
+  RT_CUDA(cudaStreamSynchronize(s));
+  e->launches = total;
+  return 0;
+}
+}

@@ -30,14 +30,25 @@ def _chk_cuda(*ts):
 
 
 _ws_cache = {}
+_cnt_cache = {}
+
+
+def _counters(device) -> torch.Tensor:
+    """zeroed once; split-K / split-L arrival counters reset themselves after every launch."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    cur = _cnt_cache.get(key)
+    if cur is None:
+        cur = torch.zeros(1 << 16, dtype=torch.int32, device=device)
+        _cnt_cache[key] = cur
+    return cur
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    """zero-initialised scratch (split-K / split-L counters must start at 0 and are self-resetting)."""
+    """scratch for split-K / split-L partials (contents need not be initialised)."""
     key = (device.index if device.index is not None else torch.cuda.current_device())
     cur = _ws_cache.get(key)
     if cur is None or cur.numel() < nbytes:
-        cur = torch.zeros(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
+        cur = torch.empty(max(nbytes, 1 << 22), dtype=torch.uint8, device=device)
         _ws_cache[key] = cur
     return cur
 
@@ -118,7 +129,8 @@ def gemm_tc(kind, x, w, *, w_scale=None, sc=None, sr=None, residual=None, out_dt
     ws = _workspace(need, x.device)
     check(lib.tb_gemm_tc(kind, _p(c), _OUT_TYPES[out_dtype], _p(x), _p(w), _p(w_scale), _p(sc), _p(sr),
                          int(sc is not None and sc.numel() > 1), int(sr is not None and sr.numel() > 1), _p(residual),
-                         M, N, K, _p(ws), ws.numel(), force_splits, force_nt, _stream()), "tb_gemm_tc")
+                         M, N, K, _p(ws), ws.numel(), _p(_counters(x.device)), force_splits, force_nt, _stream()),
+          "tb_gemm_tc")
     return c
 
 
@@ -173,7 +185,7 @@ def mmha_decode(qkv, kv_cache, past_len, *, num_heads, head_size, max_input_len,
     ws = _workspace(lib.tb_mmha_workspace_bytes(B, num_heads, max(nsplit, max_splits)), qkv.device)
     out = torch.empty((B, num_heads * head_size), dtype=torch.float16, device=qkv.device)
     check(lib.tb_mmha_decode(_p(out), _p(qkv), _p(kv_cache), _p(seq_lens), _p(input_lengths), _p(masked_tokens),
-                             _p(kv_scale_orig_quant), _p(kv_scale_quant_orig), _p(ws), B, num_heads, head_size, S_max,
+                             _p(kv_scale_orig_quant), _p(kv_scale_quant_orig), _p(ws), _p(_counters(qkv.device)), B, num_heads, head_size, S_max,
                              int(past_len), int(max_input_len), int(cap), rot, float(q_scaling), int(int8_kv),
                              nsplit, _stream()), "tb_mmha_decode")
     return out

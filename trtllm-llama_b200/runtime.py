@@ -1,0 +1,242 @@
+"""Python face of the C++ runtime (include/trtllm_b200_runtime.h) with the reference runtime's names.
+
+Mirrors T/tensorrt_llm/runtime/generation.py: ``ModelConfig`` (:103-117), ``SamplingConfig`` (:119-138),
+``GenerationSession.setup`` / ``.decode`` (:413-488, :782-997) for the contiguous-KV greedy path.  The
+session holds a ``tbrt_engine``; torch supplies device memory and the stream, nothing else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import torch
+
+from ._lib import KernelError, TbrtConfig, lib
+from .quantization import QuantMode, quantize_per_channel_int8, symmetric_quantize_last_axis_of_batched_matrix
+
+MODE_FP16, MODE_W8, MODE_W4, MODE_SQ = 0, 1, 2, 3
+
+
+@dataclass
+class ModelConfig:
+    """generation.py:103-117 (+ the sizes build.py bakes into config.json)."""
+    vocab_size: int = 32000
+    num_layers: int = 32
+    num_heads: int = 32
+    hidden_size: int = 4096
+    inter_size: int = 11008
+    gpt_attention_plugin: bool = True
+    multi_query_mode: bool = False
+    remove_input_padding: bool = False
+    paged_kv_cache: bool = False
+    rms_eps: float = 1e-6
+    quant_mode: QuantMode = QuantMode(0)
+    max_batch_size: int = 8
+    max_input_len: int = 128
+    max_output_len: int = 128
+    tp_size: int = 1
+    tp_rank: int = 0
+
+    @property
+    def mode(self) -> int:
+        q = self.quant_mode
+        if q.has_act_and_weight_quant():
+            return MODE_SQ
+        if q.is_int4_weight_only():
+            return MODE_W4
+        if q.is_int8_weight_only():
+            return MODE_W8
+        return MODE_FP16
+
+
+@dataclass
+class SamplingConfig:
+    """generation.py:119-138.  Only the greedy defaults (top_k = 1, num_beams = 1) are built."""
+    end_id: int = 2
+    pad_id: int = 2
+    num_beams: int = 1
+    temperature: float = 1.0
+    top_k: int = 1
+    top_p: float = 0.0
+    length_penalty: float = 1.0
+    repetition_penalty: float = 1.0
+    min_length: int = 1
+    output_log_probs: bool = field(init=False, default=False)
+
+
+def _err(what):
+    return KernelError(f"{what}: {lib.tbrt_last_error().decode()}")
+
+
+# ------------------------------------------------------------------------------------------------
+# weights: fp16 torch-Linear tensors -> the engine's named, quantised, tensor-parallel-sharded tensors
+# ------------------------------------------------------------------------------------------------
+def shard_weights(w, tp_size, rank, num_heads):
+    """Megatron split of one decoder's fp16 weights (T/examples/llama/weight.py:71-178):
+    qkv rows per head group, dense / proj input dim, fc / gate rows, lm_head vocab rows."""
+    if tp_size == 1:
+        return w
+    out = {k: w[k] for k in ("vocab_embedding", "ln_f")}
+    out["lm_head"] = w["lm_head"].chunk(tp_size, dim=0)[rank].contiguous()
+    out["layers"] = []
+    for lw in w["layers"]:
+        hidden = lw["dense"].shape[0]
+        q, k, v = lw["qkv"].view(3, hidden, hidden).unbind(0)
+        e = {"input_layernorm": lw["input_layernorm"], "post_layernorm": lw["post_layernorm"],
+             "qkv": torch.cat([t.chunk(tp_size, dim=0)[rank] for t in (q, k, v)], dim=0).contiguous(),
+             "dense": lw["dense"].chunk(tp_size, dim=1)[rank].contiguous(),
+             "gate": lw["gate"].chunk(tp_size, dim=0)[rank].contiguous(),
+             "up": lw["up"].chunk(tp_size, dim=0)[rank].contiguous(),
+             "down": lw["down"].chunk(tp_size, dim=1)[rank].contiguous()}
+        out["layers"].append(e)
+    return out
+
+
+def quantize_linear(w_nk: torch.Tensor, mode: int):
+    """one Linear weight [N, K] fp16 -> {"weight": ..., "per_channel_scale": ...} in the plugin's layout."""
+    if mode == MODE_FP16:
+        return {"weight": w_nk.contiguous()}
+    if mode in (MODE_W8, MODE_W4):
+        qt = torch.int8 if mode == MODE_W8 else torch.quint4x2
+        processed, scales = symmetric_quantize_last_axis_of_batched_matrix(w_nk.t(), qt)   # op takes [K, N]
+        return {"weight": processed, "per_channel_scale": scales}
+    q, s = quantize_per_channel_int8(w_nk)
+    return {"weight": q, "per_channel_scale": s}
+
+
+def build_engine_tensors(w, cfg: ModelConfig, kv_scale: float = 4.0 / 127.0):
+    """fp16 weights (this rank's shard, see ``shard_weights``) -> {engine tensor name: device tensor}."""
+    mode = cfg.mode
+    t = {"vocab_embedding.weight": w["vocab_embedding"], "ln_f.weight": w["ln_f"], "lm_head.weight": w["lm_head"]}
+    for i, lw in enumerate(w["layers"]):
+        p = f"layers.{i}."
+        t[p + "input_layernorm.weight"] = lw["input_layernorm"]
+        t[p + "post_layernorm.weight"] = lw["post_layernorm"]
+        if mode == MODE_SQ and cfg.tp_size > 1:
+            raise NotImplementedError("SmoothQuant with tensor parallelism: quantise before sharding (see DESIGN.md)")
+        # fc = gate_proj, gate = up_proj (LQ/weight_quant.py:343-404); fused as one [2*inter, K] projection
+        named = {"attention.qkv": lw["qkv"], "attention.dense": lw["dense"],
+                 "mlp.fc_gate": torch.cat([lw["gate"], lw["up"]], dim=0), "mlp.proj": lw["down"]}
+        for name, wt in named.items():
+            for k, v in quantize_linear(wt, mode).items():
+                t[p + name + "." + k] = v
+        if cfg.quant_mode.has_int8_kv_cache():
+            dev = lw["qkv"].device
+            # LQ/weight_quant.py:439-446: kv_orig_quant_scale = 1/t, kv_quant_orig_scale = t
+            t[p + "attention.kv_orig_quant_scale"] = torch.tensor([1.0 / kv_scale], dtype=torch.float32, device=dev)
+            t[p + "attention.kv_quant_orig_scale"] = torch.tensor([kv_scale], dtype=torch.float32, device=dev)
+    return {k: v.contiguous() for k, v in t.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+class GenerationSession:
+    """generation.py:151-242 GenerationSession, holding a tbrt_engine instead of a TensorRT context."""
+
+    def __init__(self, model_config: ModelConfig, engine_tensors: dict, use_cuda_graph: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GenerationSession needs a CUDA device (sm_100a); there is no CPU path")
+        mc = self.cfg = model_config
+        c = TbrtConfig(hidden=mc.hidden_size, heads=mc.num_heads, inter=mc.inter_size, layers=mc.num_layers,
+                       vocab=mc.vocab_size, head_size=mc.hidden_size // mc.num_heads, rms_eps=mc.rms_eps, mode=mc.mode,
+                       int8_kv=int(mc.quant_mode.has_int8_kv_cache()), max_batch=mc.max_batch_size,
+                       max_input_len=mc.max_input_len, max_output_len=mc.max_output_len, tp_size=mc.tp_size,
+                       tp_rank=mc.tp_rank, use_cuda_graph=int(use_cuda_graph))
+        self._e = lib.tbrt_create(C.byref(c))
+        if not self._e:
+            raise _err("tbrt_create")
+        self._tensors = engine_tensors      # keep the device memory alive
+        for name, t in engine_tensors.items():
+            if not t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"engine tensor {name} must be a contiguous CUDA tensor")
+            if lib.tbrt_set_tensor(self._e, name.encode(), t.data_ptr(), t.numel() * t.element_size()):
+                raise _err("tbrt_set_tensor")
+        if lib.tbrt_finalize(self._e):
+            raise _err("tbrt_finalize")
+        self.batch_size = self.max_input_len = self.max_new_tokens = 0
+
+    def __del__(self):
+        e, self._e = getattr(self, "_e", None), None
+        if e:
+            lib.tbrt_destroy(e)
+
+    @property
+    def device_bytes(self):
+        return lib.tbrt_device_bytes(self._e)
+
+    @property
+    def last_launches(self):
+        return lib.tbrt_last_launches(self._e)
+
+    def setup(self, batch_size, max_input_length, max_new_tokens, beam_width=1):
+        """generation.py:413-488: fixes the shapes of the next decode (buffers were sized at engine build)."""
+        if beam_width != 1:
+            raise NotImplementedError("beam search is out of scope (SURVEY 8f-4)")
+        mc = self.cfg
+        if batch_size > mc.max_batch_size or max_input_length > mc.max_input_len or max_new_tokens > mc.max_output_len:
+            raise ValueError("setup() exceeds the limits the engine was built with")
+        self.batch_size, self.max_input_len, self.max_new_tokens = batch_size, max_input_length, max_new_tokens
+
+    def _stream(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    # granular entry points (tests compare logits step by step)
+    def context(self, input_ids: torch.Tensor, input_lengths: torch.Tensor):
+        B, S = input_ids.shape
+        ids = input_ids.to(device="cuda", dtype=torch.int32).contiguous()
+        lens = input_lengths.to(device="cuda", dtype=torch.int32).contiguous()
+        if lib.tbrt_context(self._e, ids.data_ptr(), lens.data_ptr(), B, S, self._stream()):
+            raise _err("tbrt_context")
+        self._B = B
+        return self.logits()
+
+    def step(self):
+        if lib.tbrt_step(self._e, self._stream()):
+            raise _err("tbrt_step")
+        return self.logits()
+
+    def logits(self) -> torch.Tensor:
+        """fp32 [B, vocab] copy of the engine's logits buffer."""
+        n = self._B * self.cfg.vocab_size
+        out = torch.empty((self._B, self.cfg.vocab_size), dtype=torch.float32, device="cuda")
+        _memcpy_d2d(out.data_ptr(), lib.tbrt_logits(self._e), n * 4, self._stream())
+        return out
+
+    def output_ids(self, n_tokens) -> torch.Tensor:
+        full = torch.empty((self._B, self.cfg.max_output_len), dtype=torch.int32, device="cuda")
+        _memcpy_d2d(full.data_ptr(), lib.tbrt_output_ids(self._e), full.numel() * 4, self._stream())
+        return full[:, :n_tokens]
+
+    def kv_cache(self, layer) -> torch.Tensor:
+        mc = self.cfg
+        shape = (mc.max_batch_size, 2, mc.num_heads // mc.tp_size, mc.max_input_len + mc.max_output_len,
+                 mc.hidden_size // mc.num_heads)
+        dt = torch.int8 if mc.quant_mode.has_int8_kv_cache() else torch.float16
+        out = torch.empty(shape, dtype=dt, device="cuda")
+        _memcpy_d2d(out.data_ptr(), lib.tbrt_kv_cache(self._e, layer), out.numel() * out.element_size(), self._stream())
+        return out
+
+    def decode(self, input_ids: torch.Tensor, input_lengths: torch.Tensor, sampling_config: SamplingConfig = None,
+               max_new_tokens: int = None, out: torch.Tensor = None) -> torch.Tensor:
+        """generation.py:782-997 for greedy sampling.  ``input_ids`` [B, S] / ``input_lengths`` [B] are HOST int32
+        tensors (pinned for asynchronous copies); returns HOST output ids [B, max_new_tokens] — the host<->device
+        copies are part of the call, as in the reference's run.py timing (LQ/run.py:117-198)."""
+        sc = sampling_config or SamplingConfig()
+        if sc.num_beams != 1 or sc.top_k != 1:
+            raise NotImplementedError("only greedy decoding (top_k=1, num_beams=1) is built (SURVEY 8f-4)")
+        B, S = input_ids.shape
+        n = max_new_tokens or self.max_new_tokens
+        if input_ids.is_cuda or input_ids.dtype != torch.int32 or not input_ids.is_contiguous():
+            raise ValueError("decode() takes contiguous host int32 input_ids")
+        if out is None:
+            out = torch.empty((B, n), dtype=torch.int32, pin_memory=True)
+        lens = input_lengths.to(dtype=torch.int32).contiguous()
+        if lib.tbrt_generate(self._e, input_ids.data_ptr(), lens.data_ptr(), B, S, n, out.data_ptr(), self._stream()):
+            raise _err("tbrt_generate")
+        self._B = B
+        return out
+
+
+def _memcpy_d2d(dst, src, nbytes, stream):
+    rc = lib.tb_copy(dst, src, nbytes, stream)
+    if rc:
+        raise KernelError(f"tb_copy failed with {rc}")
