@@ -56,6 +56,14 @@ int tb_quantize_tensor(int8_t* dst, const void* src, int64_t size, const float* 
 int tb_gemv(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
             const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
             int swiglu, tb_stream_t stream);
+/* tb_gemv with a fused activation prologue (x is fp16 [M,K] whenever prologue != 0):
+ *   1  RMSNorm(x, gamma, eps)                        — the TRT-native rms_norm in front of qkv / gate+up
+ *   2  RMSNorm + dynamic per-token int8 (kind 3)     — RmsnormQuantization (K/layernormKernels.cu:141-193 semantics)
+ *   3  dynamic per-token int8 (kind 3)               — QuantizePerToken (K/quantization.cu:93-117)
+ * With 2 and 3 the per-token scales are computed in the kernel and `sr` is ignored.               */
+int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
+                  const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
+                  int swiglu, int prologue, const void* gamma, float eps, tb_stream_t stream);
 
 /* ---- tcgen05 GEMM (any M) ---------------------------------------------------------------------
  * kind as tb_gemv.  out_type: 0 fp16, 1 fp32, 2 int32 (SmoothQuantGemm type_id half/float/int32).

@@ -157,6 +157,43 @@ def test_gemv_swiglu(ops):
     np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), rtol=4e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("M", [1, 2, 3])
+@pytest.mark.parametrize("N,K,swiglu", [(512, 4096, False), (768, 11008, False), (2 * 384, 4096, True), (10, 256, False)])
+def test_gemv_fused_rmsnorm(ops, M, N, K, swiglu):
+    """prologue 1: the TRT-native rms_norm in front of a projection, fused into the GEMV's activation staging."""
+    rng = np.random.default_rng(31)
+    h = rng.standard_normal((M, K)).astype(np.float16)
+    g = (1 + 0.1 * rng.standard_normal(K)).astype(np.float16)
+    w = (rng.standard_normal((N, K)) * 0.03).astype(np.float16)
+    y = host(ops.gemv(ops.KIND_F16, dev(h), dev(w), swiglu=swiglu, prologue=ops.PRO_RMS, gamma=dev(g), eps=1e-6))
+    ref = R.gemm_f16(R.rmsnorm(h, g, 1e-6), w)
+    if swiglu:
+        ref = R.swiglu(ref[:, :N // 2], ref[:, N // 2:])
+    np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), rtol=4e-3, atol=4e-3)
+
+
+@pytest.mark.parametrize("M", [1, 4])
+@pytest.mark.parametrize("prologue", [2, 3])
+def test_gemv_fused_quant_prologues(ops, M, prologue):
+    """prologue 2 = RmsnormQuantization, 3 = QuantizePerToken, fused in front of the W8A8 GEMV."""
+    rng = np.random.default_rng(32)
+    N, K = 640, 4096
+    h = rng.standard_normal((M, K)).astype(np.float16)
+    g = (1 + 0.1 * rng.standard_normal(K)).astype(np.float16)
+    b = rng.integers(-128, 128, (N, K), dtype=np.int8)
+    sb = (rng.integers(1, 10, (1, N)) * 1e-3).astype(np.float32)
+    r = rng.standard_normal((M, N)).astype(np.float16)
+    y = host(ops.gemv(ops.KIND_A8W8, dev(h), dev(b), sc=dev(sb), residual=dev(r), prologue=prologue, gamma=dev(g), eps=1e-6))
+    q, st = R.rmsnorm_quant(h, g, 1e-6, dynamic=True) if prologue == 2 else R.quantize_per_token(h)
+    ref = R.residual_add(R.sq_gemm(q, b, st, sb, np.float16), r)
+    # int8 codes may flip by one where rsqrt rounding differs (see test_rmsnorm_quant): compare at output scale
+    tol = 4e-3 * float(np.abs(ref.astype(np.float32)).max()) if prologue == 2 else 0.0
+    if prologue == 3:
+        assert np.array_equal(y, ref)      # same quantiser arithmetic, integer GEMM: bit-exact
+    else:
+        np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), atol=tol)
+
+
 # ------------------------------------------------------------------------------------------------
 TC_SHAPES = [(1, 256, 512), (8, 384, 4096), (16, 128, 256), (40, 200, 1376), (128, 512, 1024), (300, 256, 2048)]
 

@@ -1,27 +1,41 @@
-// Decode-shape (M <= 4 token rows) matrix-vector path: Y[M,N] = X[M,K] . W[N,K]^T with W streamed
-// exactly once from HBM in 16-byte loads, X staged in shared memory, fp32 (int32 for W8A8)
-// accumulation, warp-shuffle reduction and a fused epilogue (per-channel / per-token scales,
-// SwiGLU, residual add).  HBM-bound: algorithmic bytes = N*K*bytes_per_weight (+ M*(K+N)*2).
+// Decode-shape (M <= 4 token rows) projection: Y[M,N] = X[M,K] . W[N,K]^T, the kernel that streams the
+// model's weights once per generated token and therefore bounds decode tokens/s (HBM roofline).
+//
+// sm_100a design: persistent CTAs (2 per SM), each owning a contiguous, balanced range of output rows.
+// One producer thread streams that range through a 5-stage shared-memory ring with bulk async copies
+// (cp.async.bulk global -> shared, completion on an mbarrier, L2 evict-first: every weight byte is used once);
+// eight consumer warps read the staged 1-KB row segments with conflict-free 16-byte LDS, accumulate in fp32
+// (int32 dp4a for W8A8) and apply the fused epilogue (per-channel / per-token scales, SwiGLU, residual add).
+// ~80 KB of loads are in flight per CTA without holding registers, which is what a latency x bandwidth
+// product of ~5 MB across 148 SMs asks for.
+// Fused prologues (the TensorRT-native glue / extra plugins of the reference):
+//   RMSNorm of the residual stream, RMSNorm + dynamic per-token int8 quantisation (RmsnormQuantization),
+//   plain dynamic per-token quantisation (QuantizePerToken) — each CTA recomputes the row statistics of the
+//   8-22 KB activation it stages anyway (L2-resident), removing two to four launches per layer.
+// Programmatic dependent launch: the producer starts streaming weights (which do not depend on the previous
+// kernel) before griddepcontrol.wait; only the activation staging waits for the upstream kernel.
 //
 // Replaces (reference):
 //   T/cpp/tensorrt_llm/kernels/weightOnlyMatrixVectorMultiplication.cu:136-277,371-378 (int8/int4 GEMV)
 //   the M<=4 calls of CutlassInt8GemmRunner::gemm (int8_gemm_template.h:356-369) and of
 //   GemmPlugin/cuBLAS (P/gemmPlugin/gemmPlugin.cpp:121-230) made by the decode step.
-// Weight layouts (this repo's "processed" layouts, produced by preprocess.cpp / quantize ops):
+// Weight layouts (this library's processed layouts, quantization.py):
 //   fp16: [N, K] (torch Linear)      int8: [N, K]      int4: [N, K/2], low nibble = even k.
+// Algorithmic bytes per launch = N*K*bytes_per_weight (+ M*(K+N)*2, < 0.1 %).
 #include "common.cuh"
 #include "kernels.h"
 
 namespace tb {
 
 enum GemvKind { kF16 = 0, kW8 = 1, kW4 = 2, kA8W8 = 3 };
+enum GemvPrologue { kProNone = 0, kProRms = 1, kProRmsQuant = 2, kProQuant = 3 };
 
 struct GemvParams {
-  const void* x;          // [M, K] fp16 (int8 for kA8W8)
+  const void* x;          // [M, K] fp16 (int8 for kA8W8 without a quantising prologue)
   const void* w;          // see layouts above
   const __half* w_scale;  // [N] fp16 per-channel (kW8/kW4)
   const float* sc;        // kA8W8: per-channel [N] or [1]
-  const float* sr;        // kA8W8: per-token [M] or [1]
+  const float* sr;        // kA8W8: per-token [M] or [1] (ignored when the prologue quantises)
   int sc_per_channel, sr_per_token;
   const __half* residual;  // optional [M, N_out]
   __half* y;               // [M, N_out]
@@ -29,10 +43,17 @@ struct GemvParams {
   int M, N, K;
   int swiglu;              // W holds [2*N_out, K]: rows [0,N_out) = gate(fc), [N_out, 2N_out) = up
   int n_out;
+  int prologue;            // GemvPrologue
+  const __half* gamma;     // [K] RMSNorm weight (prologue 1, 2)
+  float eps;
 };
 
-constexpr int kGemvThreads = 256;
-constexpr int kGemvWarps = kGemvThreads / 32;
+constexpr int kGemvConsumerWarps = 8;
+constexpr int kGemvConsumers = kGemvConsumerWarps * 32;
+constexpr int kGemvThreads = kGemvConsumers + 32;             // + one producer warp
+constexpr int kStageBytes = 16 * 1024;                        // one bulk copy (two with SwiGLU) per stage
+constexpr int kGemvStages = 4;
+constexpr int kMaxRowsPerStage = 8;
 
 template <int KIND> struct KTraits;
 template <> struct KTraits<kF16>  { static constexpr int kElemsPer16B = 8;  };
@@ -42,15 +63,27 @@ template <> struct KTraits<kA8W8> { static constexpr int kElemsPer16B = 16; };
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
 
-// dot of one 16-byte weight chunk with the matching activation chunk(s) for MB rows
+__device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kGemvConsumers) : "memory"); }
+
+// dot of one 16-byte weight chunk with the matching activation chunk(s) for MB rows.
+// xs: staged activations, row stride `xstride` bytes; k0: first k element of this chunk.
 template <int KIND, int MB>
-__device__ __forceinline__ void chunk_fma(const uint4& wq, const uint8_t* xs, int k0, int K, float (&acc)[MB],
+__device__ __forceinline__ void chunk_fma(const uint4& wq, const uint8_t* xs, int k0, int xstride, float (&acc)[MB],
                                           int (&iacc)[MB]) {
   if constexpr (KIND == kF16) {
     const __half2* w2 = reinterpret_cast<const __half2*>(&wq);
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
-      uint4 xv = *reinterpret_cast<const uint4*>(xs + ((size_t) m * K + k0) * 2);
+      uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t) m * xstride + (size_t) k0 * 2);
       const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -67,7 +100,7 @@ __device__ __forceinline__ void chunk_fma(const uint4& wq, const uint8_t* xs, in
     i8x4_to_h2x2(wq.w, wh[6], wh[7]);
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
-      const uint4* xp = reinterpret_cast<const uint4*>(xs + ((size_t) m * K + k0) * 2);
+      const uint4* xp = reinterpret_cast<const uint4*>(xs + (size_t) m * xstride + (size_t) k0 * 2);
       uint4 xa = xp[0], xb = xp[1];
       const __half2* x2a = reinterpret_cast<const __half2*>(&xa);
       const __half2* x2b = reinterpret_cast<const __half2*>(&xb);
@@ -92,7 +125,7 @@ __device__ __forceinline__ void chunk_fma(const uint4& wq, const uint8_t* xs, in
     i4x8_to_h2x4(wq.w, wh + 12);
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
-      const uint4* xp = reinterpret_cast<const uint4*>(xs + ((size_t) m * K + k0) * 2);
+      const uint4* xp = reinterpret_cast<const uint4*>(xs + (size_t) m * xstride + (size_t) k0 * 2);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 xv = xp[q];
@@ -108,7 +141,7 @@ __device__ __forceinline__ void chunk_fma(const uint4& wq, const uint8_t* xs, in
   } else {  // kA8W8
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
-      uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t) m * K + k0);
+      uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t) m * xstride + k0);
       iacc[m] = __dp4a((int) wq.x, (int) xv.x, iacc[m]);
       iacc[m] = __dp4a((int) wq.y, (int) xv.y, iacc[m]);
       iacc[m] = __dp4a((int) wq.z, (int) xv.z, iacc[m]);
@@ -117,97 +150,286 @@ __device__ __forceinline__ void chunk_fma(const uint4& wq, const uint8_t* xs, in
   }
 }
 
-// Each warp owns one output column n (two weight rows when SwiGLU is fused).  Persistent-style:
-// a CTA walks columns n = warp_global + i * total_warps so X is staged once per CTA.
+// sum / max over the 8 consumer warps (256 threads); red has 8 floats, safe to call back to back
+__device__ __forceinline__ float consumer_reduce(float v, float* red, bool is_max) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  consumer_sync();
+  if (lane == 0) red[warp] = v;
+  consumer_sync();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < kGemvConsumerWarps; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+// Stage geometry (host and device agree through these helpers): a stage holds `rps` whole weight rows
+// when a row fits (row_bytes <= kStageBytes / (SWIGLU ? 2 : 1)), else one K-piece of a single row.
+struct StageGeom {
+  int rps;          // rows per stage (per half for SwiGLU)
+  int pieces;       // K-pieces per row
+  int piece_bytes;  // bytes of a full piece (multiple of 16)
+};
+__host__ __device__ inline StageGeom stage_geom(int row_bytes, bool swiglu) {
+  const int cap = swiglu ? kStageBytes / 2 : kStageBytes;
+  StageGeom g;
+  if (row_bytes <= cap) {
+    g.rps = cap / row_bytes;
+    if (g.rps > (swiglu ? kMaxRowsPerStage / 2 : kMaxRowsPerStage)) g.rps = swiglu ? kMaxRowsPerStage / 2 : kMaxRowsPerStage;
+    g.pieces = 1;
+    g.piece_bytes = row_bytes;
+  } else {
+    g.rps = 1;
+    g.pieces = (row_bytes + cap - 1) / cap;
+    g.piece_bytes = ((row_bytes + g.pieces - 1) / g.pieces + 15) & ~15;
+  }
+  return g;
+}
+
 template <int KIND, int MB, bool SWIGLU>
-__global__ void __launch_bounds__(kGemvThreads) gemv_kernel(GemvParams p) {
-  extern __shared__ __align__(16) uint8_t xs[];
-  constexpr int EPC = KTraits<KIND>::kElemsPer16B;   // k elements per 16-byte weight chunk
+__global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int EPC = KTraits<KIND>::kElemsPer16B;     // k elements per 16-byte weight chunk
+  constexpr int XB = KIND == kA8W8 ? 1 : 2;            // bytes per staged activation element
+  constexpr int ST = kGemvStages;
+  constexpr int RMAX = kMaxRowsPerStage;               // weight rows per stage (gate + up rows for SwiGLU)
+  uint8_t* ring = smem;                                 // [ST][kStageBytes]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + ST * kStageBytes);
+  uint64_t* empty = full + ST;
+  float* red = reinterpret_cast<float*>(empty + ST);    // [8] reduction scratch
+  float* srow = red + 8;                                // [4] per-token scales produced by a quantising prologue
+  float* part = srow + 4;                               // [2][RMAX * MB][8] per-warp partial sums, double-buffered
+  uint8_t* xs = reinterpret_cast<uint8_t*>(part + 2 * RMAX * MB * kGemvConsumerWarps);   // [MB][K * XB]
+
   const int K = p.K;
-  const int x_bytes = p.M * K * (KIND == kA8W8 ? 1 : 2);
-  const int xs_bytes = MB * K * (KIND == kA8W8 ? 1 : 2);    // rows [M, MB) are zero-filled
-  for (int i = threadIdx.x * 16; i < xs_bytes; i += kGemvThreads * 16)
-    *reinterpret_cast<uint4*>(xs + i) =
-        i < x_bytes ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + i) : make_uint4(0, 0, 0, 0);
+  const int xstride = K * XB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_bytes = K / EPC * 16;
+  const StageGeom geo = stage_geom(row_bytes, SWIGLU);
+  // balanced contiguous split of the output rows over the persistent CTAs (row granularity: <= 1 row of imbalance)
+  const int n0 = (int) ((long long) p.n_out * blockIdx.x / gridDim.x);
+  const int n1 = (int) ((long long) p.n_out * (blockIdx.x + 1) / gridDim.x);
+  const int nsteps = (n1 - n0 + geo.rps - 1) / geo.rps;   // row-steps; each is `pieces` stages
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kGemvConsumerWarps);
+    }
+    fence_barrier_init();
+  }
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int total_warps = gridDim.x * kGemvWarps;
-  const int chunks = K / EPC;                         // 16-byte chunks per weight row
-  const size_t row_bytes = (size_t) chunks * 16;
-  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
-  constexpr int R = SWIGLU ? 2 : 1;
-
-  for (int n = blockIdx.x * kGemvWarps + warp; n < p.n_out; n += total_warps) {
-    float acc[R][MB];
-    int iacc[R][MB];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int m = 0; m < MB; ++m) { acc[r][m] = 0.f; iacc[r][m] = 0; }
-    const uint8_t* wr[R];
-    wr[0] = wbase + (size_t) n * row_bytes;
-    if constexpr (SWIGLU) wr[1] = wbase + (size_t) (n + p.n_out) * row_bytes;
-
-    constexpr int U = SWIGLU ? 4 : 8;                 // chunks in flight per lane per row
-    int c = lane;
-    for (; c + 32 * (U - 1) < chunks; c += 32 * U) {
-      uint4 wq[R][U];
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int u = 0; u < U; ++u) wq[r][u] = ldg_nc_v4(wr[r] + (size_t) (c + 32 * u) * 16);
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int u = 0; u < U; ++u) chunk_fma<KIND, MB>(wq[r][u], xs, (c + 32 * u) * EPC, K, acc[r], iacc[r]);
-    }
-    for (; c < chunks; c += 32) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        uint4 wq = ldg_nc_v4(wr[r] + (size_t) c * 16);
-        chunk_fma<KIND, MB>(wq, xs, c * EPC, K, acc[r], iacc[r]);
-      }
-    }
-    // reduce across the warp, lane 0 applies the epilogue
-    float res[R][MB];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int m = 0; m < MB; ++m) {
-        if constexpr (KIND == kA8W8) {
-          int v = iacc[r][m];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          res[r][m] = (float) v;
-        } else {
-          res[r][m] = warp_sum(acc[r][m]);
+  if (warp == kGemvConsumerWarps) {
+    // =========================== producer: stream this CTA's weight rows ===========================
+    // consecutive rows are contiguous in memory, so a stage is ONE bulk copy (gate rows + up rows: two)
+    if (lane == 0) {
+      const uint64_t pol = policy_evict_first();
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
+      int stage = 0, phase = 0;
+      for (int st = 0; st < nsteps; ++st) {
+        const int r = n0 + st * geo.rps;
+        const int nr = min(geo.rps, n1 - r);
+        for (int pc = 0; pc < geo.pieces; ++pc) {
+          const int off = pc * geo.piece_bytes;
+          const int pb = min(geo.piece_bytes, row_bytes - off);
+          const uint32_t bytes = geo.pieces == 1 ? (uint32_t) nr * row_bytes : (uint32_t) pb;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* dst = ring + stage * kStageBytes;
+          mbar_expect_tx(&full[stage], SWIGLU ? 2 * bytes : bytes);
+          bulk_load_1d_hint(dst, wbase + (size_t) r * row_bytes + off, bytes, &full[stage], pol);
+          if (SWIGLU)
+            bulk_load_1d_hint(dst + kStageBytes / 2, wbase + (size_t) (r + p.n_out) * row_bytes + off, bytes, &full[stage], pol);
+          if (++stage == ST) { stage = 0; phase ^= 1; }
         }
       }
-    if (lane == 0) {
+    }
+    return;
+  }
+
+  // =========================== consumers ==========================================================
+  // activations come from the upstream kernel: wait for it (weights are already streaming), then let
+  // the downstream kernel start its own prefetch as early as resources allow
+  pdl_wait();
+  pdl_launch_dependents();
+  const int ctid = threadIdx.x;                         // 0..255
+  if (p.prologue == kProNone) {
+    const int x_bytes = p.M * xstride, xs_bytes = MB * xstride;     // rows [M, MB) are zero-filled
+    for (int i = ctid * 16; i < xs_bytes; i += kGemvConsumers * 16)
+      *reinterpret_cast<uint4*>(xs + i) =
+          i < x_bytes ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + i) : make_uint4(0, 0, 0, 0);
+    if (KIND == kA8W8 && ctid < 4) srow[ctid] = ctid < p.M ? p.sr[p.sr_per_token ? ctid : 0] : 0.f;
+  } else {
+    // x is fp16 [M, K]; per row: (RMSNorm ->) fp16 (-> dynamic int8).  Same arithmetic as norm_quant.cu.
+    const __half* xin = reinterpret_cast<const __half*>(p.x);
+    for (int m = 0; m < MB; ++m) {
+      if (m >= p.M) {
+        for (int i = ctid * 16; i < xstride; i += kGemvConsumers * 16)
+          *reinterpret_cast<uint4*>(xs + (size_t) m * xstride + i) = make_uint4(0, 0, 0, 0);
+        if (ctid == 0) srow[m] = 0.f;
+        continue;
+      }
+      const __half* xr = xin + (size_t) m * K;
+      float inv = 1.f;
+      if (p.prologue != kProQuant) {
+        float sq = 0.f;
+        for (int i = ctid * 8; i < K; i += kGemvConsumers * 8) {
+          uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
+          const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-      for (int m = 0; m < MB; ++m) {
-        if (m >= p.M) break;
-        float v[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int nr = n + r * p.n_out;
-          v[r] = res[r][m];
-          if constexpr (KIND == kW8 || KIND == kW4) v[r] *= __half2float(p.w_scale[nr]);
-          if constexpr (KIND == kA8W8) {
-            // reference grouping: accum * (scale_col * scale_row)  (epilogue_per_row_per_col_scale.h:325,341)
-            const float scv = p.sc[p.sc_per_channel ? nr : 0], srv = p.sr[p.sr_per_token ? m : 0];
-            v[r] = v[r] * (scv * srv);
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(h[j]);
+            sq += f.x * f.x + f.y * f.y;
           }
         }
+        sq = consumer_reduce(sq, red, false);
+        inv = rsqrtf(sq / K + p.eps);
+      }
+      float amax = 0.f;
+      for (int i = ctid * 8; i < K; i += kGemvConsumers * 8) {
+        uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
+        __half2* h = reinterpret_cast<__half2*>(&raw);
+        if (p.prologue != kProQuant) {
+          uint4 g4 = *reinterpret_cast<const uint4*>(p.gamma + i);
+          const __half2* g = reinterpret_cast<const __half2*>(&g4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(h[j]), gg = __half22float2(g[j]);
+            h[j] = __floats2half2_rn(f.x * inv * gg.x, f.y * inv * gg.y);
+          }
+        }
+        if constexpr (KIND == kA8W8) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(h[j]);
+            amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+          }
+        } else {
+          *reinterpret_cast<uint4*>(xs + (size_t) m * xstride + (size_t) i * 2) = raw;
+        }
+      }
+      if constexpr (KIND == kA8W8) {
+        amax = fmaxf(consumer_reduce(amax, red, true), __half2float(__float2half_rn(1e-6f)));
+        const float qs = 127.f / amax;
+        if (ctid == 0) srow[m] = amax / 127.f;
+        for (int i = ctid * 8; i < K; i += kGemvConsumers * 8) {
+          uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
+          __half2* h = reinterpret_cast<__half2*>(&raw);
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 t = __half22float2(h[j]);
+            if (p.prologue != kProQuant) {
+              float2 gg = __half22float2(reinterpret_cast<const __half2*>(p.gamma + i)[j]);
+              t = __half22float2(__floats2half2_rn(t.x * inv * gg.x, t.y * inv * gg.y));
+            }
+            f[2 * j] = t.x * qs;
+            f[2 * j + 1] = t.y * qs;
+          }
+          uint2 o;
+          o.x = pack4_i8(f[0], f[1], f[2], f[3]);
+          o.y = pack4_i8(f[4], f[5], f[6], f[7]);
+          *reinterpret_cast<uint2*>(xs + (size_t) m * xstride + i) = o;
+        }
+      }
+    }
+  }
+  consumer_sync();
+
+  // Split-K inside the CTA: consumer thread t owns the 16-byte chunks c = t + 256*j of every row (of every
+  // piece); the eight per-warp partial sums of a row are combined through shared memory in warp order.
+  int stage = 0, phase = 0, buf = 0;
+  const int rows_w = SWIGLU ? 2 * geo.rps : geo.rps;            // weight rows resident per stage
+  for (int st = 0; st < nsteps; ++st) {
+    const int r = n0 + st * geo.rps;
+    const int nr = min(geo.rps, n1 - r);
+    float acc[RMAX][MB];
+    int iacc[RMAX][MB];
+#pragma unroll
+    for (int a = 0; a < RMAX; ++a)
+#pragma unroll
+      for (int m = 0; m < MB; ++m) { acc[a][m] = 0.f; iacc[a][m] = 0; }
+
+    for (int pc = 0; pc < geo.pieces; ++pc) {
+      const int off = pc * geo.piece_bytes;
+      const int pchunks = min(geo.piece_bytes, row_bytes - off) >> 4;
+      const int kbase = (off >> 4) * EPC;
+      mbar_wait(&full[stage], phase);
+      const uint8_t* sbase = ring + stage * kStageBytes;
+      for (int c = ctid; c < pchunks; c += kGemvConsumers) {
+        const int k0 = kbase + c * EPC;
+#pragma unroll
+        for (int a = 0; a < RMAX; ++a) {
+          if (a < rows_w) {
+            // SwiGLU: rows [0, rps) are gate rows, [rps, 2*rps) the matching up rows (second half of the stage)
+            const int rr = SWIGLU ? (a < geo.rps ? a : a - geo.rps) : a;
+            const uint8_t* rowp = (SWIGLU && a >= geo.rps ? sbase + kStageBytes / 2 : sbase) + (size_t) rr * row_bytes * (geo.pieces == 1);
+            if (rr < nr) {
+              const uint4 wq = *reinterpret_cast<const uint4*>(rowp + c * 16);
+              chunk_fma<KIND, MB>(wq, xs, k0, xstride, acc[a], iacc[a]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == ST) { stage = 0; phase ^= 1; }
+    }
+
+    // per-warp partials -> shared memory -> one thread per (row, m) sums the eight in warp order
+    float* pb = part + buf * (RMAX * MB * kGemvConsumerWarps);
+#pragma unroll
+    for (int a = 0; a < RMAX; ++a) {
+      if (a < rows_w) {
+#pragma unroll
+        for (int m = 0; m < MB; ++m) {
+          float v;
+          if constexpr (KIND == kA8W8) {
+            int iv = iacc[a][m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) iv += __shfl_xor_sync(0xffffffffu, iv, o);
+            v = __int_as_float(iv);
+          } else {
+            v = warp_sum(acc[a][m]);
+          }
+          if (lane == 0) pb[(a * MB + m) * kGemvConsumerWarps + warp] = v;
+        }
+      }
+    }
+    consumer_sync();
+    if (ctid < nr * MB) {
+      const int rr = ctid / MB, m = ctid % MB;
+      if (m < p.M) {
+        auto total = [&](int a) -> float {
+          const float* q = pb + (a * MB + m) * kGemvConsumerWarps;
+          if constexpr (KIND == kA8W8) {
+            int t = 0;
+#pragma unroll
+            for (int w = 0; w < kGemvConsumerWarps; ++w) t += __float_as_int(q[w]);
+            return (float) t;
+          } else {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kGemvConsumerWarps; ++w) t += q[w];
+            return t;
+          }
+        };
+        auto scaled = [&](float v, int nrow) -> float {
+          if constexpr (KIND == kW8 || KIND == kW4) v *= __half2float(p.w_scale[nrow]);
+          // reference grouping: accum * (scale_col * scale_row)  (epilogue_per_row_per_col_scale.h:325,341)
+          if constexpr (KIND == kA8W8) v = v * (p.sc[p.sc_per_channel ? nrow : 0] * srow[m]);
+          return v;
+        };
+        const int n = r + rr;
+        const size_t oi = (size_t) m * p.n_out + n;
         float o;
         if constexpr (SWIGLU) {
-          const float g = __half2float(__float2half_rn(v[0])), u = __half2float(__float2half_rn(v[1]));
-          o = __half2float(__float2half_rn(silu_f(g))) * u;
+          const float gte = __half2float(__float2half_rn(scaled(total(rr), n)));
+          const float up = __half2float(__float2half_rn(scaled(total(geo.rps + rr), n + p.n_out)));
+          o = __half2float(__float2half_rn(silu_f(gte))) * up;
         } else {
-          o = v[0];
+          o = scaled(total(rr), n);
         }
-        const size_t oi = (size_t) m * p.n_out + n;
         if (p.y_f32) {
           p.y_f32[oi] = o;
         } else {
@@ -217,25 +439,37 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(GemvParams p) {
         }
       }
     }
+    buf ^= 1;
   }
 }
 
 template <int KIND, int MB, bool SWIGLU>
 static int launch_gemv_t(const GemvParams& p, cudaStream_t stream) {
-  const size_t smem = (size_t) MB * p.K * (KIND == kA8W8 ? 1 : 2);
+  const size_t xs_bytes = (size_t) MB * p.K * (KIND == kA8W8 ? 1 : 2);
+  const size_t smem = (size_t) kGemvStages * kStageBytes + 2 * kGemvStages * sizeof(uint64_t) +
+                      (12 + 2 * kMaxRowsPerStage * MB * kGemvConsumerWarps) * sizeof(float) + xs_bytes;
+  if (smem > 220 * 1024) return -2;
   auto kern = gemv_kernel<KIND, MB, SWIGLU>;
-  if (smem > 48 * 1024) {
-    if (smem > 200 * 1024) return -2;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  static bool attr_done = false;   // per template instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return (int) e;
+    attr_done = true;
   }
-  // persistent grid: a multiple of the SM count, capped by the number of columns
-  int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
-  int grid = kNumSMs * per_sm;
-  const int need = (p.n_out + kGemvWarps - 1) / kGemvWarps;
-  if (grid > need) grid = need;
-  kern<<<grid, kGemvThreads, smem, stream>>>(p);
-  return (int) cudaGetLastError();
+  // persistent grid: two CTAs per SM when the staged activations leave room, capped by the work
+  int grid = kNumSMs * (smem <= 110 * 1024 ? 2 : 1);
+  if (grid > p.n_out) grid = p.n_out;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int) cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 template <int KIND, bool SWIGLU>
@@ -250,18 +484,25 @@ static int launch_gemv_m(const GemvParams& p, cudaStream_t stream) {
 
 using namespace tb;
 
-extern "C" int tb_gemv(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale,
-                       const float* sc, const float* sr, int sc_per_channel, int sr_per_token, const void* residual,
-                       int M, int N, int K, int swiglu, cudaStream_t stream) {
+extern "C" int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale,
+                             const float* sc, const float* sr, int sc_per_channel, int sr_per_token, const void* residual,
+                             int M, int N, int K, int swiglu, int prologue, const void* gamma, float eps,
+                             cudaStream_t stream) {
   GemvParams p{};
   p.x = x; p.w = w; p.w_scale = (const __half*) w_scale; p.sc = sc; p.sr = sr;
   p.sc_per_channel = sc_per_channel; p.sr_per_token = sr_per_token; p.residual = (const __half*) residual;
   p.y = (__half*) y; p.y_f32 = y_f32; p.M = M; p.N = N; p.K = K; p.swiglu = swiglu;
   p.n_out = swiglu ? N / 2 : N;
+  p.prologue = prologue; p.gamma = (const __half*) gamma; p.eps = eps;
   const int epc = kind == kF16 ? 8 : (kind == kW4 ? 32 : 16);
   if (M < 1 || M > 4 || K % epc != 0 || (swiglu && (N & 1))) return -1;
   if ((kind == kW8 || kind == kW4) && !w_scale) return -1;
-  if (kind == kA8W8 && (!sc || !sr)) return -1;
+  if (kind == kA8W8 && (!sc || (prologue < kProRmsQuant && !sr))) return -1;
+  if (prologue < 0 || prologue > 3) return -1;
+  if ((prologue == kProRms || prologue == kProRmsQuant) && !gamma) return -1;
+  if ((prologue >= kProRmsQuant) != (kind == kA8W8) && prologue != kProNone && prologue != kProRms) return -1;
+  if (prologue == kProRms && kind == kA8W8) return -1;
+  if (swiglu && residual) return -1;
   switch (kind) {
     case kF16:  return swiglu ? launch_gemv_m<kF16, true>(p, stream)  : launch_gemv_m<kF16, false>(p, stream);
     case kW8:   return swiglu ? launch_gemv_m<kW8, true>(p, stream)   : launch_gemv_m<kW8, false>(p, stream);
@@ -269,4 +510,11 @@ extern "C" int tb_gemv(int kind, void* y, float* y_f32, const void* x, const voi
     case kA8W8: return swiglu ? launch_gemv_m<kA8W8, true>(p, stream) : launch_gemv_m<kA8W8, false>(p, stream);
   }
   return -1;
+}
+
+extern "C" int tb_gemv(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale,
+                       const float* sc, const float* sr, int sc_per_channel, int sr_per_token, const void* residual,
+                       int M, int N, int K, int swiglu, cudaStream_t stream) {
+  return tb_gemv_fused(kind, y, y_f32, x, w, w_scale, sc, sr, sc_per_channel, sr_per_token, residual, M, N, K, swiglu,
+                       kProNone, nullptr, 0.f, stream);
 }

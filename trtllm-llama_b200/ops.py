@@ -100,8 +100,12 @@ def quantize_tensor(x, scale):
 
 
 # ------------------------------------------------------------------------------------------------
-def gemv(kind, x, w, *, w_scale=None, sc=None, sr=None, residual=None, swiglu=False, out_fp32=False):
-    _chk_cuda(x, w, w_scale, sc, sr, residual)
+PRO_NONE, PRO_RMS, PRO_RMS_QUANT, PRO_QUANT = 0, 1, 2, 3
+
+
+def gemv(kind, x, w, *, w_scale=None, sc=None, sr=None, residual=None, swiglu=False, out_fp32=False, prologue=0,
+         gamma=None, eps=1e-6):
+    _chk_cuda(x, w, w_scale, sc, sr, residual, gamma)
     M, K = x.numel() // x.shape[-1], x.shape[-1]
     N = w.shape[0]
     n_out = N // 2 if swiglu else N
@@ -111,9 +115,9 @@ def gemv(kind, x, w, *, w_scale=None, sc=None, sr=None, residual=None, swiglu=Fa
     else:
         y = torch.empty(x.shape[:-1] + (n_out,), dtype=torch.float16, device=x.device)
         y32 = None
-    check(lib.tb_gemv(kind, _p(y), _p(y32), _p(x), _p(w), _p(w_scale), _p(sc), _p(sr),
-                      int(sc is not None and sc.numel() > 1), int(sr is not None and sr.numel() > 1), _p(residual),
-                      M, N, K, int(swiglu), _stream()), "tb_gemv")
+    check(lib.tb_gemv_fused(kind, _p(y), _p(y32), _p(x), _p(w), _p(w_scale), _p(sc), _p(sr),
+                            int(sc is not None and sc.numel() > 1), int(sr is not None and sr.numel() > 1), _p(residual),
+                            M, N, K, int(swiglu), int(prologue), _p(gamma), float(eps), _stream()), "tb_gemv_fused")
     return y32 if out_fp32 else y
 
 
