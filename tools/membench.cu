@@ -40,6 +40,28 @@ __global__ void ldg_rows(const uint4* __restrict__ p, int rows, int row16, unsig
   if (acc == 0x12345) *out = acc;
 }
 
+// MMA-fragment pattern: a warp owns 16 rows; per k-step lane (g = lane/4, t = lane%4) loads 16 B from row g and row g+8
+// at byte offset kstep*64 + t*16  (each instruction touches 8 rows x 64 contiguous bytes)
+template <int U>
+__global__ void ldg_frag(const uint4* __restrict__ p, int rows, int row16, unsigned* out) {
+  unsigned acc = 0;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+  const int ksteps = row16 / 4;
+  for (int r0 = gw * 16; r0 < rows; r0 += tw * 16) {
+    const uint4* lo = p + (size_t) (r0 + g) * row16 + t;
+    const uint4* hi = p + (size_t) (r0 + g + 8) * row16 + t;
+    for (int ks = 0; ks < ksteps; ks += U) {
+      uint4 a[U], b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { a[u] = ldg_nc_v4(lo + (ks + u) * 4); b[u] = ldg_nc_v4(hi + (ks + u) * 4); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc += a[u].x ^ a[u].y ^ a[u].z ^ a[u].w ^ b[u].x ^ b[u].y ^ b[u].z ^ b[u].w;
+    }
+  }
+  if (acc == 0x12345) *out = acc;
+}
+
 __device__ __forceinline__ void bulk_ld(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
@@ -118,6 +140,12 @@ int main() {
     for (int bps : {4, 6, 8}) {
       float ms = time_it([&] { ldg_rows<8><<<148 * bps, 256>>>((const uint4*) next(), (int) (sz / 8192), 512, out); });
       printf("ldg_rows (8KB rows) U=8 blocks/SM=%d : %.2f us  %.0f GB/s\n", bps, ms * 1e3, sz / ms / 1e6);
+    }
+    for (int bps : {2, 3, 4}) {
+      float ms = time_it([&] { ldg_frag<4><<<148 * bps, 256>>>((const uint4*) next(), (int) (sz / 8192), 512, out); });
+      printf("ldg_frag (16 rows x 64B) U=4 blocks/SM=%d : %.2f us  %.0f GB/s\n", bps, ms * 1e3, sz / ms / 1e6);
+      ms = time_it([&] { ldg_frag<8><<<148 * bps, 256>>>((const uint4*) next(), (int) (sz / 8192), 512, out); });
+      printf("ldg_frag (16 rows x 64B) U=8 blocks/SM=%d : %.2f us  %.0f GB/s\n", bps, ms * 1e3, sz / ms / 1e6);
     }
     cudaFuncSetAttribute(bulk_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     struct C { int grid_per_sm, stage, nst, ncopies; };

@@ -388,7 +388,8 @@ static int launch_gemm_tc(GemmTcParams p, const void* x, const void* w, void* wo
   const int base_items = p.n_tiles * p.m_tiles;
   if (force_splits > 0) {
     splits = force_splits;
-  } else if (base_items < kNumSMs) {
+  } else if (base_items < kNumSMs && NT <= 32) {
+    // split-K only for decode-like shapes: the in-order partial-sum reduction is serial in the token dimension
     splits = (2 * kNumSMs + base_items - 1) / base_items;
     const int max_by_k = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
     if (splits > max_by_k) splits = max_by_k;
@@ -411,11 +412,19 @@ static int launch_gemm_tc(GemmTcParams p, const void* x, const void* w, void* wo
   return (int) cudaGetLastError();
 }
 
+// token-tile width: the smallest of 16..256 covering M; prefill-like shapes shrink it until the grid covers the SMs
+static int select_nt(int M, int N) {
+  int nt = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256)));
+  const int n_tiles = (N + kTileN - 1) / kTileN;
+  while (nt > 32 && n_tiles * ((M + nt - 1) / nt) < kNumSMs) nt >>= 1;
+  return nt;
+}
+
 template <int KIND>
 static int dispatch_nt(const GemmTcParams& p, const void* x, const void* w, void* ws, size_t ws_bytes, int* counters,
                        int force_splits, int force_nt, cudaStream_t stream) {
   int nt = force_nt;
-  if (nt <= 0) nt = p.M <= 16 ? 16 : (p.M <= 32 ? 32 : (p.M <= 64 ? 64 : (p.M <= 128 ? 128 : 256)));
+  if (nt <= 0) nt = select_nt(p.M, p.N);
   switch (nt) {
     case 16:  return launch_gemm_tc<KIND, 16>(p, x, w, ws, ws_bytes, counters, force_splits, stream);
     case 32:  return launch_gemm_tc<KIND, 32>(p, x, w, ws, ws_bytes, counters, force_splits, stream);
@@ -433,13 +442,13 @@ using namespace tb;
 extern "C" {
 
 size_t tb_gemm_tc_workspace_bytes(int M, int N, int K) {
-  // worst case: splits so that items ~ 2*148, NT = 16 for the shapes that split
+  // upper bound of what launch_gemm_tc uses: same tile selection, split count before the k-block caps
   (void) K;
   const int n_tiles = (N + kTileN - 1) / kTileN;
-  const int nt = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256)));
+  const int nt = select_nt(M, N);
   const int m_tiles = (M + nt - 1) / nt;
   const size_t base = (size_t) n_tiles * m_tiles;
-  size_t splits = base < (size_t) kNumSMs ? (2 * kNumSMs + base - 1) / base : 1;
+  size_t splits = (base < (size_t) kNumSMs && nt <= 32) ? (2 * kNumSMs + base - 1) / base : 1;
   return base * splits * nt * kTileN * sizeof(float) + 256;
 }
 size_t tb_gemm_tc_counter_bytes(void) { return (size_t) kGemmMaxCounters * sizeof(int); }

@@ -1,13 +1,14 @@
 // Decode-shape (M <= 4 token rows) projection: Y[M,N] = X[M,K] . W[N,K]^T, the kernel that streams the
 // model's weights once per generated token and therefore bounds decode tokens/s (HBM roofline).
 //
-// sm_100a design: persistent CTAs (2 per SM), each owning a contiguous, balanced range of output rows.
-// One producer thread streams that range through a 5-stage shared-memory ring with bulk async copies
-// (cp.async.bulk global -> shared, completion on an mbarrier, L2 evict-first: every weight byte is used once);
-// eight consumer warps read the staged 1-KB row segments with conflict-free 16-byte LDS, accumulate in fp32
-// (int32 dp4a for W8A8) and apply the fused epilogue (per-channel / per-token scales, SwiGLU, residual add).
-// ~80 KB of loads are in flight per CTA without holding registers, which is what a latency x bandwidth
-// product of ~5 MB across 148 SMs asks for.
+// sm_100a design (measured with tools/membench.cu on this pool's B200s: a ring of cp.async.bulk copies tops out
+// at ~6.1 TB/s with a ~4 us ramp because every stage is a dependent round trip, while plain 16-byte LDG streams
+// with >= 128 KB in flight per SM reach 7.3 TB/s with no ramp): one warp per output row, rows dealt round-robin
+// so that at any instant the whole chip reads one contiguous window of the weight matrix; each lane keeps TWO
+// batches of 16-byte loads in flight (software-pipelined registers), so the FMA / shuffle-reduce work of one
+// batch always overlaps the HBM latency of the next, across row boundaries; activations are staged once per
+// CTA in shared memory; fp32 accumulation (int32 dp4a for W8A8); fused epilogue (per-channel / per-token
+// scales, SwiGLU, residual add).
 // Fused prologues (the TensorRT-native glue / extra plugins of the reference):
 //   RMSNorm of the residual stream, RMSNorm + dynamic per-token int8 quantisation (RmsnormQuantization),
 //   plain dynamic per-token quantisation (QuantizePerToken) — each CTA recomputes the row statistics of the
@@ -48,12 +49,9 @@ struct GemvParams {
   float eps;
 };
 
-constexpr int kGemvConsumerWarps = 8;
-constexpr int kGemvConsumers = kGemvConsumerWarps * 32;
-constexpr int kGemvThreads = kGemvConsumers + 32;             // + one producer warp
-constexpr int kStageBytes = 16 * 1024;                        // one bulk copy (two with SwiGLU) per stage
-constexpr int kGemvStages = 4;
-constexpr int kMaxRowsPerStage = 8;
+constexpr int kGemvThreads = 256;
+constexpr int kGemvWarps = kGemvThreads / 32;
+constexpr int kGemvU = 8;                                     // 16-byte weight loads in flight per lane
 
 template <int KIND> struct KTraits;
 template <> struct KTraits<kF16>  { static constexpr int kElemsPer16B = 8;  };
@@ -63,16 +61,8 @@ template <> struct KTraits<kA8W8> { static constexpr int kElemsPer16B = 16; };
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
 
-__device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
-                                                  uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kGemvConsumers) : "memory"); }
 
 // dot of one 16-byte weight chunk with the matching activation chunk(s) for MB rows.
 // xs: staged activations, row stride `xstride` bytes; k0: first k element of this chunk.
@@ -150,130 +140,64 @@ __device__ __forceinline__ void chunk_fma(const uint4& wq, const uint8_t* xs, in
   }
 }
 
-// sum / max over the 8 consumer warps (256 threads); red has 8 floats, safe to call back to back
-__device__ __forceinline__ float consumer_reduce(float v, float* red, bool is_max) {
+// sum / max over the CTA; red has kGemvWarps floats, safe to call back to back
+__device__ __forceinline__ float cta_reduce(float v, float* red, bool is_max) {
   v = is_max ? warp_max(v) : warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  consumer_sync();
+  __syncthreads();
   if (lane == 0) red[warp] = v;
-  consumer_sync();
+  __syncthreads();
   float r = red[0];
 #pragma unroll
-  for (int w = 1; w < kGemvConsumerWarps; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  for (int w = 1; w < kGemvWarps; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
   return r;
 }
 
-// Stage geometry (host and device agree through these helpers): a stage holds `rps` whole weight rows
-// when a row fits (row_bytes <= kStageBytes / (SWIGLU ? 2 : 1)), else one K-piece of a single row.
-struct StageGeom {
-  int rps;          // rows per stage (per half for SwiGLU)
-  int pieces;       // K-pieces per row
-  int piece_bytes;  // bytes of a full piece (multiple of 16)
-};
-__host__ __device__ inline StageGeom stage_geom(int row_bytes, bool swiglu) {
-  const int cap = swiglu ? kStageBytes / 2 : kStageBytes;
-  StageGeom g;
-  if (row_bytes <= cap) {
-    g.rps = cap / row_bytes;
-    if (g.rps > (swiglu ? kMaxRowsPerStage / 2 : kMaxRowsPerStage)) g.rps = swiglu ? kMaxRowsPerStage / 2 : kMaxRowsPerStage;
-    g.pieces = 1;
-    g.piece_bytes = row_bytes;
-  } else {
-    g.rps = 1;
-    g.pieces = (row_bytes + cap - 1) / cap;
-    g.piece_bytes = ((row_bytes + g.pieces - 1) / g.pieces + 15) & ~15;
-  }
-  return g;
-}
-
 template <int KIND, int MB, bool SWIGLU>
-__global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvParams p) {
+__global__ void __launch_bounds__(kGemvThreads, (MB >= 4 ? 2 : 4)) gemv_kernel(const GemvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int EPC = KTraits<KIND>::kElemsPer16B;     // k elements per 16-byte weight chunk
   constexpr int XB = KIND == kA8W8 ? 1 : 2;            // bytes per staged activation element
-  constexpr int ST = kGemvStages;
-  constexpr int RMAX = kMaxRowsPerStage;               // weight rows per stage (gate + up rows for SwiGLU)
-  uint8_t* ring = smem;                                 // [ST][kStageBytes]
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring + ST * kStageBytes);
-  uint64_t* empty = full + ST;
-  float* red = reinterpret_cast<float*>(empty + ST);    // [8] reduction scratch
-  float* srow = red + 8;                                // [4] per-token scales produced by a quantising prologue
-  float* part = srow + 4;                               // [2][RMAX * MB][8] per-warp partial sums, double-buffered
-  uint8_t* xs = reinterpret_cast<uint8_t*>(part + 2 * RMAX * MB * kGemvConsumerWarps);   // [MB][K * XB]
+  constexpr int U = kGemvU;
+  float* red = reinterpret_cast<float*>(smem);          // [8] reduction scratch
+  float* srow = red + 8;                                // [4] per-token scales (W8A8)
+  uint8_t* xs = reinterpret_cast<uint8_t*>(srow + 8);   // [MB][K * XB] staged activations
 
   const int K = p.K;
   const int xstride = K * XB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_bytes = K / EPC * 16;
-  const StageGeom geo = stage_geom(row_bytes, SWIGLU);
-  // balanced contiguous split of the output rows over the persistent CTAs (row granularity: <= 1 row of imbalance)
-  const int n0 = (int) ((long long) p.n_out * blockIdx.x / gridDim.x);
-  const int n1 = (int) ((long long) p.n_out * (blockIdx.x + 1) / gridDim.x);
-  const int nsteps = (n1 - n0 + geo.rps - 1) / geo.rps;   // row-steps; each is `pieces` stages
+  const int cpr = K / EPC;                              // 16-byte chunks per weight row
+  const size_t row_bytes = (size_t) cpr * 16;
+  const int gw = blockIdx.x * kGemvWarps + warp, tw = gridDim.x * kGemvWarps;
+  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < ST; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kGemvConsumerWarps);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-
-  if (warp == kGemvConsumerWarps) {
-    // =========================== producer: stream this CTA's weight rows ===========================
-    // consecutive rows are contiguous in memory, so a stage is ONE bulk copy (gate rows + up rows: two)
-    if (lane == 0) {
-      const uint64_t pol = policy_evict_first();
-      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
-      int stage = 0, phase = 0;
-      for (int st = 0; st < nsteps; ++st) {
-        const int r = n0 + st * geo.rps;
-        const int nr = min(geo.rps, n1 - r);
-        for (int pc = 0; pc < geo.pieces; ++pc) {
-          const int off = pc * geo.piece_bytes;
-          const int pb = min(geo.piece_bytes, row_bytes - off);
-          const uint32_t bytes = geo.pieces == 1 ? (uint32_t) nr * row_bytes : (uint32_t) pb;
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* dst = ring + stage * kStageBytes;
-          mbar_expect_tx(&full[stage], SWIGLU ? 2 * bytes : bytes);
-          bulk_load_1d_hint(dst, wbase + (size_t) r * row_bytes + off, bytes, &full[stage], pol);
-          if (SWIGLU)
-            bulk_load_1d_hint(dst + kStageBytes / 2, wbase + (size_t) (r + p.n_out) * row_bytes + off, bytes, &full[stage], pol);
-          if (++stage == ST) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-    return;
-  }
-
-  // =========================== consumers ==========================================================
-  // activations come from the upstream kernel: wait for it (weights are already streaming), then let
-  // the downstream kernel start its own prefetch as early as resources allow
+  // activations come from the upstream kernel (programmatic dependent launch: this grid may already be
+  // resident while it drains); let the downstream kernel start its own launch as early as resources allow
   pdl_wait();
   pdl_launch_dependents();
-  const int ctid = threadIdx.x;                         // 0..255
+
+  const int tid = threadIdx.x;
   if (p.prologue == kProNone) {
     const int x_bytes = p.M * xstride, xs_bytes = MB * xstride;     // rows [M, MB) are zero-filled
-    for (int i = ctid * 16; i < xs_bytes; i += kGemvConsumers * 16)
+    for (int i = tid * 16; i < xs_bytes; i += kGemvThreads * 16)
       *reinterpret_cast<uint4*>(xs + i) =
           i < x_bytes ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.x) + i) : make_uint4(0, 0, 0, 0);
-    if (KIND == kA8W8 && ctid < 4) srow[ctid] = ctid < p.M ? p.sr[p.sr_per_token ? ctid : 0] : 0.f;
+    if (KIND == kA8W8 && tid < 4) srow[tid] = tid < p.M ? p.sr[p.sr_per_token ? tid : 0] : 0.f;
   } else {
     // x is fp16 [M, K]; per row: (RMSNorm ->) fp16 (-> dynamic int8).  Same arithmetic as norm_quant.cu.
     const __half* xin = reinterpret_cast<const __half*>(p.x);
     for (int m = 0; m < MB; ++m) {
       if (m >= p.M) {
-        for (int i = ctid * 16; i < xstride; i += kGemvConsumers * 16)
+        for (int i = tid * 16; i < xstride; i += kGemvThreads * 16)
           *reinterpret_cast<uint4*>(xs + (size_t) m * xstride + i) = make_uint4(0, 0, 0, 0);
-        if (ctid == 0) srow[m] = 0.f;
+        if (tid == 0) srow[m] = 0.f;
         continue;
       }
       const __half* xr = xin + (size_t) m * K;
       float inv = 1.f;
       if (p.prologue != kProQuant) {
         float sq = 0.f;
-        for (int i = ctid * 8; i < K; i += kGemvConsumers * 8) {
+        for (int i = tid * 8; i < K; i += kGemvThreads * 8) {
           uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
           const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
@@ -282,11 +206,11 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvParams 
             sq += f.x * f.x + f.y * f.y;
           }
         }
-        sq = consumer_reduce(sq, red, false);
+        sq = cta_reduce(sq, red, false);
         inv = rsqrtf(sq / K + p.eps);
       }
       float amax = 0.f;
-      for (int i = ctid * 8; i < K; i += kGemvConsumers * 8) {
+      for (int i = tid * 8; i < K; i += kGemvThreads * 8) {
         uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
         __half2* h = reinterpret_cast<__half2*>(&raw);
         if (p.prologue != kProQuant) {
@@ -309,10 +233,10 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvParams 
         }
       }
       if constexpr (KIND == kA8W8) {
-        amax = fmaxf(consumer_reduce(amax, red, true), __half2float(__float2half_rn(1e-6f)));
+        amax = fmaxf(cta_reduce(amax, red, true), __half2float(__float2half_rn(1e-6f)));
         const float qs = 127.f / amax;
-        if (ctid == 0) srow[m] = amax / 127.f;
-        for (int i = ctid * 8; i < K; i += kGemvConsumers * 8) {
+        if (tid == 0) srow[m] = amax / 127.f;
+        for (int i = tid * 8; i < K; i += kGemvThreads * 8) {
           uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
           __half2* h = reinterpret_cast<__half2*>(&raw);
           float f[8];
@@ -334,102 +258,76 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvParams 
       }
     }
   }
-  consumer_sync();
+  __syncthreads();
 
-  // Split-K inside the CTA: consumer thread t owns the 16-byte chunks c = t + 256*j of every row (of every
-  // piece); the eight per-warp partial sums of a row are combined through shared memory in warp order.
-  int stage = 0, phase = 0, buf = 0;
-  const int rows_w = SWIGLU ? 2 * geo.rps : geo.rps;            // weight rows resident per stage
-  for (int st = 0; st < nsteps; ++st) {
-    const int r = n0 + st * geo.rps;
-    const int nr = min(geo.rps, n1 - r);
-    float acc[RMAX][MB];
-    int iacc[RMAX][MB];
+  constexpr int R = SWIGLU ? 2 : 1;                  // weight rows per output (gate row, up row)
+  constexpr int UR = U / R;                            // 16-byte loads in flight per lane per row
+  for (int n = gw; n < p.n_out; n += tw) {
+    float acc[R][MB];
+    int iacc[R][MB];
 #pragma unroll
-    for (int a = 0; a < RMAX; ++a)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int m = 0; m < MB; ++m) { acc[a][m] = 0.f; iacc[a][m] = 0; }
+      for (int m = 0; m < MB; ++m) { acc[r][m] = 0.f; iacc[r][m] = 0; }
+    const uint8_t* wr[R];
+    wr[0] = wbase + (size_t) n * row_bytes;
+    if constexpr (SWIGLU) wr[1] = wbase + (size_t) (n + p.n_out) * row_bytes;
 
-    for (int pc = 0; pc < geo.pieces; ++pc) {
-      const int off = pc * geo.piece_bytes;
-      const int pchunks = min(geo.piece_bytes, row_bytes - off) >> 4;
-      const int kbase = (off >> 4) * EPC;
-      mbar_wait(&full[stage], phase);
-      const uint8_t* sbase = ring + stage * kStageBytes;
-      for (int c = ctid; c < pchunks; c += kGemvConsumers) {
-        const int k0 = kbase + c * EPC;
+    int c = lane;
+    for (; c + 32 * (UR - 1) < cpr; c += 32 * UR) {
+      uint4 wq[R][UR];
 #pragma unroll
-        for (int a = 0; a < RMAX; ++a) {
-          if (a < rows_w) {
-            // SwiGLU: rows [0, rps) are gate rows, [rps, 2*rps) the matching up rows (second half of the stage)
-            const int rr = SWIGLU ? (a < geo.rps ? a : a - geo.rps) : a;
-            const uint8_t* rowp = (SWIGLU && a >= geo.rps ? sbase + kStageBytes / 2 : sbase) + (size_t) rr * row_bytes * (geo.pieces == 1);
-            if (rr < nr) {
-              const uint4 wq = *reinterpret_cast<const uint4*>(rowp + c * 16);
-              chunk_fma<KIND, MB>(wq, xs, k0, xstride, acc[a], iacc[a]);
-            }
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
-      if (++stage == ST) { stage = 0; phase ^= 1; }
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int u = 0; u < UR; ++u) wq[r][u] = ldg_nc_v4(wr[r] + (size_t) (c + 32 * u) * 16);
+#pragma unroll
+      for (int u = 0; u < UR; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) chunk_fma<KIND, MB>(wq[r][u], xs, (c + 32 * u) * EPC, xstride, acc[r], iacc[r]);
     }
-
-    // per-warp partials -> shared memory -> one thread per (row, m) sums the eight in warp order
-    float* pb = part + buf * (RMAX * MB * kGemvConsumerWarps);
+    for (; c < cpr; c += 32) {
 #pragma unroll
-    for (int a = 0; a < RMAX; ++a) {
-      if (a < rows_w) {
-#pragma unroll
-        for (int m = 0; m < MB; ++m) {
-          float v;
-          if constexpr (KIND == kA8W8) {
-            int iv = iacc[a][m];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) iv += __shfl_xor_sync(0xffffffffu, iv, o);
-            v = __int_as_float(iv);
-          } else {
-            v = warp_sum(acc[a][m]);
-          }
-          if (lane == 0) pb[(a * MB + m) * kGemvConsumerWarps + warp] = v;
-        }
+      for (int r = 0; r < R; ++r) {
+        const uint4 wq = ldg_nc_v4(wr[r] + (size_t) c * 16);
+        chunk_fma<KIND, MB>(wq, xs, c * EPC, xstride, acc[r], iacc[r]);
       }
     }
-    consumer_sync();
-    if (ctid < nr * MB) {
-      const int rr = ctid / MB, m = ctid % MB;
-      if (m < p.M) {
-        auto total = [&](int a) -> float {
-          const float* q = pb + (a * MB + m) * kGemvConsumerWarps;
-          if constexpr (KIND == kA8W8) {
-            int t = 0;
+    // reduce across the warp, lane 0 applies the epilogue
+    float res[R][MB];
 #pragma unroll
-            for (int w = 0; w < kGemvConsumerWarps; ++w) t += __float_as_int(q[w]);
-            return (float) t;
-          } else {
-            float t = 0.f;
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int w = 0; w < kGemvConsumerWarps; ++w) t += q[w];
-            return t;
-          }
-        };
-        auto scaled = [&](float v, int nrow) -> float {
-          if constexpr (KIND == kW8 || KIND == kW4) v *= __half2float(p.w_scale[nrow]);
+      for (int m = 0; m < MB; ++m) {
+        if constexpr (KIND == kA8W8) {
+          int v = iacc[r][m];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          res[r][m] = (float) v;
+        } else {
+          res[r][m] = warp_sum(acc[r][m]);
+        }
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        if (m >= p.M) break;
+        float v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int nr = n + r * p.n_out;
+          v[r] = res[r][m];
+          if constexpr (KIND == kW8 || KIND == kW4) v[r] *= __half2float(p.w_scale[nr]);
           // reference grouping: accum * (scale_col * scale_row)  (epilogue_per_row_per_col_scale.h:325,341)
-          if constexpr (KIND == kA8W8) v = v * (p.sc[p.sc_per_channel ? nrow : 0] * srow[m]);
-          return v;
-        };
-        const int n = r + rr;
-        const size_t oi = (size_t) m * p.n_out + n;
+          if constexpr (KIND == kA8W8) v[r] = v[r] * (p.sc[p.sc_per_channel ? nr : 0] * srow[m]);
+        }
         float o;
         if constexpr (SWIGLU) {
-          const float gte = __half2float(__float2half_rn(scaled(total(rr), n)));
-          const float up = __half2float(__float2half_rn(scaled(total(geo.rps + rr), n + p.n_out)));
+          const float gte = __half2float(__float2half_rn(v[0])), up = __half2float(__float2half_rn(v[1]));
           o = __half2float(__float2half_rn(silu_f(gte))) * up;
         } else {
-          o = scaled(total(rr), n);
+          o = v[0];
         }
+        const size_t oi = (size_t) m * p.n_out + n;
         if (p.y_f32) {
           p.y_f32[oi] = o;
         } else {
@@ -439,26 +337,27 @@ __global__ void __launch_bounds__(kGemvThreads, 2) gemv_kernel(const GemvParams 
         }
       }
     }
-    buf ^= 1;
   }
 }
 
 template <int KIND, int MB, bool SWIGLU>
 static int launch_gemv_t(const GemvParams& p, cudaStream_t stream) {
   const size_t xs_bytes = (size_t) MB * p.K * (KIND == kA8W8 ? 1 : 2);
-  const size_t smem = (size_t) kGemvStages * kStageBytes + 2 * kGemvStages * sizeof(uint64_t) +
-                      (12 + 2 * kMaxRowsPerStage * MB * kGemvConsumerWarps) * sizeof(float) + xs_bytes;
-  if (smem > 220 * 1024) return -2;
+  const size_t smem = 16 * sizeof(float) + xs_bytes;
+  if (smem > 200 * 1024) return -2;
   auto kern = gemv_kernel<KIND, MB, SWIGLU>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return (int) e;
     attr_done = true;
   }
-  // persistent grid: two CTAs per SM when the staged activations leave room, capped by the work
-  int grid = kNumSMs * (smem <= 110 * 1024 ? 2 : 1);
-  if (grid > p.n_out) grid = p.n_out;
+  // one warp per output row, dealt round-robin: size the grid to a whole number of resident CTAs per SM
+  int per_sm = smem > 100 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : (smem > 54 * 1024 ? 3 : 4));
+  if (MB >= 4 && per_sm > 2) per_sm = 2;     // register budget of the MB = 4 variants
+  int grid = kNumSMs * per_sm;
+  const int need = (p.n_out + kGemvWarps - 1) / kGemvWarps;
+  if (grid > need) grid = need;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemvThreads);

@@ -174,7 +174,8 @@ class SmoothQuantGemmPlugin : public BasePlugin {
     static const std::vector<PluginField> t = {field_decl("has_per_channel_scaling", FT::kINT32),
                                                field_decl("has_per_token_scaling", FT::kINT32),
                                                field_decl("type_id", FT::kINT32), field_decl("fused_swiglu", FT::kINT32),
-                                               field_decl("fused_residual", FT::kINT32)};
+                                               field_decl("fused_residual", FT::kINT32),
+                                               field_decl("fused_prologue", FT::kINT32), field_decl("eps", FT::kFLOAT32)};
     return t;
   }
   explicit SmoothQuantGemmPlugin(Fields& f) {
@@ -183,19 +184,21 @@ class SmoothQuantGemmPlugin : public BasePlugin {
     type_ = f.required<int32_t>("type_id");
     swiglu_ = f.optional<int32_t>("fused_swiglu", 0) != 0;
     residual_ = f.optional<int32_t>("fused_residual", 0) != 0;
+    prologue_ = f.optional<int32_t>("fused_prologue", 0);
+    eps_ = f.optional<float>("eps", 1e-6f);
     validate();
   }
   explicit SmoothQuantGemmPlugin(Reader& r) {
     // reference order perChannel, perToken, type (smoothQuantGemmPlugin.cpp:253-282); the reference's
     // CUTLASS tactic table that follows is replaced by this library's two extension flags
     per_channel_ = r.get<bool>(); per_token_ = r.get<bool>(); type_ = r.get<int32_t>();
-    swiglu_ = r.get<bool>(); residual_ = r.get<bool>();
+    swiglu_ = r.get<bool>(); residual_ = r.get<bool>(); prologue_ = r.get<int32_t>(); eps_ = r.get<float>();
     validate();
   }
-  size_t getSerializationSize() const noexcept override { return 4 * sizeof(bool) + sizeof(int32_t); }
+  size_t getSerializationSize() const noexcept override { return 4 * sizeof(bool) + 2 * sizeof(int32_t) + sizeof(float); }
   void serialize(void* buf) const noexcept override {
     Writer w{static_cast<char*>(buf)};
-    w.put(per_channel_); w.put(per_token_); w.put(type_); w.put(swiglu_); w.put(residual_);
+    w.put(per_channel_); w.put(per_token_); w.put(type_); w.put(swiglu_); w.put(residual_); w.put(prologue_); w.put(eps_);
   }
   SmoothQuantGemmPlugin* clone() const noexcept override {
     auto* p = new SmoothQuantGemmPlugin(*this);
@@ -211,11 +214,10 @@ class SmoothQuantGemmPlugin : public BasePlugin {
   }
   DataType getOutputDataType(int32_t, const DataType*, int32_t) const noexcept override { return (DataType) type_; }
   bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nb_in, int32_t) noexcept override {
-    if (pos == 0) return linear(io[pos], DataType::kINT8);
+    if (pos == 0) return linear(io[pos], prologue_ ? DataType::kHALF : DataType::kINT8);
     if (pos == 1) return io[pos].format == TensorFormat::kLINEAR && (io[pos].type == DataType::kINT8 || io[pos].type == DataType::kFLOAT);
     if (pos == 2 || pos == 3) return linear(io[pos], DataType::kFLOAT);
-    if (residual_ && pos == 4) return linear(io[pos], DataType::kHALF);
-    (void) nb_in;
+    if (pos < nb_in) return linear(io[pos], DataType::kHALF);   // residual / gamma [ext]
     return linear(io[pos], (DataType) type_);
   }
   size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
@@ -225,13 +227,15 @@ class SmoothQuantGemmPlugin : public BasePlugin {
                   void* workspace, cudaStream_t stream) noexcept override {
     return guarded("SmoothQuantGemm::enqueue", [&]() -> int {
       const int M = (int) rows_of(id[0].dims), N = id[1].dims.d[0], K = last_dim(id[0].dims);
-      const void* res = residual_ ? in[4] : nullptr;
+      int next = 4;
+      const void* res = residual_ ? in[next++] : nullptr;
+      const void* gamma = prologue_ == 2 ? in[next++] : nullptr;
       const float* st = static_cast<const float*>(in[2]);
       const float* sc = static_cast<const float*>(in[3]);
       if (M <= 4 && is_half(type_))
-        return tb_gemv(3, out[0], nullptr, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K, swiglu_,
-                       stream);
-      TBP_REQUIRE(!swiglu_, "fused_swiglu is only available on the decode (M <= 4) path");
+        return tb_gemv_fused(3, out[0], nullptr, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K,
+                             swiglu_, prologue_, gamma, eps_, stream);
+      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= 4) path");
       const int ot = is_half(type_) ? 0 : (type_ == (int32_t) DataType::kFLOAT ? 1 : 2);
       (void) od;
       return tb_gemm_tc(3, out[0], ot, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K, workspace,
@@ -244,9 +248,13 @@ class SmoothQuantGemmPlugin : public BasePlugin {
     TBP_REQUIRE(is_half(type_) || type_ == (int32_t) DataType::kFLOAT || type_ == (int32_t) DataType::kINT32,
                 "type_id must be half, float or int32");
     TBP_REQUIRE(!(swiglu_ || residual_) || is_half(type_), "fused epilogues need a half output");
+    // [ext] fused_prologue: 2 = RmsnormQuantization (extra input gamma, field eps), 3 = QuantizePerToken; input 0 is
+    // then the fp16 activation and scale_tokens (input 2) is ignored
+    TBP_REQUIRE(prologue_ == 0 || prologue_ == 2 || prologue_ == 3, "fused_prologue must be 0, 2 or 3");
   }
   bool per_channel_ = false, per_token_ = false, swiglu_ = false, residual_ = false;
-  int32_t type_ = (int32_t) DataType::kHALF;
+  int32_t type_ = (int32_t) DataType::kHALF, prologue_ = 0;
+  float eps_ = 1e-6f;
   DeviceCounters counters_;
 };
 
@@ -262,7 +270,8 @@ class WeightOnlyQuantMatmulPlugin : public BasePlugin {
   static const std::vector<PluginField>& field_table() {
     static const std::vector<PluginField> t = {field_decl("type_id", FT::kINT32), field_decl("weight_type_id", FT::kINT32),
                                                field_decl("fused_swiglu", FT::kINT32),
-                                               field_decl("fused_residual", FT::kINT32)};
+                                               field_decl("fused_residual", FT::kINT32),
+                                               field_decl("fused_prologue", FT::kINT32), field_decl("eps", FT::kFLOAT32)};
     return t;
   }
   explicit WeightOnlyQuantMatmulPlugin(Fields& f) {
@@ -270,17 +279,19 @@ class WeightOnlyQuantMatmulPlugin : public BasePlugin {
     weight_type_ = f.required<int32_t>("weight_type_id");
     swiglu_ = f.optional<int32_t>("fused_swiglu", 0) != 0;
     residual_ = f.optional<int32_t>("fused_residual", 0) != 0;
+    prologue_ = f.optional<int32_t>("fused_prologue", 0);
+    eps_ = f.optional<float>("eps", 1e-6f);
     validate();
   }
   explicit WeightOnlyQuantMatmulPlugin(Reader& r) {
     type_ = r.get<int32_t>(); weight_type_ = r.get<int32_t>();   // weightOnlyQuantMatmulPlugin.cpp:256-267
-    swiglu_ = r.get<bool>(); residual_ = r.get<bool>();
+    swiglu_ = r.get<bool>(); residual_ = r.get<bool>(); prologue_ = r.get<int32_t>(); eps_ = r.get<float>();
     validate();
   }
-  size_t getSerializationSize() const noexcept override { return 2 * sizeof(int32_t) + 2 * sizeof(bool); }
+  size_t getSerializationSize() const noexcept override { return 3 * sizeof(int32_t) + 2 * sizeof(bool) + sizeof(float); }
   void serialize(void* buf) const noexcept override {
     Writer w{static_cast<char*>(buf)};
-    w.put(type_); w.put(weight_type_); w.put(swiglu_); w.put(residual_);
+    w.put(type_); w.put(weight_type_); w.put(swiglu_); w.put(residual_); w.put(prologue_); w.put(eps_);
   }
   WeightOnlyQuantMatmulPlugin* clone() const noexcept override {
     auto* p = new WeightOnlyQuantMatmulPlugin(*this);
@@ -309,9 +320,13 @@ class WeightOnlyQuantMatmulPlugin : public BasePlugin {
       const int M = (int) rows_of(id[0].dims), N = id[1].dims.d[1] * pack(), K = last_dim(id[0].dims);
       TBP_REQUIRE(id[1].dims.d[0] == K, "weight rows must equal the activation's last dim");
       const int kind = weight_type_ == 1 ? 1 : 2;
-      const void* res = residual_ ? in[3] : nullptr;
-      if (M <= 4) return tb_gemv(kind, out[0], nullptr, in[0], in[1], in[2], nullptr, nullptr, 0, 0, res, M, N, K, swiglu_, stream);
-      TBP_REQUIRE(!swiglu_, "fused_swiglu is only available on the decode (M <= 4) path");
+      int next = 3;
+      const void* res = residual_ ? in[next++] : nullptr;
+      const void* gamma = prologue_ ? in[next++] : nullptr;
+      if (M <= 4)
+        return tb_gemv_fused(kind, out[0], nullptr, in[0], in[1], in[2], nullptr, nullptr, 0, 0, res, M, N, K, swiglu_,
+                             prologue_, gamma, eps_, stream);
+      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= 4) path");
       return tb_gemm_tc(kind, out[0], 0, in[0], in[1], in[2], nullptr, nullptr, 0, 0, res, M, N, K, workspace,
                         tb_gemm_tc_workspace_bytes(M, N, K), counters_.get(tb_gemm_tc_counter_bytes()), 0, 0, stream);
     });
@@ -321,8 +336,11 @@ class WeightOnlyQuantMatmulPlugin : public BasePlugin {
   void validate() const {
     TBP_REQUIRE(is_half(type_), "only type_id = half is supported (as in the reference, weightOnlyQuantMatmulPlugin.cpp:47-63)");
     TBP_REQUIRE(weight_type_ == 1 || weight_type_ == 2, "weight_type_id must be 1 (int8) or 2 (int4)");
+    // [ext] fused_prologue 1: RMSNorm(x, gamma, eps) applied while staging the activations (extra last input gamma)
+    TBP_REQUIRE(prologue_ == 0 || prologue_ == 1, "fused_prologue must be 0 or 1");
   }
-  int32_t type_ = (int32_t) DataType::kHALF, weight_type_ = 1;
+  int32_t type_ = (int32_t) DataType::kHALF, weight_type_ = 1, prologue_ = 0;
+  float eps_ = 1e-6f;
   bool swiglu_ = false, residual_ = false;
   DeviceCounters counters_;
 };
@@ -338,7 +356,8 @@ class GemmPlugin : public BasePlugin {
   static const std::vector<PluginField>& field_table() {
     static const std::vector<PluginField> t = {field_decl("transa", FT::kINT32), field_decl("transb", FT::kINT32),
                                                field_decl("type_id", FT::kINT32), field_decl("fused_swiglu", FT::kINT32),
-                                               field_decl("fused_residual", FT::kINT32), field_decl("out_fp32", FT::kINT32)};
+                                               field_decl("fused_residual", FT::kINT32), field_decl("out_fp32", FT::kINT32),
+                                               field_decl("fused_prologue", FT::kINT32), field_decl("eps", FT::kFLOAT32)};
     return t;
   }
   explicit GemmPlugin(Fields& f) {
@@ -348,17 +367,21 @@ class GemmPlugin : public BasePlugin {
     swiglu_ = f.optional<int32_t>("fused_swiglu", 0) != 0;
     residual_ = f.optional<int32_t>("fused_residual", 0) != 0;
     out_fp32_ = f.optional<int32_t>("out_fp32", 0) != 0;
+    prologue_ = f.optional<int32_t>("fused_prologue", 0);
+    eps_ = f.optional<float>("eps", 1e-6f);
     validate();
   }
   explicit GemmPlugin(Reader& r) {
     transa_ = r.get<int32_t>(); transb_ = r.get<int32_t>(); type_ = r.get<int32_t>();
-    swiglu_ = r.get<bool>(); residual_ = r.get<bool>(); out_fp32_ = r.get<bool>();
+    swiglu_ = r.get<bool>(); residual_ = r.get<bool>(); out_fp32_ = r.get<bool>(); prologue_ = r.get<int32_t>();
+    eps_ = r.get<float>();
     validate();
   }
-  size_t getSerializationSize() const noexcept override { return 3 * sizeof(int32_t) + 3 * sizeof(bool); }
+  size_t getSerializationSize() const noexcept override { return 4 * sizeof(int32_t) + 3 * sizeof(bool) + sizeof(float); }
   void serialize(void* buf) const noexcept override {
     Writer w{static_cast<char*>(buf)};
-    w.put(transa_); w.put(transb_); w.put(type_); w.put(swiglu_); w.put(residual_); w.put(out_fp32_);
+    w.put(transa_); w.put(transb_); w.put(type_); w.put(swiglu_); w.put(residual_); w.put(out_fp32_); w.put(prologue_);
+    w.put(eps_);
   }
   GemmPlugin* clone() const noexcept override {
     auto* p = new GemmPlugin(*this);
@@ -387,11 +410,13 @@ class GemmPlugin : public BasePlugin {
     return guarded("Gemm::enqueue", [&]() -> int {
       const int M = (int) rows_of(id[0].dims), N = id[1].dims.d[0], K = last_dim(id[0].dims);
       TBP_REQUIRE(id[1].dims.d[1] == K, "B must be [N, K]");
-      const void* res = residual_ ? in[2] : nullptr;
+      int next = 2;
+      const void* res = residual_ ? in[next++] : nullptr;
+      const void* gamma = prologue_ ? in[next++] : nullptr;
       if (M <= 4)
-        return tb_gemv(0, out_fp32_ ? nullptr : out[0], out_fp32_ ? static_cast<float*>(out[0]) : nullptr, in[0], in[1],
-                       nullptr, nullptr, nullptr, 0, 0, res, M, N, K, swiglu_, stream);
-      TBP_REQUIRE(!swiglu_, "fused_swiglu is only available on the decode (M <= 4) path");
+        return tb_gemv_fused(0, out_fp32_ ? nullptr : out[0], out_fp32_ ? static_cast<float*>(out[0]) : nullptr, in[0],
+                             in[1], nullptr, nullptr, nullptr, 0, 0, res, M, N, K, swiglu_, prologue_, gamma, eps_, stream);
+      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= 4) path");
       return tb_gemm_tc(0, out[0], out_fp32_ ? 1 : 0, in[0], in[1], nullptr, nullptr, nullptr, 0, 0, res, M, N, K,
                         workspace, tb_gemm_tc_workspace_bytes(M, N, K), counters_.get(tb_gemm_tc_counter_bytes()), 0, 0,
                         stream);
@@ -403,8 +428,10 @@ class GemmPlugin : public BasePlugin {
     TBP_REQUIRE(is_half(type_), "only type_id = half is built");
     TBP_REQUIRE(transa_ == 0 && transb_ == 1, "only C = A . B^T (transa=0, transb=1) is built");
     TBP_REQUIRE(!(out_fp32_ && (residual_ || swiglu_)), "out_fp32 excludes the fused epilogues");
+    TBP_REQUIRE(prologue_ == 0 || prologue_ == 1, "fused_prologue must be 0 or 1 (RMSNorm; extra last input gamma)");
   }
-  int32_t transa_ = 0, transb_ = 1, type_ = (int32_t) DataType::kHALF;
+  int32_t transa_ = 0, transb_ = 1, type_ = (int32_t) DataType::kHALF, prologue_ = 0;
+  float eps_ = 1e-6f;
   bool swiglu_ = false, residual_ = false, out_fp32_ = false;
   DeviceCounters counters_;
 };

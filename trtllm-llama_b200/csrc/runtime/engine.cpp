@@ -102,6 +102,8 @@ struct tbrt_engine {
 
   // plugins (one instance per distinct configuration, shared by all layers)
   PluginPtr lin, lin_res, lin_swiglu, lm, attn, normq, qpt, allreduce, allgather;
+  // decode-shape (M <= 4) variants with the norm / quantiser fused into the projection's prologue ([ext] fields)
+  PluginPtr lin_n, lin_n_swiglu, lin_q_res, lm_n;
 
   // device memory
   std::vector<void*> allocs;
@@ -143,9 +145,10 @@ struct tbrt_engine {
   int bind();
   int build_plugins();
   int linear(IPluginV2DynamicExt* p, const LinearW& w, const void* in, const float* in_scales, void* out,
-             const void* residual, int M, DataType out_t, cudaStream_t s);
+             const void* residual, int M, DataType out_t, cudaStream_t s, const void* gamma = nullptr,
+             bool half_in = false);
   int layers_forward(int M, int S, bool context, cudaStream_t s);
-  int head(int rows, cudaStream_t s);
+  int head(int rows, const __half* src, cudaStream_t s);
   int step_body(cudaStream_t s);
 };
 
@@ -205,7 +208,7 @@ int tbrt_engine::bind() {
 int tbrt_engine::build_plugins() {
   initLibNvInferPlugins(nullptr, kNamespace);
   const int32_t half_t = (int32_t) DataType::kHALF;
-  auto make_linear = [&](bool swiglu, bool residual) -> PluginPtr {
+  auto make_linear = [&](bool swiglu, bool residual, int prologue = 0) -> PluginPtr {
     FieldList fl;
     const char* name = nullptr;
     if (c.mode == TBRT_MODE_FP16) {
@@ -225,11 +228,19 @@ int tbrt_engine::build_plugins() {
     }
     if (swiglu) fl.add<int32_t>("fused_swiglu", PluginFieldType::kINT32, 1);
     if (residual) fl.add<int32_t>("fused_residual", PluginFieldType::kINT32, 1);
+    if (prologue) {
+      fl.add<int32_t>("fused_prologue", PluginFieldType::kINT32, prologue);
+      fl.add<float>("eps", PluginFieldType::kFLOAT32, c.rms_eps);
+    }
     return make_plugin(name, fl);
   };
+  const bool sq_mode = c.mode == TBRT_MODE_SQ;
   if (!(lin = make_linear(false, false))) return -1;
   if (!(lin_res = make_linear(false, true))) return -1;
   if (!(lin_swiglu = make_linear(true, false))) return -1;
+  if (!(lin_n = make_linear(false, false, sq_mode ? 2 : 1))) return -1;
+  if (!(lin_n_swiglu = make_linear(true, false, sq_mode ? 2 : 1))) return -1;
+  if (sq_mode && !(lin_q_res = make_linear(false, true, 3))) return -1;
   {
     FieldList fl;
     fl.add<int32_t>("transa", PluginFieldType::kINT32, 0);
@@ -237,6 +248,9 @@ int tbrt_engine::build_plugins() {
     fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
     fl.add<int32_t>("out_fp32", PluginFieldType::kINT32, c.tp_size == 1 ? 1 : 0);
     if (!(lm = make_plugin("Gemm", fl))) return -1;
+    fl.add<int32_t>("fused_prologue", PluginFieldType::kINT32, 1);     // ln_f rides in the lm_head GEMV (rows <= 4)
+    fl.add<float>("eps", PluginFieldType::kFLOAT32, c.rms_eps);
+    if (!(lm_n = make_plugin("Gemm", fl))) return -1;
   }
   {
     // the fields T/tensorrt_llm/functional.py:2833-2891 passes for a LLaMA layer
@@ -287,17 +301,18 @@ int tbrt_engine::build_plugins() {
 // one projection through its plugin: fp16 / weight-only take (x, w[, scales][, residual]); SmoothQuant
 // takes (x int8, w, scale_tokens, scale_channels[, residual]) — same input order as the reference plugins
 int tbrt_engine::linear(IPluginV2DynamicExt* p, const LinearW& w, const void* in, const float* in_scales, void* out,
-                        const void* residual, int M, DataType out_t, cudaStream_t s) {
-  PluginTensorDesc id[5], od[1];
-  const void* inputs[5];
+                        const void* residual, int M, DataType out_t, cudaStream_t s, const void* gamma, bool half_in) {
+  PluginTensorDesc id[6], od[1];
+  const void* inputs[6];
   void* outputs[1] = {out};
   int n = 0;
-  if (c.mode == TBRT_MODE_SQ && p != lm.get()) {
-    id[n] = desc({M, w.K}, DataType::kINT8); inputs[n++] = in;
+  const bool is_lm = (p == lm.get() || p == lm_n.get());   // lm_head stays fp16 (LQ/quant.py:58-59)
+  if (c.mode == TBRT_MODE_SQ && !is_lm) {
+    id[n] = desc({M, w.K}, half_in ? DataType::kHALF : DataType::kINT8); inputs[n++] = in;
     id[n] = desc({w.N, w.K / 4}, DataType::kFLOAT); inputs[n++] = w.w;
     id[n] = desc({M, 1}, DataType::kFLOAT); inputs[n++] = in_scales;
     id[n] = desc({1, w.N}, DataType::kFLOAT); inputs[n++] = w.scale;
-  } else if ((c.mode == TBRT_MODE_W8 || c.mode == TBRT_MODE_W4) && p != lm.get()) {
+  } else if ((c.mode == TBRT_MODE_W8 || c.mode == TBRT_MODE_W4) && !is_lm) {
     const int pack = c.mode == TBRT_MODE_W8 ? 4 : 8;
     id[n] = desc({M, w.K}, DataType::kHALF); inputs[n++] = in;
     id[n] = desc({w.K, w.N / pack}, DataType::kFLOAT); inputs[n++] = w.w;
@@ -307,6 +322,7 @@ int tbrt_engine::linear(IPluginV2DynamicExt* p, const LinearW& w, const void* in
     id[n] = desc({w.N, w.K}, DataType::kHALF); inputs[n++] = w.w;
   }
   if (residual) { id[n] = desc({M, w.N}, DataType::kHALF); inputs[n++] = residual; }
+  if (gamma) { id[n] = desc({w.K}, DataType::kHALF); inputs[n++] = gamma; }
   od[0] = desc({M, w.N}, out_t);
   ++launches;
   return p->enqueue(id, od, inputs, outputs, workspace, s);
@@ -344,13 +360,16 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     return qpt->enqueue(id, od, in, out, workspace, s);
   };
   const void* lin_in = sq ? static_cast<const void*>(xq) : static_cast<const void*>(x);
+  // decode shapes: RMSNorm (+ per-token quantisation) rides in the projection's prologue -> 5 kernels per layer
+  const bool fused = M <= 4;
 
   __half* cur = h;   // residual stream
   __half* nxt = h2;
-  RT_CALL(norm(cur, L[0].ln_in, nullptr, nullptr));
+  if (!fused) RT_CALL(norm(cur, L[0].ln_in, nullptr, nullptr));
   for (int li = 0; li < c.layers; ++li) {
     const LayerW& l = L[li];
-    RT_CALL(linear(lin.get(), l.qkv, lin_in, xs, qkv, nullptr, M, DataType::kHALF, s));
+    if (fused) RT_CALL(linear(lin_n.get(), l.qkv, cur, xs, qkv, nullptr, M, DataType::kHALF, s, l.ln_in, true));
+    else RT_CALL(linear(lin.get(), l.qkv, lin_in, xs, qkv, nullptr, M, DataType::kHALF, s));
     {
       const DataType kvt = c.int8_kv ? DataType::kINT8 : DataType::kHALF;
       PluginTensorDesc id[10] = {desc({Bq, context ? S : 1, 3 * hid_l}, DataType::kHALF),
@@ -366,11 +385,14 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       launches += context ? 2 : 1;
       RT_CALL(attn->enqueue(id, od, in, out, workspace, s));
     }
+    IPluginV2DynamicExt* row_lin = (fused && sq) ? lin_q_res.get() : lin_res.get();   // QuantizePerToken fused in
+    IPluginV2DynamicExt* row_lin_nores = (fused && sq) ? nullptr : lin.get();
     const void* dense_in = att;
-    if (sq) { RT_CALL(quant(att, hid_l)); dense_in = xq; }
+    if (sq && !(fused && !tp)) { RT_CALL(quant(att, hid_l)); dense_in = xq; }
+    (void) row_lin_nores;
     if (!tp) {
-      RT_CALL(linear(lin_res.get(), l.dense, dense_in, xs, nxt, cur, M, DataType::kHALF, s));   // nxt = cur + dense(att)
-      RT_CALL(norm(nxt, l.ln_post, nullptr, nullptr));
+      RT_CALL(linear(row_lin, l.dense, dense_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, fused && sq));   // nxt = cur + dense(att)
+      if (!fused) RT_CALL(norm(nxt, l.ln_post, nullptr, nullptr));
     } else {
       RT_CALL(linear(lin.get(), l.dense, dense_in, xs, o, nullptr, M, DataType::kHALF, s));
       PluginTensorDesc d1[1] = {desc({M, hid}, DataType::kHALF)};
@@ -378,10 +400,17 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       void* out[1] = {o};
       launches += 1;
       RT_CALL(allreduce->enqueue(d1, d1, in, out, workspace, s));
-      RT_CALL(norm(o, l.ln_post, cur, nxt));                                                    // nxt = o + cur, x = norm(nxt)
+      if (fused) {
+        launches += 1;
+        RT_CALL(tb_add(nxt, o, cur, (int64_t) M * hid, s));
+      } else {
+        RT_CALL(norm(o, l.ln_post, cur, nxt));                                                  // nxt = o + cur, x = norm(nxt)
+      }
     }
     std::swap(cur, nxt);
-    if (fuse_swiglu) {
+    if (fused) {
+      RT_CALL(linear(lin_n_swiglu.get(), l.fc_gate, cur, xs, act, nullptr, M, DataType::kHALF, s, l.ln_post, true));
+    } else if (fuse_swiglu) {
       RT_CALL(linear(lin_swiglu.get(), l.fc_gate, lin_in, xs, act, nullptr, M, DataType::kHALF, s));
     } else {
       RT_CALL(linear(lin.get(), l.fc_gate, lin_in, xs, gu, nullptr, M, DataType::kHALF, s));
@@ -389,12 +418,12 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       RT_CALL(tb_swiglu(act, gu, gu + inter_l, M, inter_l, 2 * inter_l, s));
     }
     const void* proj_in = act;
-    if (sq) { RT_CALL(quant(act, inter_l)); proj_in = xq; }
+    if (sq && !(fused && !tp)) { RT_CALL(quant(act, inter_l)); proj_in = xq; }
     const void* next_gamma = li + 1 < c.layers ? L[li + 1].ln_in : nullptr;
     if (!tp) {
-      RT_CALL(linear(lin_res.get(), l.proj, proj_in, xs, nxt, cur, M, DataType::kHALF, s));
+      RT_CALL(linear(row_lin, l.proj, proj_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, fused && sq));
       std::swap(cur, nxt);
-      if (next_gamma) RT_CALL(norm(cur, next_gamma, nullptr, nullptr));
+      if (next_gamma && !fused) RT_CALL(norm(cur, next_gamma, nullptr, nullptr));
     } else {
       RT_CALL(linear(lin.get(), l.proj, proj_in, xs, o, nullptr, M, DataType::kHALF, s));
       PluginTensorDesc d1[1] = {desc({M, hid}, DataType::kHALF)};
@@ -402,7 +431,7 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       void* out[1] = {o};
       launches += 1;
       RT_CALL(allreduce->enqueue(d1, d1, in, out, workspace, s));
-      if (next_gamma) {
+      if (next_gamma && !fused) {
         RT_CALL(norm(o, next_gamma, cur, nxt));
       } else {
         launches += 1;
@@ -418,14 +447,19 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
 }
 
 // ln_f -> lm_head (fp32 logits) -> greedy argmax -> device-side bookkeeping
-int tbrt_engine::head(int rows, cudaStream_t s) {
+int tbrt_engine::head(int rows, const __half* src, cudaStream_t s) {
   LinearW w;
   w.w = lm_head; w.N = vocab_l; w.K = c.hidden;
-  launches += 3;
-  RT_CALL(tb_rmsnorm(x, hl, nullptr, nullptr, ln_f, c.rms_eps, rows, c.hidden, s));
-  if (c.tp_size == 1) {
+  launches += 2;
+  if (c.tp_size == 1 && rows <= 4) {
+    RT_CALL(linear(lm_n.get(), w, src, nullptr, logits, nullptr, rows, DataType::kFLOAT, s, ln_f));
+  } else if (c.tp_size == 1) {
+    launches += 1;
+    RT_CALL(tb_rmsnorm(x, src, nullptr, nullptr, ln_f, c.rms_eps, rows, c.hidden, s));
     RT_CALL(linear(lm.get(), w, x, nullptr, logits, nullptr, rows, DataType::kFLOAT, s));
   } else {
+    launches += 1;
+    RT_CALL(tb_rmsnorm(x, src, nullptr, nullptr, ln_f, c.rms_eps, rows, c.hidden, s));
     // vocab-parallel lm_head + all-gather (T/tensorrt_llm/layers/linear.py:78-97 gather_output)
     RT_CALL(linear(lm.get(), w, x, nullptr, logits_h, nullptr, rows, DataType::kHALF, s));
     PluginTensorDesc id[1] = {desc({rows, vocab_l}, DataType::kHALF)};
@@ -445,8 +479,7 @@ int tbrt_engine::step_body(cudaStream_t s) {
   launches += 1;
   RT_CALL(tb_embedding(h, emb, d_ids, B, c.hidden, c.vocab, s));
   if (layers_forward(B, 1, false, s)) return -1;
-  RT_CUDA(cudaMemcpyAsync(hl, h, (size_t) B * c.hidden * 2, cudaMemcpyDeviceToDevice, s));
-  return head(B, s);
+  return head(B, h, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -548,7 +581,7 @@ int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_length
   if (e->layers_forward(M, seq, true, s)) return -1;
   e->launches += 1;
   RT_CALL(tb_gather_last_token(e->hl, e->h, e->d_in_lens, batch, seq, e->c.hidden, s));
-  return e->head(batch, s);
+  return e->head(batch, e->hl, s);
 }
 
 int tbrt_step(tbrt_engine* e, tb_stream_t st) {
