@@ -165,8 +165,10 @@ using namespace tb::plugins;
 
 extern "C" {
 
+#ifndef TB_HAVE_TENSORRT   // with TensorRT present its own registry (libnvinfer) is the one plugins register into
 IPluginRegistry* getPluginRegistry() noexcept { return &registry(); }
 int32_t getInferLibVersion() noexcept { return NV_TENSORRT_VERSION; }
+#endif
 
 // P/api/InferPlugin.cpp:149-171: register every creator once under `libNamespace`.
 bool initLibNvInferPlugins(void* logger, const char* libNamespace) {
