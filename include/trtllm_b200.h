@@ -46,13 +46,14 @@ int tb_quantize_per_token(int8_t* dst, float* scales, const void* src, int rows,
 int tb_quantize_tensor(int8_t* dst, const void* src, int64_t size, const float* scale, int src_is_fp32,
                        tb_stream_t stream);
 
-/* ---- decode-shape GEMV (M <= 4) ---------------------------------------------------------------
+/* ---- decode-shape GEMV (M <= tb_gemv_max_rows: 8 on the tensor-core kernel, 4 otherwise) ----------
  * kind: 0 fp16 weights [N,K]; 1 int8 weight-only [N,K] + fp16 scales[N]; 2 int4 weight-only [N,K/2];
  *       3 W8A8 SmoothQuant (x int8 [M,K], w int8 [N,K], sc per-channel, sr per-token fp32).
  * replaces K/weightOnlyMatrixVectorMultiplication.cu:371-378 weight_only_gemv_launcher and the M<=4
  * calls of CutlassInt8GemmRunner::gemm / cuBLAS GemmPlugin.
  * swiglu != 0: w holds [N = 2*inter, K] (gate rows then up rows), y is [M, inter] = silu(gate)*up.
  * y_f32 != NULL writes fp32 instead of fp16 (lm_head logits).                                   */
+int tb_gemv_max_rows(int kind, int K);
 int tb_gemv(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
             const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
             int swiglu, tb_stream_t stream);

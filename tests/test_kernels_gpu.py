@@ -108,9 +108,11 @@ def _wo_tol(ref, bits):
     return 2e-3 * np.abs(ref.astype(np.float32)).max() + 1e-3
 
 
-@pytest.mark.parametrize("M", [1, 2, 4])
-@pytest.mark.parametrize("N,K", [(512, 4096), (256, 11008)])
+@pytest.mark.parametrize("M", [1, 2, 4, 7, 8])
+@pytest.mark.parametrize("N,K", [(512, 4096), (256, 11008), (100, 4096), (64, 136)])
 def test_gemv_f16(ops, M, N, K):
+    if M > ops.lib.tb_gemv_max_rows(ops.KIND_F16, K):
+        pytest.skip("M > 4 needs the tensor-core GEMV (K multiple of 32)")
     rng = np.random.default_rng(5)
     x = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
     w = (rng.standard_normal((N, K)) * 0.05).astype(np.float16)
@@ -122,10 +124,13 @@ def test_gemv_f16(ops, M, N, K):
 
 
 @pytest.mark.parametrize("bits", [8, 4])
-@pytest.mark.parametrize("M", [1, 3])
-def test_gemv_weight_only(ops, bits, M):
+@pytest.mark.parametrize("M", [1, 3, 8])
+@pytest.mark.parametrize("N,K", [(384, 4096), (200, 11008), (96, 320)])
+def test_gemv_weight_only(ops, bits, M, N, K):
+    if M > ops.lib.tb_gemv_max_rows(ops.KIND_W8 if bits == 8 else ops.KIND_W4, K):
+        pytest.skip("M > 4 needs the tensor-core GEMV")
     rng = np.random.default_rng(6)
-    x, wp, scales, ref = _wo_inputs(rng, M, 384, 4096, bits)
+    x, wp, scales, ref = _wo_inputs(rng, M, N, K, bits)
     y = host(ops.weight_only_quant_matmul(dev(x), dev(wp), dev(scales), 1 if bits == 8 else 2, use_gemv=True))
     np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), atol=_wo_tol(ref, bits))
 
@@ -139,16 +144,17 @@ def _sq_inputs(rng, M, N, K, per_token, per_channel):
 
 
 @pytest.mark.parametrize("per_token,per_channel", [(True, True), (False, True), (True, False), (False, False)])
-def test_gemv_sq(ops, per_token, per_channel):
+@pytest.mark.parametrize("M,N,K", [(4, 768, 768), (8, 520, 4096), (3, 64, 11008), (2, 100, 208)])
+def test_gemv_sq(ops, per_token, per_channel, M, N, K):
     rng = np.random.default_rng(7)
-    a, b, sa, sb = _sq_inputs(rng, 4, 768, 768, per_token, per_channel)
+    a, b, sa, sb = _sq_inputs(rng, M, N, K, per_token, per_channel)
     y = host(ops.smooth_quant_gemm(dev(a), dev(b), dev(sa), dev(sb), per_token, per_channel, use_gemv=True))
     assert np.array_equal(y, R.sq_gemm(a, b, sa, sb, np.float16))   # bit-exact (test_smooth_quant_gemm.py:109)
 
 
-def test_gemv_swiglu(ops):
+@pytest.mark.parametrize("M,K,inter", [(2, 1024, 384), (8, 4096, 1000), (1, 136, 24)])
+def test_gemv_swiglu(ops, M, K, inter):
     rng = np.random.default_rng(8)
-    M, K, inter = 2, 1024, 384
     x = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
     w = (rng.standard_normal((2 * inter, K)) * 0.05).astype(np.float16)
     y = host(ops.gemv(ops.KIND_F16, dev(x), dev(w), swiglu=True))
@@ -157,7 +163,7 @@ def test_gemv_swiglu(ops):
     np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), rtol=4e-3, atol=2e-3)
 
 
-@pytest.mark.parametrize("M", [1, 2, 3])
+@pytest.mark.parametrize("M", [1, 2, 3, 8])
 @pytest.mark.parametrize("N,K,swiglu", [(512, 4096, False), (768, 11008, False), (2 * 384, 4096, True), (10, 256, False)])
 def test_gemv_fused_rmsnorm(ops, M, N, K, swiglu):
     """prologue 1: the TRT-native rms_norm in front of a projection, fused into the GEMV's activation staging."""
@@ -172,7 +178,7 @@ def test_gemv_fused_rmsnorm(ops, M, N, K, swiglu):
     np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), rtol=4e-3, atol=4e-3)
 
 
-@pytest.mark.parametrize("M", [1, 4])
+@pytest.mark.parametrize("M", [1, 4, 8])
 @pytest.mark.parametrize("prologue", [2, 3])
 def test_gemv_fused_quant_prologues(ops, M, prologue):
     """prologue 2 = RmsnormQuantization, 3 = QuantizePerToken, fused in front of the W8A8 GEMV."""

@@ -2,3 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "../../include/trtllm_b200.h"
+
+namespace tb {
+// gemv_mma.cu: tensor-core decode projection (M <= 8) used by tb_gemv_fused whenever the shape is eligible
+bool gemv_mma_eligible(int kind, int M, int K);
+int gemv_mma_launch(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
+                    const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
+                    int swiglu, int prologue, const void* gamma, float eps, cudaStream_t stream);
+}  // namespace tb

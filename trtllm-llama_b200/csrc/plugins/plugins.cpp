@@ -232,10 +232,10 @@ class SmoothQuantGemmPlugin : public BasePlugin {
       const void* gamma = prologue_ == 2 ? in[next++] : nullptr;
       const float* st = static_cast<const float*>(in[2]);
       const float* sc = static_cast<const float*>(in[3]);
-      if (M <= 4 && is_half(type_))
+      if (M <= tb_gemv_max_rows(3, K) && is_half(type_))
         return tb_gemv_fused(3, out[0], nullptr, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K,
                              swiglu_, prologue_, gamma, eps_, stream);
-      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= 4) path");
+      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= tb_gemv_max_rows) path");
       const int ot = is_half(type_) ? 0 : (type_ == (int32_t) DataType::kFLOAT ? 1 : 2);
       (void) od;
       return tb_gemm_tc(3, out[0], ot, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K, workspace,
@@ -323,10 +323,10 @@ class WeightOnlyQuantMatmulPlugin : public BasePlugin {
       int next = 3;
       const void* res = residual_ ? in[next++] : nullptr;
       const void* gamma = prologue_ ? in[next++] : nullptr;
-      if (M <= 4)
+      if (M <= tb_gemv_max_rows(kind, K))
         return tb_gemv_fused(kind, out[0], nullptr, in[0], in[1], in[2], nullptr, nullptr, 0, 0, res, M, N, K, swiglu_,
                              prologue_, gamma, eps_, stream);
-      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= 4) path");
+      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= tb_gemv_max_rows) path");
       return tb_gemm_tc(kind, out[0], 0, in[0], in[1], in[2], nullptr, nullptr, 0, 0, res, M, N, K, workspace,
                         tb_gemm_tc_workspace_bytes(M, N, K), counters_.get(tb_gemm_tc_counter_bytes()), 0, 0, stream);
     });
@@ -413,10 +413,10 @@ class GemmPlugin : public BasePlugin {
       int next = 2;
       const void* res = residual_ ? in[next++] : nullptr;
       const void* gamma = prologue_ ? in[next++] : nullptr;
-      if (M <= 4)
+      if (M <= tb_gemv_max_rows(0, K))
         return tb_gemv_fused(0, out_fp32_ ? nullptr : out[0], out_fp32_ ? static_cast<float*>(out[0]) : nullptr, in[0],
                              in[1], nullptr, nullptr, nullptr, 0, 0, res, M, N, K, swiglu_, prologue_, gamma, eps_, stream);
-      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= 4) path");
+      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= tb_gemv_max_rows) path");
       return tb_gemm_tc(0, out[0], out_fp32_ ? 1 : 0, in[0], in[1], nullptr, nullptr, nullptr, 0, 0, res, M, N, K,
                         workspace, tb_gemm_tc_workspace_bytes(M, N, K), counters_.get(tb_gemm_tc_counter_bytes()), 0, 0,
                         stream);

@@ -331,7 +331,11 @@ int tbrt_engine::linear(IPluginV2DynamicExt* p, const LinearW& w, const void* in
 int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
   const int hid = c.hidden, Bq = context ? M / S : M;
   const bool sq = c.mode == TBRT_MODE_SQ, tp = c.tp_size > 1;
-  const bool fuse_swiglu = M <= 4;
+  const int kind = c.mode;   // TBRT_MODE_* == tb_gemv kind
+  int gemv_rows = tb_gemv_max_rows(kind, c.hidden);
+  if (tb_gemv_max_rows(kind, hid_l) < gemv_rows) gemv_rows = tb_gemv_max_rows(kind, hid_l);
+  if (tb_gemv_max_rows(kind, inter_l) < gemv_rows) gemv_rows = tb_gemv_max_rows(kind, inter_l);
+  const bool fuse_swiglu = M <= gemv_rows;
   int host_len[2] = {context ? 0 : c.max_input_len, context ? 1 : 0};   // device_lengths [ext]: step position is on the device
 
   auto norm = [&](const __half* src, const void* gamma, const __half* residual, __half* sum_out) -> int {
@@ -361,7 +365,7 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
   };
   const void* lin_in = sq ? static_cast<const void*>(xq) : static_cast<const void*>(x);
   // decode shapes: RMSNorm (+ per-token quantisation) rides in the projection's prologue -> 5 kernels per layer
-  const bool fused = M <= 4;
+  const bool fused = M <= gemv_rows;
 
   __half* cur = h;   // residual stream
   __half* nxt = h2;
@@ -451,7 +455,7 @@ int tbrt_engine::head(int rows, const __half* src, cudaStream_t s) {
   LinearW w;
   w.w = lm_head; w.N = vocab_l; w.K = c.hidden;
   launches += 2;
-  if (c.tp_size == 1 && rows <= 4) {
+  if (c.tp_size == 1 && rows <= tb_gemv_max_rows(0, c.hidden)) {
     RT_CALL(linear(lm_n.get(), w, src, nullptr, logits, nullptr, rows, DataType::kFLOAT, s, ln_f));
   } else if (c.tp_size == 1) {
     launches += 1;

@@ -144,7 +144,7 @@ def smooth_quant_gemm(x_i8, w_i8, scale_tokens, scale_channels, per_token_scalin
     x int8 [..., K], w int8 [N, K]; scales fp32 ([M,1]|[1,1], [1,N]|[1,1])."""
     M = x_i8.numel() // x_i8.shape[-1]
     if use_gemv is None:
-        use_gemv = M <= 4 and out_dtype == torch.float16
+        use_gemv = M <= lib.tb_gemv_max_rows(KIND_A8W8, x_i8.shape[-1]) and out_dtype == torch.float16
     if use_gemv:
         return gemv(KIND_A8W8, x_i8, w_i8, sc=scale_channels, sr=scale_tokens)
     return gemm_tc(KIND_A8W8, x_i8, w_i8, sc=scale_channels, sr=scale_tokens, out_dtype=out_dtype)
@@ -156,7 +156,7 @@ def weight_only_quant_matmul(x, w_processed, scales, weight_type_id, use_gemv=No
     kind = KIND_W8 if weight_type_id == 1 else KIND_W4
     M = x.numel() // x.shape[-1]
     if use_gemv is None:
-        use_gemv = M <= 4
+        use_gemv = M <= lib.tb_gemv_max_rows(kind, x.shape[-1])
     if use_gemv:
         return gemv(kind, x, w_processed, w_scale=scales)
     return gemm_tc(kind, x, w_processed, w_scale=scales)
@@ -166,7 +166,7 @@ def matmul_f16(x, w, residual=None, out_fp32=False, use_gemv=None):
     """Gemm plugin / TRT-native MatMul(x, W^T), W [N,K] (T/tensorrt_llm/layers/linear.py:13-35)."""
     M = x.numel() // x.shape[-1]
     if use_gemv is None:
-        use_gemv = M <= 4
+        use_gemv = M <= lib.tb_gemv_max_rows(KIND_F16, x.shape[-1])
     if use_gemv:
         return gemv(KIND_F16, x, w, residual=residual, out_fp32=out_fp32)
     return gemm_tc(KIND_F16, x, w, residual=residual, out_dtype=torch.float32 if out_fp32 else torch.float16)
