@@ -77,7 +77,10 @@ def test_engine_matches_oracle(mode, int8_kv, B):
         decided = (top2[:, 1] - top2[:, 0]) > 2 * tol
         assert np.array_equal(got_ids[decided, s], ref_ids[decided, s]), f"greedy ids differ at step {s}"
         if not np.array_equal(got_ids[:, s], ref_ids[:, s]):
-            pytest.skip("near-tie in the oracle's logits: sequences diverge legitimately after this step")
+            # a near-tie (margin below the logit tolerance) was broken differently: the sequences legitimately differ
+            # from here on, so the step-wise comparison ends; everything up to and including this step was checked
+            assert s >= 1, "diverged already at the context step"
+            return
 
     # KV cache of layer 0 for the real (non-padded) positions
     kv = sess.kv_cache(0).cpu().numpy()

@@ -24,6 +24,7 @@ namespace tb {
 
 constexpr int kMmhaThreads = 256;
 constexpr int kDh = 128;
+constexpr int kMaxClusterSplits = 8;                 // portable thread-block-cluster limit
 
 struct MmhaParams {
   const __half* qkv;         // [B, 3*H*Dh]
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(kMmhaThreads) mmha_decode_kernel(MmhaParams p)
   __shared__ __align__(16) __half kcur_s[kDh];
   __shared__ __align__(16) __half vcur_s[kDh];
   __shared__ float red[2 * (kMmhaThreads / 32)];
-  __shared__ int s_is_last;
+  __shared__ float c_o[kMaxClusterSplits][kDh];      // split partial outputs, written by the cluster's CTAs into rank 0
+  __shared__ float c_ml[kMaxClusterSplits][2];       // split (max, sum)
 
   const int h = blockIdx.x, b = blockIdx.y, split = blockIdx.z, nsplit = gridDim.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -258,44 +260,46 @@ __global__ void __launch_bounds__(kMmhaThreads) mmha_decode_kernel(MmhaParams p)
   for (int j = 0; j < DPL; ++j) o_red[grp * kDh + gl * DPL + j] = acc[j] * kv_dq;
   __syncthreads();
 
-  float* part = p.partial + ((size_t) (b * H + h) * nsplit + split) * (kDh + 2);
+  if (nsplit == 1) {
+    if (tid < kDh) {
+      float o = 0.f;
+#pragma unroll 8
+      for (int g = 0; g < KPI; ++g) o += o_red[g * kDh + tid];
+      if (has_cur) o = fmaf(s_s[len], __half2float(vcur_s[tid]), o);
+      p.out[(size_t) b * hidden + h * kDh + tid] = __float2half_rn(o);
+    }
+    return;
+  }
+
+  // ---- split-L combine inside the thread-block cluster: every CTA of the (b, h) cluster stores its partial
+  // (o, max, sum) into rank 0's shared memory through DSMEM; after the cluster barrier rank 0 merges the splits
+  // in index order (deterministic, no atomics, no global round trip) -------------------------------------------
   if (tid < kDh) {
     float o = 0.f;
 #pragma unroll 8
     for (int g = 0; g < KPI; ++g) o += o_red[g * kDh + tid];
     if (has_cur) o = fmaf(s_s[len], __half2float(vcur_s[tid]), o);
-    if (nsplit == 1) {
-      p.out[(size_t) b * hidden + h * kDh + tid] = __float2half_rn(o);
-    } else {
-      part[tid] = o;
-      if (tid == 0) { part[kDh] = m_s; part[kDh + 1] = l_s; }
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&c_o[split][tid])), "r"(0));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(o) : "memory");
+    if (tid < 2) {
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&c_ml[split][tid])), "r"(0));
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(tid == 0 ? m_s : l_s) : "memory");
     }
   }
-  if (nsplit == 1) return;
-
-  // ---- last CTA of this (b, h) combines the splits in index order (deterministic) --------------
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int prev = atomicAdd(&p.counters[b * H + h], 1);
-    s_is_last = (prev == nsplit - 1);
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (split != 0) return;
   if (tid < kDh) {
-    const float* pb = p.partial + (size_t) (b * H + h) * nsplit * (kDh + 2);
     float gm = -3.0e38f;
-    for (int s = 0; s < nsplit; ++s) gm = fmaxf(gm, __ldcg(pb + s * (kDh + 2) + kDh));
+    for (int s = 0; s < nsplit; ++s) gm = fmaxf(gm, c_ml[s][0]);
     float o = 0.f, l = 0.f;
     for (int s = 0; s < nsplit; ++s) {
-      const float w = __expf(__ldcg(pb + s * (kDh + 2) + kDh) - gm);
-      o = fmaf(w, __ldcg(pb + s * (kDh + 2) + tid), o);
-      l = fmaf(w, __ldcg(pb + s * (kDh + 2) + kDh + 1), l);
+      const float w = __expf(c_ml[s][0] - gm);
+      o = fmaf(w, c_o[s][tid], o);
+      l = fmaf(w, c_ml[s][1], l);
     }
     p.out[(size_t) b * hidden + h * kDh + tid] = __float2half_rn(o * __fdividef(1.f, l + 1.e-6f));
   }
-  if (tid == 0) p.counters[b * H + h] = 0;
 }
 
 }  // namespace tb
@@ -317,6 +321,7 @@ int tb_mmha_num_splits(int batch, int num_heads, int len_hint, int max_splits) {
   if (by_len < 1) by_len = 1;
   int n = want < by_len ? want : by_len;
   if (n > max_splits) n = max_splits;
+  if (n > kMaxClusterSplits) n = kMaxClusterSplits;   // the splits of one (b, h) form a thread-block cluster
   if (n < 1) n = 1;
   return n;
 }
@@ -331,7 +336,8 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
   if (past_len + 1 > max_seq_len || len_cap + 1 > max_seq_len + 1) return -2;
   if (int8_kv && (!kv_scale_orig_quant || !kv_scale_quant_orig)) return -1;
   if (nsplit < 1) nsplit = 1;
-  if (nsplit > 1 && (!workspace || !counters)) return -1;
+  if (nsplit > kMaxClusterSplits) return -1;
+  (void) workspace; (void) counters;   // kept in the ABI: split partials now live in distributed shared memory
   MmhaParams p{};
   p.qkv = (const __half*) qkv; p.kv_cache = kv_cache; p.out = (__half*) out; p.seq_lens = seq_lens;
   p.input_lengths = input_lengths; p.masked_tokens = masked_tokens;
@@ -346,14 +352,23 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
   chunk = (chunk + kpi - 1) / kpi * kpi;
   const size_t smem = ((size_t) ((chunk + 1 + 3) & ~3) + (size_t) kpi * kDh) * sizeof(float);
   if (smem > 200 * 1024) return -3;
-  dim3 grid(num_heads, batch, nsplit);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_heads, batch, nsplit);
+  cfg.blockDim = dim3(kMmhaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = nsplit;
+  cfg.attrs = attr;
+  cfg.numAttrs = nsplit > 1 ? 1 : 0;
   if (int8_kv) {
     if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    mmha_decode_kernel<true><<<grid, kMmhaThreads, smem, stream>>>(p);
-  } else {
-    if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    mmha_decode_kernel<false><<<grid, kMmhaThreads, smem, stream>>>(p);
+    return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<true>, p);
   }
-  return (int) cudaGetLastError();
+  if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<false>, p);
 }
 }

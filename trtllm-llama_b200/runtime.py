@@ -156,8 +156,11 @@ class GenerationSession:
 
     def __del__(self):
         e, self._e = getattr(self, "_e", None), None
-        if e:
-            lib.tbrt_destroy(e)
+        try:
+            if e:
+                lib.tbrt_destroy(e)
+        except Exception:      # interpreter shutdown: the library wrapper may already be gone
+            pass
 
     @property
     def device_bytes(self):
