@@ -34,6 +34,7 @@ WORKLOADS = {
     "cfg3": ("w8", False, 8, 1920, 128, "LLaMA-7B weight-only int8, batch=8, 2048-ctx decode (1920-in/128-out), fp16 KV"),
     "cfg3_int8kv": ("w8", True, 8, 1920, 128, "LLaMA-7B weight-only int8 + int8 KV, batch=8, 2048-ctx decode"),
     "cfg5": ("w4", True, 1, 128, 128, "LLaMA-7B int4 weight-only + int8 KV-cache, batch=1, 128-in/128-out"),
+    "w8_b1": ("w8", True, 1, 128, 128, "LLaMA-7B weight-only int8 + int8 KV-cache, batch=1, 128-in/128-out"),
     "sq": ("sq", True, 1, 128, 128, "LLaMA-7B SmoothQuant per-token/per-channel int8 + int8 KV, batch=1, 128-in/128-out"),
 }
 

@@ -165,7 +165,13 @@ def test_product_quantiser_matches_oracle_bit_exact():
         q, s = R.symmetric_quantize(np.ascontiguousarray(w_nk.T), bits)
         unp, proc, sc = Q._symmetric_quantize_last_axis_of_batched_matrix(torch.from_numpy(w_nk).t(), qt)
         q_nk = np.ascontiguousarray(q.T)
-        assert np.array_equal(proc.numpy(), q_nk if bits == 8 else R.pack_int4(q_nk))
+        if bits == 8:
+            assert np.array_equal(proc.numpy(), q_nk)
+        else:
+            # processed int4: nibble positions of every 8-element group hold elements (0,2,4,6,1,3,5,7)
+            assert np.array_equal(Q.unpack_processed_int4(proc).numpy(), q_nk)
+            grp = q_nk.reshape(q_nk.shape[0], -1, 8)[:, :, [0, 2, 4, 6, 1, 3, 5, 7]].reshape(q_nk.shape)
+            assert np.array_equal(proc.numpy(), R.pack_int4(grp))
         assert np.array_equal(unp.numpy(), q if bits == 8 else R.pack_int4(q))
         assert np.array_equal(sc.numpy().view(np.uint16), s.view(np.uint16))
         # round trip helpers (thop/weightOnlyQuantOp.cpp:347-356)

@@ -93,13 +93,18 @@ def test_quantize_tensor(ops):
 
 
 # ------------------------------------------------------------------------------------------------
+def _pack_processed_int4(q_nk):
+    from trtllm_llama_b200.quantization import pack_processed_int4
+    return pack_processed_int4(torch.from_numpy(np.ascontiguousarray(q_nk))).numpy()
+
+
 def _wo_inputs(rng, M, N, K, bits):
     w = (rng.random((K, N), dtype=np.float32) * 2 - 1).astype(np.float16)       # test_weight_only_quant_matmul.py:87
     q, scales = R.symmetric_quantize(w, bits)
     x = (rng.random((M, K), dtype=np.float32) * 0.2 - 0.1).astype(np.float16)
     ref = R.weight_only_matmul(x, q, scales)
     qt = np.ascontiguousarray(q.T)                                               # this repo's processed layout [N, K]
-    wp = qt if bits == 8 else R.pack_int4(qt)
+    wp = qt if bits == 8 else _pack_processed_int4(qt)
     return x, wp, scales, ref
 
 

@@ -169,7 +169,8 @@ def test_weight_only_gemv_reference_kernel(ref, ops, bits):
     tol = 1.5 * np.abs(y_or).max() / (1 << (bits - 1))   # reference's own tolerance (_utils.py:62-89)
     np.testing.assert_allclose(y_or, y_ref, atol=tol)
     qt = np.ascontiguousarray(q.T)
-    wp = qt if bits == 8 else R.pack_int4(qt)
+    from trtllm_llama_b200.quantization import pack_processed_int4
+    wp = qt if bits == 8 else pack_processed_int4(torch.from_numpy(np.ascontiguousarray(qt))).numpy()
     for use_gemv in (True, False):
         y_my = host(ops.weight_only_quant_matmul(d_x, dev(wp), d_s, 1 if bits == 8 else 2, use_gemv=use_gemv))
         np.testing.assert_allclose(y_my.astype(np.float32), y_ref, atol=tol)

@@ -56,17 +56,25 @@ __device__ __forceinline__ void i8x4_to_h2x2(uint32_t w, __half2& lo, __half2& h
   lo = __hsub2(*reinterpret_cast<__half2*>(&l), bias);
   hi = __hsub2(*reinterpret_cast<__half2*>(&h), bias);
 }
-// 8 packed signed int4 (nibble i = element i) -> 4 half2 {e0,e1},{e2,e3},{e4,e5},{e6,e7}, exact.
+// 8 packed signed int4 in this library's processed order (nibble positions 0..7 hold elements 0,2,4,6,1,3,5,7;
+// quantization.py pack_processed_int4) -> 4 half2 {e0,e1},{e2,e3},{e4,e5},{e6,e7}, exact.
+// n ^ 8 is the offset-binary nibble; (x & 0x000F000F) | 0x64006400 is the half2 {1024 + n_lo, 1024 + n_hi}: subtract
+// 1032.  The nibbles one position up come out as 1024 + 16 n: one HFMA2 with 1/16 and -(64 + 8) (exact: <= 11 bits).
 __device__ __forceinline__ void i4x8_to_h2x4(uint32_t w, __half2 out[4]) {
-  // (n ^ 8) | 0x6400 = 1024 + (n + 8) ; subtract 1032.
-  uint32_t u = w ^ 0x88888888u;
-  const __half2 bias = __halves2half2(__ushort_as_half(0x6408), __ushort_as_half(0x6408));
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t b = (u >> (8 * i)) & 0xffu;           // two nibbles: low = e(2i), high = e(2i+1)
-    uint32_t v = (b & 0xfu) | ((b >> 4) << 16) | 0x64006400u;
-    out[i] = __hsub2(*reinterpret_cast<__half2*>(&v), bias);
-  }
+  const uint32_t u = w ^ 0x88888888u;
+  const __half2 bias = __halves2half2(__ushort_as_half(0x6408), __ushort_as_half(0x6408));         // 1032
+  const __half2 sixteenth = __halves2half2(__ushort_as_half(0x2C00), __ushort_as_half(0x2C00));    // 1/16
+  const __half2 bias16 = __halves2half2(__ushort_as_half(0xD480), __ushort_as_half(0xD480));       // -72
+  uint32_t t0, t1, t2, t3;
+  asm("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(t0) : "r"(u));        // (u & m) | c : elements {e0, e1}
+  asm("lop3.b32 %0, %1, 0x00F000F0, 0x64006400, 0xEA;" : "=r"(t1) : "r"(u));        // {e2, e3} * 16
+  const uint32_t v = u >> 8;
+  asm("lop3.b32 %0, %1, 0x000F000F, 0x64006400, 0xEA;" : "=r"(t2) : "r"(v));        // {e4, e5}
+  asm("lop3.b32 %0, %1, 0x00F000F0, 0x64006400, 0xEA;" : "=r"(t3) : "r"(v));        // {e6, e7} * 16
+  out[0] = __hsub2(*reinterpret_cast<__half2*>(&t0), bias);
+  out[1] = __hfma2(*reinterpret_cast<__half2*>(&t1), sixteenth, bias16);
+  out[2] = __hsub2(*reinterpret_cast<__half2*>(&t2), bias);
+  out[3] = __hfma2(*reinterpret_cast<__half2*>(&t3), sixteenth, bias16);
 }
 
 // ---------------------------------------------------------------------------------------------

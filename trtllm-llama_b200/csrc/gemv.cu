@@ -23,6 +23,7 @@
 // Weight layouts (this library's processed layouts, quantization.py):
 //   fp16: [N, K] (torch Linear)      int8: [N, K]      int4: [N, K/2], low nibble = even k.
 // Algorithmic bytes per launch = N*K*bytes_per_weight (+ M*(K+N)*2, < 0.1 %).
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -405,9 +406,12 @@ extern "C" int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, con
   if ((prologue >= kProRmsQuant) != (kind == kA8W8) && prologue != kProNone && prologue != kProRms) return -1;
   if (prologue == kProRms && kind == kA8W8) return -1;
   if (swiglu && residual) return -1;
-  // M <= 4: the FMA kernel's one-warp-per-row stream is faster (measured: fp16 2.73 vs 3.28 ms per LLaMA-7B step,
-  // W8A8 1.83 vs 2.70 ms); the tensor-core kernel takes the batches it cannot (5..8 rows)
-  if (M > 4 && gemv_mma_eligible(kind, M, K))
+  // Which kernel: measured on LLaMA-7B decode steps (B200, CUDA-graph replay).  M <= 4: the FMA kernel's
+  // one-warp-per-row stream wins for fp16 (2.66 vs 2.99 ms), W8 (2.17 vs 2.30) and W8A8 (1.84 vs 2.74); int4 is
+  // conversion-bound on FMAs and wins on tensor cores (2.05 vs 2.26 ms).  5..8 rows: tensor-core kernel only.
+  static const int mma_min_m_env = getenv("TB_GEMV_MMA_MIN_M") ? atoi(getenv("TB_GEMV_MMA_MIN_M")) : 0;   // A/B switch
+  const int mma_min_m = mma_min_m_env > 0 ? mma_min_m_env : (kind == kW4 ? 1 : 5);
+  if (M >= mma_min_m && gemv_mma_eligible(kind, M, K))
     return gemv_mma_launch(kind, y, y_f32, x, w, w_scale, sc, sr, sc_per_channel, sr_per_token, residual, M, N, K, swiglu,
                            prologue, gamma, eps, stream);
   switch (kind) {

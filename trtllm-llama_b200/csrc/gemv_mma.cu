@@ -43,7 +43,7 @@ struct GemvMmaParams {
 
 constexpr int kMmaThreads = 256;
 constexpr int kMmaWarps = 8;
-constexpr int kMmaU = 4;   // k-steps in flight per lane (2 x 16-byte loads each)
+constexpr int kMmaU = 8;   // k-steps in flight per lane (2 x 16-byte loads each)
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                         uint32_t b1) {
@@ -98,7 +98,7 @@ __device__ __forceinline__ float cta_reduce_mma(float v, float* red, bool is_max
 }
 
 template <int KIND, bool SWIGLU>
-__global__ void __launch_bounds__(kMmaThreads, 3) gemv_mma_kernel(const GemvMmaParams p) {
+__global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   using TR = MmaTraits<KIND>;
   constexpr bool INT = KIND == kMA8W8;
@@ -106,23 +106,16 @@ __global__ void __launch_bounds__(kMmaThreads, 3) gemv_mma_kernel(const GemvMmaP
   float* red = reinterpret_cast<float*>(smem);             // [8]
   float* srow = red + 8;                                    // [8] per-token scales (W8A8)
   float* wpart = srow + 8;                                  // [8 warps][16][8] per-warp partial tiles
-  float* cpart = wpart + kMmaWarps * 128;                   // [4 ranks][16][8] per-CTA partial tiles (cluster reduce)
-  uint8_t* xs = reinterpret_cast<uint8_t*>(cpart + 4 * 128);   // [M][K * XB] only when a prologue transforms x
+  float* cpart = wpart + kMmaWarps * 128;                   // [2 parities][4 ranks][16][8] per-CTA partial tiles (cluster reduce)
+  uint8_t* xs = reinterpret_cast<uint8_t*>(cpart + 2 * 4 * 128);   // [M][K * XB] only when a prologue transforms x
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int K = p.K, M = p.M;
   const uint32_t crank = p.S > 1 ? cluster_rank() : 0;
-  const int tile = blockIdx.x / p.S;
   const int row_bytes = K / TR::kStepElems * 64;
   const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
-  // rows of this tile: fragment row g and g + 8
-  const int r_lo = SWIGLU ? tile * 8 + g : tile * 16 + g;
-  const int r_hi = SWIGLU ? p.n_out + tile * 8 + g : tile * 16 + 8 + g;
+  const int tiles = SWIGLU ? (p.n_out + 7) / 8 : (p.N + 15) / 16;
   const int rows_real = SWIGLU ? 2 * p.n_out : p.N;
-  const bool lo_ok = SWIGLU ? (tile * 8 + g < p.n_out) : (r_lo < rows_real);
-  const bool hi_ok = SWIGLU ? lo_ok : (r_hi < rows_real);
-  const uint8_t* p_lo = wbase + (size_t) (lo_ok ? r_lo : 0) * row_bytes + t * 16;
-  const uint8_t* p_hi = wbase + (size_t) (hi_ok ? r_hi : 0) * row_bytes + t * 16;
   // this warp's K slab
   const int ksteps = K / TR::kStepElems;
   const int slabs = kMmaWarps * p.S, slab = crank * kMmaWarps + warp;
@@ -139,13 +132,15 @@ __global__ void __launch_bounds__(kMmaThreads, 3) gemv_mma_kernel(const GemvMmaP
     if (INT && tid < 8) srow[tid] = tid < M ? p.sr[p.sr_per_token ? tid : 0] : 0.f;
     if (INT) __syncthreads();
   } else {
+    // one warp per token row (M <= 8 rows, 8 warps): every row's statistics are warp-local reductions, so the rows
+    // proceed in parallel and the whole prologue costs two L2 round trips instead of 2 x M block-wide ones
     const __half* xin = reinterpret_cast<const __half*>(p.x);
-    for (int m = 0; m < M; ++m) {
+    for (int m = warp; m < M; m += kMmaWarps) {
       const __half* xr = xin + (size_t) m * K;
       float inv = 1.f;
       if (p.prologue != kMProQuant) {
         float sq = 0.f;
-        for (int i = tid * 8; i < K; i += kMmaThreads * 8) {
+        for (int i = lane * 8; i < K; i += 32 * 8) {
           uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
           const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
@@ -154,11 +149,11 @@ __global__ void __launch_bounds__(kMmaThreads, 3) gemv_mma_kernel(const GemvMmaP
             sq += f.x * f.x + f.y * f.y;
           }
         }
-        sq = cta_reduce_mma(sq, red, false);
+        sq = warp_sum(sq);
         inv = rsqrtf(sq / K + p.eps);
       }
       float amax = 0.f;
-      for (int i = tid * 8; i < K; i += kMmaThreads * 8) {
+      for (int i = lane * 8; i < K; i += 32 * 8) {
         uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
         __half2* h = reinterpret_cast<__half2*>(&raw);
         if (p.prologue != kMProQuant) {
@@ -181,10 +176,10 @@ __global__ void __launch_bounds__(kMmaThreads, 3) gemv_mma_kernel(const GemvMmaP
         }
       }
       if constexpr (INT) {
-        amax = fmaxf(cta_reduce_mma(amax, red, true), __half2float(__float2half_rn(1e-6f)));
+        amax = fmaxf(warp_max(amax), __half2float(__float2half_rn(1e-6f)));
         const float qs = 127.f / amax;
-        if (tid == 0) srow[m] = amax / 127.f;
-        for (int i = tid * 8; i < K; i += kMmaThreads * 8) {
+        if (lane == 0) srow[m] = amax / 127.f;
+        for (int i = lane * 8; i < K; i += 32 * 8) {
           uint4 raw = *reinterpret_cast<const uint4*>(xr + i);
           __half2* h = reinterpret_cast<__half2*>(&raw);
           float f[8];
@@ -209,138 +204,153 @@ __global__ void __launch_bounds__(kMmaThreads, 3) gemv_mma_kernel(const GemvMmaP
     xsrc = xs;
   }
 
-  // ---- main loop: stream this warp's slab of the 16 rows -------------------------------------------------------------
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  int iacc[4] = {0, 0, 0, 0};
+  // ---- persistent loop over 16-row tiles: the prologue above is paid once per CTA --------------------------------------
   const bool x_ok = g < M;                                   // fragment column g = token g
   const uint8_t* xrow = xsrc + (size_t) (x_ok ? g : 0) * xstride + (size_t) t * TR::kXBytesPerLane;
   constexpr int XSTEP = TR::kStepElems * XB;                 // activation bytes per k-step per token
+  const int nclusters = gridDim.x / p.S;
+  int parity = 0;
+  for (int tile = blockIdx.x / p.S; tile < tiles; tile += nclusters, parity ^= 1) {
+    // rows of this tile: fragment row g and g + 8
+    const int r_lo = SWIGLU ? tile * 8 + g : tile * 16 + g;
+    const int r_hi = SWIGLU ? p.n_out + tile * 8 + g : tile * 16 + 8 + g;
+    const bool lo_ok = SWIGLU ? (tile * 8 + g < p.n_out) : (r_lo < rows_real);
+    const bool hi_ok = SWIGLU ? lo_ok : (r_hi < rows_real);
+    const uint8_t* p_lo = wbase + (size_t) (lo_ok ? r_lo : 0) * row_bytes + t * 16;
+    const uint8_t* p_hi = wbase + (size_t) (hi_ok ? r_hi : 0) * row_bytes + t * 16;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int iacc[4] = {0, 0, 0, 0};
 
-  auto consume = [&](const uint4& lo, const uint4& hi, int ks) {
-    const uint8_t* xp = xrow + (size_t) ks * XSTEP;
-    if constexpr (KIND == kMF16) {
-      uint4 xv = x_ok ? ld_x16(xp) : make_uint4(0, 0, 0, 0);
-      mma_f16(acc, lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
-      mma_f16(acc, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
-    } else if constexpr (KIND == kMA8W8) {
-      uint4 xv = x_ok ? ld_x16(xp) : make_uint4(0, 0, 0, 0);
-      mma_s8(iacc, lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
-      mma_s8(iacc, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
-    } else if constexpr (KIND == kMW8) {
-      uint4 xa = make_uint4(0, 0, 0, 0), xb = xa;
-      if (x_ok) { xa = ld_x16(xp); xb = ld_x16(xp + 16); }
-      const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
-      const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    auto consume = [&](const uint4& lo, const uint4& hi, int ks) {
+      const uint8_t* xp = xrow + (size_t) ks * XSTEP;
+      if constexpr (KIND == kMF16) {
+        uint4 xv = x_ok ? ld_x16(xp) : make_uint4(0, 0, 0, 0);
+        mma_f16(acc, lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
+        mma_f16(acc, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
+      } else if constexpr (KIND == kMA8W8) {
+        uint4 xv = x_ok ? ld_x16(xp) : make_uint4(0, 0, 0, 0);
+        mma_s8(iacc, lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
+        mma_s8(iacc, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
+      } else if constexpr (KIND == kMW8) {
+        uint4 xa = make_uint4(0, 0, 0, 0), xb = xa;
+        if (x_ok) { xa = ld_x16(xp); xb = ld_x16(xp + 16); }
+        const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
+        const uint32_t xw[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {       // 4 int8 of each row -> one MMA
-        __half2 l0, l1, h0, h1;
-        i8x4_to_h2x2(wl[j], l0, l1);
-        i8x4_to_h2x2(wh[j], h0, h1);
-        mma_f16(acc, h2u(l0), h2u(h0), h2u(l1), h2u(h1), xw[2 * j], xw[2 * j + 1]);
+        for (int j = 0; j < 4; ++j) {       // 4 int8 of each row -> one MMA
+          __half2 l0, l1, h0, h1;
+          i8x4_to_h2x2(wl[j], l0, l1);
+          i8x4_to_h2x2(wh[j], h0, h1);
+          mma_f16(acc, h2u(l0), h2u(h0), h2u(l1), h2u(h1), xw[2 * j], xw[2 * j + 1]);
+        }
+      } else {  // kMW4
+        const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {       // 8 int4 of each row -> two MMAs
+          __half2 l[4], h[4];
+          i4x8_to_h2x4(wl[j], l);
+          i4x8_to_h2x4(wh[j], h);
+          uint4 xv = x_ok ? ld_x16(xp + 16 * j) : make_uint4(0, 0, 0, 0);
+          mma_f16(acc, h2u(l[0]), h2u(h[0]), h2u(l[1]), h2u(h[1]), xv.x, xv.y);
+          mma_f16(acc, h2u(l[2]), h2u(h[2]), h2u(l[3]), h2u(h[3]), xv.z, xv.w);
+        }
       }
-    } else {  // kMW4
-      const uint32_t wl[4] = {lo.x, lo.y, lo.z, lo.w}, wh[4] = {hi.x, hi.y, hi.z, hi.w};
+    };
+
+    int ks = ks0;
+    for (; ks + kMmaU <= ks1; ks += kMmaU) {
+      uint4 lo[kMmaU], hi[kMmaU];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {       // 8 int4 of each row -> two MMAs
-        __half2 l[4], h[4];
-        i4x8_to_h2x4(wl[j], l);
-        i4x8_to_h2x4(wh[j], h);
-        uint4 xv = x_ok ? ld_x16(xp + 16 * j) : make_uint4(0, 0, 0, 0);
-        mma_f16(acc, h2u(l[0]), h2u(h[0]), h2u(l[1]), h2u(h[1]), xv.x, xv.y);
-        mma_f16(acc, h2u(l[2]), h2u(h[2]), h2u(l[3]), h2u(h[3]), xv.z, xv.w);
+      for (int u = 0; u < kMmaU; ++u) {
+        lo[u] = ldg_nc_v4(p_lo + (size_t) (ks + u) * 64);
+        hi[u] = ldg_nc_v4(p_hi + (size_t) (ks + u) * 64);
       }
+#pragma unroll
+      for (int u = 0; u < kMmaU; ++u) consume(lo[u], hi[u], ks + u);
     }
-  };
+    for (; ks < ks1; ++ks) {
+      const uint4 lo = ldg_nc_v4(p_lo + (size_t) ks * 64), hi = ldg_nc_v4(p_hi + (size_t) ks * 64);
+      consume(lo, hi, ks);
+    }
 
-  int ks = ks0;
-  for (; ks + kMmaU <= ks1; ks += kMmaU) {
-    uint4 lo[kMmaU], hi[kMmaU];
+    // ---- reduce: warps (shared memory, warp order) then cluster ranks (DSMEM, rank order) -----------------------------
+    // fragment: c0,c1 = (row g, tokens 2t, 2t+1), c2,c3 = (row g + 8, tokens 2t, 2t+1)
+    {
+      float* wp = wpart + warp * 128;
+      float v[4];
 #pragma unroll
-    for (int u = 0; u < kMmaU; ++u) {
-      lo[u] = ldg_nc_v4(p_lo + (size_t) (ks + u) * 64);
-      hi[u] = ldg_nc_v4(p_hi + (size_t) (ks + u) * 64);
+      for (int i = 0; i < 4; ++i) v[i] = INT ? __int_as_float(iacc[i]) : acc[i];
+      wp[g * 8 + 2 * t] = v[0];
+      wp[g * 8 + 2 * t + 1] = v[1];
+      wp[(g + 8) * 8 + 2 * t] = v[2];
+      wp[(g + 8) * 8 + 2 * t + 1] = v[3];
     }
-#pragma unroll
-    for (int u = 0; u < kMmaU; ++u) consume(lo[u], hi[u], ks + u);
-  }
-  for (; ks < ks1; ++ks) {
-    const uint4 lo = ldg_nc_v4(p_lo + (size_t) ks * 64), hi = ldg_nc_v4(p_hi + (size_t) ks * 64);
-    consume(lo, hi, ks);
-  }
-
-  // ---- reduce: warps (shared memory, warp order) then cluster ranks (DSMEM, rank order) -------------------------------
-  // fragment: c0,c1 = (row g, tokens 2t, 2t+1), c2,c3 = (row g + 8, tokens 2t, 2t+1)
-  {
-    float* wp = wpart + warp * 128;
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = INT ? __int_as_float(iacc[i]) : acc[i];
-    wp[g * 8 + 2 * t] = v[0];
-    wp[g * 8 + 2 * t + 1] = v[1];
-    wp[(g + 8) * 8 + 2 * t] = v[2];
-    wp[(g + 8) * 8 + 2 * t + 1] = v[3];
-  }
-  __syncthreads();
-  float tot = 0.f;
-  int itot = 0;
-  if (tid < 128) {
-#pragma unroll
-    for (int w = 0; w < kMmaWarps; ++w) {
-      if constexpr (INT) itot += __float_as_int(wpart[w * 128 + tid]); else tot += wpart[w * 128 + tid];
-    }
-  }
-  if (p.S > 1) {
-    if (tid < 128) st_cluster_f32(cpart + crank * 128 + tid, 0, INT ? __int_as_float(itot) : tot);
-    cluster_sync_all();
-    if (crank != 0) return;
+    __syncthreads();
+    float tot = 0.f;
+    int itot = 0;
     if (tid < 128) {
-      tot = 0.f;
-      itot = 0;
-      for (int c = 0; c < p.S; ++c) {
-        if constexpr (INT) itot += __float_as_int(cpart[c * 128 + tid]); else tot += cpart[c * 128 + tid];
+#pragma unroll
+      for (int w = 0; w < kMmaWarps; ++w) {
+        if constexpr (INT) itot += __float_as_int(wpart[w * 128 + tid]); else tot += wpart[w * 128 + tid];
       }
     }
-  }
-  if (tid >= 128) return;
+    bool finisher = true;                                  // this CTA applies the epilogue for the tile
+    if (p.S > 1) {
+      float* cp = cpart + parity * (4 * 128);              // double-buffered by tile parity: one cluster barrier per tile
+      if (tid < 128) st_cluster_f32(cp + crank * 128 + tid, 0, INT ? __int_as_float(itot) : tot);
+      cluster_sync_all();
+      finisher = crank == 0;
+      if (finisher && tid < 128) {
+        tot = 0.f;
+        itot = 0;
+        for (int c = 0; c < p.S; ++c) {
+          if constexpr (INT) itot += __float_as_int(cp[c * 128 + tid]); else tot += cp[c * 128 + tid];
+        }
+      }
+    }
 
-  // ---- epilogue: thread = (fragment row r, token m) ---------------------------------------------------------------------
-  const int r = tid >> 3, m = tid & 7;
-  float v = INT ? (float) itot : tot;
-  const int wrow = SWIGLU ? (r < 8 ? tile * 8 + r : p.n_out + tile * 8 + (r - 8)) : tile * 16 + r;
-  const bool row_ok = SWIGLU ? (tile * 8 + (r & 7) < p.n_out) : (wrow < p.N);
-  if (row_ok) {
-    if constexpr (KIND == kMW8 || KIND == kMW4) v *= __half2float(p.w_scale[wrow]);
-    // reference grouping: accum * (scale_col * scale_row)  (epilogue_per_row_per_col_scale.h:325,341)
-    if constexpr (INT) v = v * (p.sc[p.sc_per_channel ? wrow : 0] * srow[m]);
-  }
-  if constexpr (SWIGLU) {
-    // rows 0-7 hold gate, rows 8-15 the matching up projection: exchange through shared memory
-    __syncwarp();
-    float* ex = wpart;   // reuse (all reads of wpart are done: only tid < 128 of rank 0 get here, after the sync above)
-    ex[tid] = v;
-    asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (r < 8 && row_ok && m < M) {
-      const float gte = __half2float(__float2half_rn(ex[r * 8 + m])), up = __half2float(__float2half_rn(ex[(r + 8) * 8 + m]));
-      const float o = __half2float(__float2half_rn(mma_silu(gte))) * up;
-      const size_t oi = (size_t) m * p.n_out + tile * 8 + r;
-      if (p.y_f32) p.y_f32[oi] = o; else p.y[oi] = __float2half_rn(o);
+    // ---- epilogue: thread = (fragment row r, token m) -------------------------------------------------------------------
+    if (finisher && tid < 128) {
+      const int r = tid >> 3, m = tid & 7;
+      float v = INT ? (float) itot : tot;
+      const int wrow = SWIGLU ? (r < 8 ? tile * 8 + r : p.n_out + tile * 8 + (r - 8)) : tile * 16 + r;
+      const bool row_ok = SWIGLU ? (tile * 8 + (r & 7) < p.n_out) : (wrow < p.N);
+      if (row_ok) {
+        if constexpr (KIND == kMW8 || KIND == kMW4) v *= __half2float(p.w_scale[wrow]);
+        // reference grouping: accum * (scale_col * scale_row)  (epilogue_per_row_per_col_scale.h:325,341)
+        if constexpr (INT) v = v * (p.sc[p.sc_per_channel ? wrow : 0] * srow[m]);
+      }
+      if constexpr (SWIGLU) {
+        // rows 0-7 hold gate, rows 8-15 the matching up projection: exchange through shared memory (slot 0 of wpart is
+        // only read by the thread that now overwrites it)
+        float* ex = wpart;
+        ex[tid] = v;
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (r < 8 && row_ok && m < M) {
+          const float gte = __half2float(__float2half_rn(ex[r * 8 + m])), up = __half2float(__float2half_rn(ex[(r + 8) * 8 + m]));
+          const float o = __half2float(__float2half_rn(mma_silu(gte))) * up;
+          const size_t oi = (size_t) m * p.n_out + tile * 8 + r;
+          if (p.y_f32) p.y_f32[oi] = o; else p.y[oi] = __float2half_rn(o);
+        }
+      } else if (row_ok && m < M) {
+        const size_t oi = (size_t) m * p.n_out + wrow;
+        if (p.y_f32) {
+          p.y_f32[oi] = v;
+        } else {
+          __half oh = __float2half_rn(v);
+          if (p.residual) oh = __float2half_rn(__half2float(oh) + __half2float(p.residual[oi]));
+          p.y[oi] = oh;
+        }
+      }
     }
-  } else if (row_ok && m < M) {
-    const size_t oi = (size_t) m * p.n_out + wrow;
-    if (p.y_f32) {
-      p.y_f32[oi] = v;
-    } else {
-      __half oh = __float2half_rn(v);
-      if (p.residual) oh = __float2half_rn(__half2float(oh) + __half2float(p.residual[oi]));
-      p.y[oi] = oh;
-    }
+    __syncthreads();   // wpart is rewritten by the next tile
   }
 }
 
 template <int KIND, bool SWIGLU>
 static int launch_gemv_mma(GemvMmaParams p, cudaStream_t stream) {
   const size_t xs_bytes = p.prologue ? (size_t) p.M * p.K * (KIND == kMA8W8 ? 1 : 2) : 0;
-  const size_t smem = (16 + kMmaWarps * 128 + 4 * 128) * sizeof(float) + xs_bytes;
+  const size_t smem = (16 + kMmaWarps * 128 + 2 * 4 * 128) * sizeof(float) + xs_bytes;
   if (smem > 200 * 1024) return -2;
   auto kern = gemv_mma_kernel<KIND, SWIGLU>;
   static bool attr_done = false;
@@ -355,7 +365,13 @@ static int launch_gemv_mma(GemvMmaParams p, cudaStream_t stream) {
   while (S < 4 && tiles * S < 3 * kNumSMs && ksteps / (kMmaWarps * S * 2) >= 1) S *= 2;
   p.S = S;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(tiles * S);
+  // persistent: at most three resident CTAs per SM (register budget), whole clusters
+  int clusters = tiles;
+  int per_sm = (int) ((220 * 1024) / (smem + 1024));
+  per_sm = per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm);
+  const int max_clusters = (per_sm * kNumSMs) / S;
+  if (clusters > max_clusters) clusters = max_clusters;
+  cfg.gridDim = dim3(clusters * S);
   cfg.blockDim = dim3(kMmaThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;

@@ -9,8 +9,8 @@ Mirrors the reference's build-time operators — same names, argument meaning an
 
 The *processed* layout is this library's own (the reference's is an Ampere ldmatrix interleave,
 cutlass_preprocessors.cpp:537-578, meaningless on sm_100): weights are stored [N, K] with K contiguous
-so each output channel is one TMA row / one coalesced 16-byte stream; int4 is packed two per byte,
-low nibble = even k.  The byte count equals the reference's, so the plugin's declared weight shape
+so each output channel is one TMA row / one coalesced 16-byte stream; int4 is packed two per byte with
+the nibbles of every 8-element group interleaved for one-LOP3 extraction (``pack_processed_int4``).  The byte count equals the reference's, so the plugin's declared weight shape
 (fp32 [K, N/4] or [K, N/8]) is unchanged.
 """
 from __future__ import annotations
@@ -124,6 +124,29 @@ def unpack_int4_packed_tensor_to_int8(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_I4_ORDER = (0, 2, 4, 6, 1, 3, 5, 7)     # element held by nibble position p of each 32-bit word (8 consecutive k)
+
+
+def pack_processed_int4(q_nk: torch.Tensor) -> torch.Tensor:
+    """[N, K] int8 in [-8, 7] -> this library's processed int4 layout [N, K/2]: every 8 consecutive k share one
+    32-bit word whose nibble positions 0..7 hold elements (0,2,4,6,1,3,5,7), so that the masks 0x000F000F << 4i pull
+    out the element PAIRS (2i, 2i+1) as two fp16 lanes with one LOP3 each (common.cuh i4x8_to_h2x4).  Same idea as the
+    reference's register relayout for its Ampere kernels (cutlass_preprocessors.cpp:383-460)."""
+    if q_nk.dtype != torch.int8 or q_nk.shape[-1] % 8:
+        raise ValueError("expected an int8 tensor whose last dim is a multiple of 8")
+    g = q_nk.reshape(*q_nk.shape[:-1], -1, 8)[..., list(_I4_ORDER)]
+    return pack_int8_tensor_to_packed_int4(g.reshape(q_nk.shape).contiguous())
+
+
+def unpack_processed_int4(p: torch.Tensor) -> torch.Tensor:
+    """inverse of ``pack_processed_int4``."""
+    u = unpack_int4_packed_tensor_to_int8(p)
+    g = u.reshape(*u.shape[:-1], -1, 8)
+    out = torch.empty_like(g)
+    out[..., list(_I4_ORDER)] = g
+    return out.reshape(u.shape)
+
+
 def preprocess_weights_for_mixed_gemm(q_kn: torch.Tensor, quant_type) -> torch.Tensor:
     """Unprocessed quantised weights ([K, N] int8, or [K, N/2] packed int4) -> this library's processed
     layout ([N, K] int8 / [N, K/2] packed int4).  Same role and signature as
@@ -131,7 +154,7 @@ def preprocess_weights_for_mixed_gemm(q_kn: torch.Tensor, quant_type) -> torch.T
     bits = _bits_of(quant_type)
     if bits == 8:
         return q_kn.t().contiguous()
-    return pack_int8_tensor_to_packed_int4(unpack_int4_packed_tensor_to_int8(q_kn).t().contiguous())
+    return pack_processed_int4(unpack_int4_packed_tensor_to_int8(q_kn).t().contiguous())
 
 
 def _symmetric_quantize(weight: torch.Tensor, bits: int):
@@ -160,7 +183,7 @@ def _symmetric_quantize_last_axis_of_batched_matrix(weight: torch.Tensor, quant_
     q, scales = _symmetric_quantize(weight, bits)
     unprocessed = q if bits == 8 else pack_int8_tensor_to_packed_int4(q)
     q_nk = q.t().contiguous()
-    processed = q_nk if bits == 8 else pack_int8_tensor_to_packed_int4(q_nk)
+    processed = q_nk if bits == 8 else pack_processed_int4(q_nk)
     return unprocessed, processed, scales
 
 
