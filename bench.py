@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--nccl-only", action="store_true", help="tensor parallel: use the NCCL AllReduce plugin on the decode path too")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -269,6 +270,8 @@ def main():
     del w
     torch.cuda.empty_cache()
     sess = rt.GenerationSession(mc, tensors, use_cuda_graph=not args.no_graph)
+    if tp > 1 and not args.nccl_only:
+        sess.enable_peer_allreduce()
     sess.setup(B, in_len, out_len)
 
     g = torch.Generator().manual_seed(1234)

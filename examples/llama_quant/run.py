@@ -89,6 +89,8 @@ def generate(args):
         ids[i, :len(r)] = r
     lens = np.array([len(r) for r in rows], dtype=np.int32)
     session = rt.GenerationSession(mc, tensors)
+    if world > 1:
+        session.enable_peer_allreduce()
     session.setup(len(rows), max_in, args.max_output_len)
     host_ids, host_lens = torch.from_numpy(ids).pin_memory(), torch.from_numpy(lens).pin_memory()
     sampling = rt.SamplingConfig(end_id=EOS_TOKEN, pad_id=PAD_TOKEN, num_beams=1)

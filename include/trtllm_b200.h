@@ -119,6 +119,20 @@ int tb_copy(void* dst, const void* src, size_t bytes, tb_stream_t s); /* device-
 /* in [tp, rows, vocab_local] fp16 (all-gathered vocab-parallel lm_head) -> out [rows, tp*vocab_local] fp32 */
 int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int tp, tb_stream_t s);
 
+/* ---- one-shot NVLink all-reduce + residual add for decode-size messages ------------------------------------
+ * replaces AllreducePlugin::enqueue -> ncclAllReduce (P/ncclPlugin/allreducePlugin.cpp:80-97) and the residual
+ * add that follows it, for messages <= max_bytes.  Setup: every rank creates its context, the host exchanges the
+ * 64-byte IPC handles (rank order) and every rank opens its peers.  Per call: the producer writes its fp16 partial
+ * into tb_ar_buffer(set); consecutive calls must alternate set = 0, 1, 0, 1, ...; out = residual + sum_r partial_r
+ * (rank-ordered fp32 sum: bit-identical on all ranks).                                                        */
+typedef struct tb_ar tb_ar;
+int tb_ar_create(tb_ar** out, int rank, int world, size_t max_bytes);
+void tb_ar_destroy(tb_ar* a);
+int tb_ar_ipc_handle(tb_ar* a, void* out64);
+int tb_ar_open_peers(tb_ar* a, const void* handles);
+void* tb_ar_buffer(tb_ar* a, int set);
+int tb_ar_allreduce(tb_ar* a, int set, void* out, const void* residual, int64_t n_half, tb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,11 @@ void* tbrt_kv_cache(const tbrt_engine* e, int layer);
  * This is GenerationSession.decode (generation.py:782-997) for greedy sampling without early stop. */
 int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_lengths, int batch, int seq, int max_new,
                   int32_t* host_out_ids, tb_stream_t s);
+/* Tensor parallel only: peer-memory all-reduce of the decode path (tb_ar_*).  After tbrt_finalize every rank reads its
+ * 64-byte IPC handle, the host all-gathers them (rank order) and hands the table back; without this call the engine
+ * uses the NCCL AllReduce plugin for every message size. */
+int tbrt_ar_handle(tbrt_engine* e, void* out64);
+int tbrt_ar_open(tbrt_engine* e, const void* handles);
 /* kernels launched by the last tbrt_context / tbrt_step / tbrt_generate call */
 int64_t tbrt_last_launches(const tbrt_engine* e);
 

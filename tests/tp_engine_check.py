@@ -45,6 +45,8 @@ def main():
     tw = {k: torch.from_numpy(w[k]).cuda() for k in ("vocab_embedding", "ln_f", "lm_head")}
     tw["layers"] = [{k: torch.from_numpy(v).cuda() for k, v in lw.items()} for lw in w["layers"]]
     sess = rt.GenerationSession(mc, rt.build_engine_tensors(rt.shard_weights(tw, world, rank, cfg.heads), mc))
+    if os.environ.get("TB_TP_NCCL_ONLY") != "1":
+        sess.enable_peer_allreduce()      # fused NVLink all-reduce + residual on the decode path
     sess.setup(B, S, new)
     logits = [sess.context(torch.from_numpy(ids), torch.from_numpy(lens)).cpu().numpy()]
     for _ in range(new - 1):

@@ -119,6 +119,14 @@ SIGNATURES.update({
     "tbrt_kv_cache": (vp, [vp, i32]),
     "tbrt_generate": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
     "tbrt_last_launches": (i64, [vp]),
+    "tbrt_ar_handle": (i32, [vp, vp]),
+    "tbrt_ar_open": (i32, [vp, vp]),
+    "tb_ar_create": (i32, [_P(vp), i32, i32, sz]),
+    "tb_ar_destroy": (None, [vp]),
+    "tb_ar_ipc_handle": (i32, [vp, vp]),
+    "tb_ar_open_peers": (i32, [vp, vp]),
+    "tb_ar_buffer": (vp, [vp, i32]),
+    "tb_ar_allreduce": (i32, [vp, i32, vp, vp, i64, vp]),
 })
 
 _lib = None

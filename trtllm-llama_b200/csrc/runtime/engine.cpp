@@ -127,6 +127,9 @@ struct tbrt_engine {
   std::map<int, int64_t> graph_nodes;
   std::map<int, int> eager_steps;
   cudaStream_t cap_stream = nullptr;
+  tb_ar* ar = nullptr;          // peer-memory all-reduce of the decode path (tensor parallel)
+  bool ar_open = false;
+  int ar_site = 0;              // call-site parity, reset per step (two calls per layer: even per step)
 
   template <class T> int alloc(T*& p, size_t bytes) {
     void* q = nullptr;
@@ -139,6 +142,7 @@ struct tbrt_engine {
   ~tbrt_engine() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (ar) tb_ar_destroy(ar);
     for (void* p : allocs) cudaFree(p);
   }
 
@@ -397,6 +401,12 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     if (!tp) {
       RT_CALL(linear(row_lin, l.dense, dense_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, fused && sq));   // nxt = cur + dense(att)
       if (!fused) RT_CALL(norm(nxt, l.ln_post, nullptr, nullptr));
+    } else if (fused && ar_open) {
+      // row-parallel partial straight into the peer-mapped buffer, then one kernel: all-reduce + residual add
+      const int set = ar_site++ & 1;
+      RT_CALL(linear(lin.get(), l.dense, dense_in, xs, tb_ar_buffer(ar, set), nullptr, M, DataType::kHALF, s));
+      launches += 1;
+      RT_CALL(tb_ar_allreduce(ar, set, nxt, cur, (int64_t) M * hid, s));
     } else {
       RT_CALL(linear(lin.get(), l.dense, dense_in, xs, o, nullptr, M, DataType::kHALF, s));
       PluginTensorDesc d1[1] = {desc({M, hid}, DataType::kHALF)};
@@ -428,6 +438,12 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       RT_CALL(linear(row_lin, l.proj, proj_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, fused && sq));
       std::swap(cur, nxt);
       if (next_gamma && !fused) RT_CALL(norm(cur, next_gamma, nullptr, nullptr));
+    } else if (fused && ar_open) {
+      const int set = ar_site++ & 1;
+      RT_CALL(linear(lin.get(), l.proj, proj_in, xs, tb_ar_buffer(ar, set), nullptr, M, DataType::kHALF, s));
+      launches += 1;
+      RT_CALL(tb_ar_allreduce(ar, set, nxt, cur, (int64_t) M * hid, s));
+      std::swap(cur, nxt);
     } else {
       RT_CALL(linear(lin.get(), l.proj, proj_in, xs, o, nullptr, M, DataType::kHALF, s));
       PluginTensorDesc d1[1] = {desc({M, hid}, DataType::kHALF)};
@@ -480,6 +496,7 @@ int tbrt_engine::head(int rows, const __half* src, cudaStream_t s) {
 }
 
 int tbrt_engine::step_body(cudaStream_t s) {
+  ar_site = 0;
   launches += 1;
   RT_CALL(tb_embedding(h, emb, d_ids, B, c.hidden, c.vocab, s));
   if (layers_forward(B, 1, false, s)) return -1;
@@ -558,6 +575,7 @@ int tbrt_finalize(tbrt_engine* e) {
       e->alloc(e->d_prompt, Mmax * 4) || e->alloc(e->d_dummy_scale, 4))
     return -1;
   RT_CUDA(cudaMemset(e->d_dummy_scale, 0, 4));
+  if (c.tp_size > 1 && c.tp_size <= 8) RT_CALL(tb_ar_create(&e->ar, c.tp_rank, c.tp_size, (size_t) 8 * c.hidden * 2));
   RT_CUDA(cudaDeviceSynchronize());
   e->finalized = true;
   return 0;
@@ -568,12 +586,23 @@ const float* tbrt_logits(const tbrt_engine* e) { return e->logits; }
 const int32_t* tbrt_output_ids(const tbrt_engine* e) { return e->d_out_ids; }
 void* tbrt_kv_cache(const tbrt_engine* e, int layer) { return (layer >= 0 && layer < (int) e->kv.size()) ? e->kv[layer] : nullptr; }
 int64_t tbrt_last_launches(const tbrt_engine* e) { return e->launches; }
+int tbrt_ar_handle(tbrt_engine* e, void* out64) {
+  if (!e->ar) return fail("no peer all-reduce context (tp_size == 1 or engine not finalized)");
+  RT_CALL(tb_ar_ipc_handle(e->ar, out64));
+  return 0;
+}
+int tbrt_ar_open(tbrt_engine* e, const void* handles) {
+  if (!e->ar) return fail("no peer all-reduce context (tp_size == 1 or engine not finalized)");
+  RT_CALL(tb_ar_open_peers(e->ar, handles));
+  e->ar_open = true;
+  return 0;
+}
 
 int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_lengths, int batch, int seq, tb_stream_t st) {
   if (!e->finalized) return fail("engine not finalized");
   if (batch < 1 || batch > e->c.max_batch || seq < 1 || seq > e->c.max_input_len) return fail("batch / seq outside the engine limits");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
-  e->B = batch; e->S_in = seq; e->steps_done = 0; e->launches = 0;
+  e->B = batch; e->S_in = seq; e->steps_done = 0; e->launches = 0; e->ar_site = 0;
   const int M = batch * seq;
   // step state: the first generated token lands in column 0; every sequence of the padded batch sits at
   // position seq afterwards (sequence_length = max_input_len + step, generation.py:686-687)

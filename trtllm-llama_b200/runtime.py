@@ -170,6 +170,21 @@ class GenerationSession:
     def last_launches(self):
         return lib.tbrt_last_launches(self._e)
 
+    def enable_peer_allreduce(self, group=None):
+        """Tensor parallel: exchange the IPC handles of the peer-memory all-reduce buffers through torch.distributed
+        (one process per GPU) so the decode path uses the fused NVLink all-reduce + residual kernel instead of NCCL."""
+        import torch.distributed as dist
+        mine = torch.zeros(64, dtype=torch.uint8)
+        if lib.tbrt_ar_handle(self._e, mine.data_ptr()):
+            raise _err("tbrt_ar_handle")
+        world = self.cfg.tp_size
+        table = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(table, mine.cuda(), group=group)
+        flat = torch.cat([t.cpu() for t in table]).contiguous()
+        if lib.tbrt_ar_open(self._e, flat.data_ptr()):
+            raise _err("tbrt_ar_open")
+        dist.barrier(group=group)
+
     def setup(self, batch_size, max_input_length, max_new_tokens, beam_width=1):
         """generation.py:413-488: fixes the shapes of the next decode (buffers were sized at engine build)."""
         if beam_width != 1:
