@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kMmhaThreads) mmha_decode_kernel(MmhaParams p)
   const int* mrow = p.masked_tokens ? p.masked_tokens + (size_t) b * p.S_max : nullptr;
 
   float lmax = -3.0e38f;
-  constexpr int UN = 4;
+  constexpr int UN = INT8 ? 4 : 8;   // 16-byte loads in flight per thread (the int8 variant is register-bound at 64)
   for (int i = grp; i - grp < len; i += KPI * UN) {   // trip count uniform across the warp (shuffles)
     uint4 raw[UN];
 #pragma unroll
