@@ -109,32 +109,52 @@ def make_weights(torch, cfg, rank, tp, seed=0):
     return w
 
 
-def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which):
-    """Time the dominant kernel class alone: one weight-streaming GEMV launch per projection of every layer
-    (M = 1), CUDA events on the launching stream, every launch reads weights no other launch touched."""
+def ncu_traffic_per_launch():
+    """dram__bytes_read + dram__bytes_write per GEMV launch from the committed `ncu --set full` capture
+    (profiles/r01_gemv_full.txt): one launch of each of the four projection shapes of a layer, averaged."""
+    import re
+    try:
+        txt = open(os.path.join(ROOT, "profiles", "r01_gemv_full.txt")).read()
+    except OSError:
+        return None
+    per_grid = {}
+    for blk in txt.split("----")[1:]:
+        rd = re.search(r"dram__bytes_read.sum = ([0-9.]+) (\w+)", blk)
+        wr = re.search(r"dram__bytes_write.sum = ([0-9.]+) (\w+)", blk)
+        if not rd or not wr:
+            continue
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = float(rd.group(1)) * unit.get(rd.group(2), 1.0) + float(wr.group(1)) * unit.get(wr.group(2), 1.0)
+        per_grid[round(float(rd.group(1)))] = tot          # de-duplicate repeated shapes by their read size
+    if len(per_grid) < 4:
+        return None
+    return int(sum(per_grid.values()) / len(per_grid))
+
+
+def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which, rows=1):
+    """Time the dominant kernel class alone: one weight-streaming decode projection launch per projection of every
+    layer (`rows` token rows), replayed as ONE CUDA graph (no host launch gaps), CUDA events on the launching stream;
+    every launch reads weights no other launch touched (13 GB of distinct weights for fp16: far beyond L2)."""
     from trtllm_llama_b200 import ops
     kind = {"fp16": ops.KIND_F16, "w8": ops.KIND_W8, "w4": ops.KIND_W4, "sq": ops.KIND_A8W8}[mode]
     bpw = {"fp16": 2.0, "w8": 1.0, "w4": 0.5, "sq": 1.0}[mode]
     hid = cfg["hidden"]
-    x16 = (torch.randn(1, max(hid, cfg["inter"]), device="cuda") * 0.1).half()
-    x8 = torch.randint(-127, 127, (1, max(hid, cfg["inter"])), device="cuda", dtype=torch.int8)
-    st = torch.ones(1, 1, device="cuda", dtype=torch.float32)
+    x16 = (torch.randn(rows, max(hid, cfg["inter"]), device="cuda") * 0.1).half()
+    x8 = torch.randint(-127, 127, (rows, max(hid, cfg["inter"])), device="cuda", dtype=torch.int8)
+    st = torch.ones(rows, 1, device="cuda", dtype=torch.float32)
     calls, bytes_total = [], 0
     for i in range(cfg["layers"]):
         for name in ("attention.qkv", "attention.dense", "mlp.fc_gate", "mlp.proj"):
             wt = sess_tensors[f"layers.{i}.{name}.weight"]
             sc = sess_tensors.get(f"layers.{i}.{name}.per_channel_scale")
             N = wt.shape[0]
-            K = wt.numel() * wt.element_size() / bpw / N
-            K = int(round(K))
+            K = int(round(wt.numel() * wt.element_size() / bpw / N))
             calls.append((wt, sc, N, K, name == "mlp.fc_gate"))
             bytes_total += int(N * K * bpw)
-
-    # pre-slice activations once so the timed loop holds only GEMV launches
     xs16 = {K: x16[:, :K].contiguous() for K in {c[3] for c in calls}}
     xs8 = {K: x8[:, :K].contiguous() for K in {c[3] for c in calls}}
 
-    def run_fast():
+    def run_all():
         for wt, sc, N, K, swiglu in calls:
             if mode == "sq":
                 ops.gemv(kind, xs8[K], wt, sc=sc.view(1, -1), sr=st, swiglu=swiglu)
@@ -143,23 +163,35 @@ def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which):
             else:
                 ops.gemv(kind, xs16[K], wt, w_scale=sc, swiglu=swiglu)
     for _ in range(3):
-        run_fast()
+        run_all()
+    torch.cuda.synchronize()
+    graphed = True
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            run_all()
+        replay = g.replay
+    except Exception:          # noqa: BLE001  (fall back to eager launches; noted in the JSON)
+        graphed, replay = False, run_all
+    replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
     e0.record()
     for _ in range(reps):
-        run_fast()
+        replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     n_launch = len(calls)
     achieved = bytes_total / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "gemv_kernel (weight-streaming projections, M=1)", "achieved": round(achieved, 1),
-            "peak": hbm_peak, "peak_source": which, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
-            "bytes_per_launch": bytes_total // n_launch, "us_per_launch": round(ms * 1e3 / n_launch, 2),
-            "launches_timed": n_launch * reps, "traffic": None,
-            "note": "includes host launch gaps between back-to-back eager launches; see profiles/ for ncu per-kernel figures"}
+    return {"bound": "hbm", "kernel": f"decode projection GEMV ({'gemv_mma_kernel' if rows > 4 or mode == 'w4' else 'gemv_kernel'}, "
+                                      f"{rows} token row{'s' if rows > 1 else ''})",
+            "achieved": round(achieved, 1), "peak": hbm_peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+            "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "bytes_per_launch": bytes_total // n_launch,
+            "us_per_launch": round(ms * 1e3 / n_launch, 2), "launches_timed": n_launch * reps,
+            "traffic": ncu_traffic_per_launch() if (mode == "fp16" and rows == 1) else None,
+            "timing": "one CUDA graph of the %d launches, replayed %d times" % (n_launch, reps) if graphed else "eager launches"}
 
 
 def run_reference(args):
@@ -345,7 +377,7 @@ def main():
     bpw = {"fp16": 2.0, "w8": 1.0, "w4": 0.5, "sq": 1.0}[mode]
     L_mid = in_len + out_len // 2
     step_bytes = (6476005376 * bpw + 262144000) / tp + 2 * 32 * B * L_mid * 4096 * (1 if int8_kv else 2) / tp
-    roof = gemv_roofline(torch, tensors, LLAMA7B, mode, hbm, which) if rank == 0 else None
+    roof = gemv_roofline(torch, tensors, LLAMA7B, mode, hbm, which, rows=min(B, 8)) if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.barrier()
