@@ -402,7 +402,7 @@ static int launch_gemm_tc(GemmTcParams p, const void* x, const void* w, void* wo
   const int base_items = p.n_tiles * p.m_tiles;
   if (force_splits > 0) {
     splits = force_splits;
-  } else if (base_items < kNumSMs && NT <= 32) {
+  } else if (base_items < kNumSMs && NT <= 16) {
     // split-K only for decode-like shapes: the in-order partial-sum reduction is serial in the token dimension
     splits = (2 * kNumSMs + base_items - 1) / base_items;
     const int max_by_k = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
@@ -462,7 +462,7 @@ size_t tb_gemm_tc_workspace_bytes(int M, int N, int K) {
   const int nt = select_nt(M, N);
   const int m_tiles = (M + nt - 1) / nt;
   const size_t base = (size_t) n_tiles * m_tiles;
-  size_t splits = (base < (size_t) kNumSMs && nt <= 32) ? (2 * kNumSMs + base - 1) / base : 1;
+  size_t splits = (base < (size_t) kNumSMs && nt <= 16) ? (2 * kNumSMs + base - 1) / base : 1;
   return base * splits * nt * kTileN * sizeof(float) + 256;
 }
 size_t tb_gemm_tc_counter_bytes(void) { return (size_t) kGemmMaxCounters * sizeof(int); }
