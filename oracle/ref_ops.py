@@ -15,7 +15,7 @@ file:line it follows.  Path aliases (same as SURVEY.md):
 Parity pinning (see DESIGN.md "Oracle"):
   * symmetric_quantize / int4 packing: pinned bit-exactly against the reference's
     own ``cutlass_preprocessors.cpp`` compiled by ``oracle/Makefile`` into
-    ``oracle/_ref/libref_host.so`` (tests/test_oracle_ref_host.py).
+    ``oracle/_ref/libref_host.so`` (tests/test_cpu_oracle_and_abi.py, live and through tests/golden/).
   * sq_gemm / quantize_per_token / rmsnorm-quant / weight-only / attention:
     pinned against the reference tests' procedural fixtures restated in
     ``tests/golden/make_golden.py`` (input distributions, seeds, tolerances of

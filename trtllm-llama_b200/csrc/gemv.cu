@@ -4,24 +4,25 @@
 // sm_100a design (measured with tools/membench.cu on this pool's B200s: a ring of cp.async.bulk copies tops out
 // at ~6.1 TB/s with a ~4 us ramp because every stage is a dependent round trip, while plain 16-byte LDG streams
 // with >= 128 KB in flight per SM reach 7.3 TB/s with no ramp): one warp per output row, rows dealt round-robin
-// so that at any instant the whole chip reads one contiguous window of the weight matrix; each lane keeps TWO
-// batches of 16-byte loads in flight (software-pipelined registers), so the FMA / shuffle-reduce work of one
-// batch always overlaps the HBM latency of the next, across row boundaries; activations are staged once per
-// CTA in shared memory; fp32 accumulation (int32 dp4a for W8A8); fused epilogue (per-channel / per-token
-// scales, SwiGLU, residual add).
+// so that at any instant the whole chip reads one contiguous window of the weight matrix; each lane keeps eight
+// 16-byte loads in flight (4 KB per warp, 4 CTAs x 8 warps per SM = 128 KB per SM); activations are staged once per
+// CTA in shared memory; products are exact (fp16 x fp16 in fp32), accumulation fp32 (int32 dp4a for W8A8); fused
+// epilogue (per-channel / per-token scales, SwiGLU, residual add).  Variants that measured slower on LLaMA-7B
+// decode steps are listed in DESIGN.md section 5.
 // Fused prologues (the TensorRT-native glue / extra plugins of the reference):
 //   RMSNorm of the residual stream, RMSNorm + dynamic per-token int8 quantisation (RmsnormQuantization),
 //   plain dynamic per-token quantisation (QuantizePerToken) — each CTA recomputes the row statistics of the
 //   8-22 KB activation it stages anyway (L2-resident), removing two to four launches per layer.
-// Programmatic dependent launch: the producer starts streaming weights (which do not depend on the previous
-// kernel) before griddepcontrol.wait; only the activation staging waits for the upstream kernel.
+// Programmatic dependent launch: griddepcontrol.launch_dependents is issued at once, so the next kernel's CTAs
+// become resident as this grid drains; griddepcontrol.wait guards the first read of upstream activations.
+// 5..8 token rows, and int4 weights at any M, go to the tensor-core kernel in gemv_mma.cu (see tb_gemv_fused).
 //
 // Replaces (reference):
 //   T/cpp/tensorrt_llm/kernels/weightOnlyMatrixVectorMultiplication.cu:136-277,371-378 (int8/int4 GEMV)
 //   the M<=4 calls of CutlassInt8GemmRunner::gemm (int8_gemm_template.h:356-369) and of
 //   GemmPlugin/cuBLAS (P/gemmPlugin/gemmPlugin.cpp:121-230) made by the decode step.
 // Weight layouts (this library's processed layouts, quantization.py):
-//   fp16: [N, K] (torch Linear)      int8: [N, K]      int4: [N, K/2], low nibble = even k.
+//   fp16: [N, K] (torch Linear)      int8: [N, K]      int4: [N, K/2], nibbles interleaved per 8 k (pack_processed_int4).
 // Algorithmic bytes per launch = N*K*bytes_per_weight (+ M*(K+N)*2, < 0.1 %).
 #include <cstdlib>
 #include "common.cuh"
