@@ -99,10 +99,14 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
                    int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv, int nsplit,
                    tb_stream_t stream);
 /* context phase: replaces GPTAttentionPluginCommon::enqueueContext (gptAttentionCommon.cpp:361-620).
- * qkv [B,S,3*H*Dh] fp16 is rotated in place (q,k), out [B,S,H*Dh].                               */
+ * qkv [B,S,3*H*Dh] fp16 is rotated in place (q,k), out [B,S,H*Dh].
+ * workspace: tb_context_attention_workspace_bytes() of scratch (V^T) selects the tcgen05 kernel; NULL selects the
+ * workspace-free warp-MMA kernel.                                                                   */
+size_t tb_context_attention_workspace_bytes(int batch, int seq_len, int num_heads);
 int tb_context_attention(void* out, void* qkv, void* kv_cache, const int* input_lengths,
-                         const float* kv_scale_orig_quant, int batch, int seq_len, int num_heads, int head_size,
-                         int max_seq_len, int rotary_dim, float q_scaling, int int8_kv, tb_stream_t stream);
+                         const float* kv_scale_orig_quant, void* workspace, int batch, int seq_len, int num_heads,
+                         int head_size, int max_seq_len, int rotary_dim, float q_scaling, int int8_kv,
+                         tb_stream_t stream);
 
 /* ---- glue (TRT-native ops in the reference, k14) ---------------------------------------------- */
 int tb_embedding(void* out, const void* table, const int* ids, int tokens, int hidden, int vocab, tb_stream_t s);

@@ -300,11 +300,12 @@ def test_mmha_decode(ops, int8_kv, past, nsplit):
         np.testing.assert_allclose(new_cache.astype(np.float32), cache_ref.astype(np.float32), atol=2e-3)
 
 
+@pytest.mark.parametrize("use_tc", [True, False])
 @pytest.mark.parametrize("int8_kv", [True, False])
-@pytest.mark.parametrize("S,lens", [(64, (64, 64)), (96, (96, 50)), (200, (130, 200)), (128, (1, 128))])
-def test_context_attention(ops, int8_kv, S, lens):
+@pytest.mark.parametrize("S,lens", [(64, (64, 64)), (96, (96, 50)), (200, (130, 200)), (128, (1, 128)), (300, (300, 257))])
+def test_context_attention(ops, int8_kv, S, lens, use_tc):
     rng = np.random.default_rng(14)
-    B, H, Dh, S_max = 2, 2, 128, 256
+    B, H, Dh, S_max = 2, 2, 128, 320
     qkv = (rng.standard_normal((B, S, 3 * H * Dh)) * 0.5).astype(np.float16)
     in_lens = np.array(lens, dtype=np.int32)
     cache_ref = np.zeros((B, 2, H, S_max, Dh), dtype=np.int8 if int8_kv else np.float16)
@@ -312,7 +313,7 @@ def test_context_attention(ops, int8_kv, S, lens):
     ref = R.context_attention(qkv, cache_ref, in_lens, num_heads=H, head_size=Dh, kv_scale_orig_quant=s_q)
     d_cache = dev(np.zeros_like(cache_ref))
     kw = dict(kv_scale_orig_quant=dev(np.array([s_q], np.float32))) if int8_kv else {}
-    out = host(ops.context_attention(dev(qkv), d_cache, dev(in_lens), num_heads=H, head_size=Dh, **kw))
+    out = host(ops.context_attention(dev(qkv), d_cache, dev(in_lens), num_heads=H, head_size=Dh, use_tc=use_tc, **kw))
     for b in range(B):   # valid rows only (padded rows are unspecified in the reference)
         L = lens[b]
         np.testing.assert_allclose(out[b, :L].astype(np.float32), ref[b, :L].astype(np.float32), atol=5e-3)

@@ -269,10 +269,14 @@ __global__ void __launch_bounds__(128) flash_ctx_kernel(const __half* __restrict
 
 using namespace tb;
 
+extern "C" size_t tb_context_attention_workspace_bytes(int batch, int seq_len, int num_heads) {
+  return flash_ctx_tc_workspace_bytes(batch, seq_len, num_heads);
+}
+
 extern "C" int tb_context_attention(void* out, void* qkv, void* kv_cache, const int* input_lengths,
-                                    const float* kv_scale_orig_quant, int batch, int seq_len, int num_heads,
-                                    int head_size, int max_seq_len, int rotary_dim, float q_scaling, int int8_kv,
-                                    cudaStream_t stream) {
+                                    const float* kv_scale_orig_quant, void* workspace, int batch, int seq_len,
+                                    int num_heads, int head_size, int max_seq_len, int rotary_dim, float q_scaling,
+                                    int int8_kv, cudaStream_t stream) {
   if (head_size != kD) return -1;
   if (rotary_dim != 0 && rotary_dim != kD) return -1;
   if (seq_len > max_seq_len || batch <= 0 || seq_len <= 0) return -2;
@@ -280,6 +284,9 @@ extern "C" int tb_context_attention(void* out, void* qkv, void* kv_cache, const 
   ctx_prep_kernel<<<dim3(batch * seq_len, num_heads), 64, 0, stream>>>((__half*) qkv, kv_cache, input_lengths,
                                                                       kv_scale_orig_quant, seq_len, num_heads,
                                                                       max_seq_len, rotary_dim, int8_kv);
+  const float qk_scale_tc = 1.f / (sqrtf((float) head_size) * q_scaling);
+  if (workspace)   // tcgen05 path (context_attn_tc.cu); without a workspace the warp-MMA kernel below runs
+    return launch_flash_ctx_tc(out, qkv, workspace, input_lengths, batch, seq_len, num_heads, qk_scale_tc, stream);
   const size_t smem = (size_t) (kBM * kQPad + kBN * kQPad + kD * kVPad) * sizeof(__half);
   static bool attr_set = false;
   if (!attr_set) {

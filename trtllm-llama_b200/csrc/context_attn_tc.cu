@@ -1,0 +1,299 @@
+// Context-phase (prefill) causal attention on tcgen05 tensor cores with TMEM accumulators and TMA-fed tiles.
+//
+// Replaces the reference's unfused prefill attention (P/gptAttentionCommon/gptAttentionCommon.cpp:494-618: two cuBLAS
+// batched GEMMs around a masked-softmax kernel over a materialised B*H*S*S score tensor, ~6.4 GB of traffic per layer at
+// B = 8, S = 2048) and this repo's own round-1 warp-MMA flash kernel (context_attn.cu, 79 TFLOP/s).
+//
+// One CTA = 128 query rows of one (batch, head); it walks the key/value tiles 0..diag (causal) of 128 keys:
+//   warp 0      TMA producer: Q tile once, then K_j and V^T_j tiles into a 2-stage ring (128B-swizzled K-major boxes)
+//   warp 1      tcgen05.mma issuer (one lane): S_j = Q.K_j^T into TMEM (double-buffered), O_j = P_j.V_j into TMEM;
+//               S_{j+1} is issued before P_j is awaited, so the softmax of tile j overlaps the QK^T of tile j+1
+//   warps 2-5   softmax: TMEM lane = query row, so a thread owns a whole row — row max / sum need no shuffles.  Online
+//               softmax in fp32; P_j is written as fp16 into a 128B-swizzled shared tile (the A operand of P.V); the
+//               per-tile product O_j is read back from TMEM and folded into the thread's fp32 output row.
+// V is needed as a K-major B operand [Dh x keys]; the activations hold it as [keys x Dh], so a small transpose kernel
+// writes V^T [B, H, Dh, S] into the caller's workspace first (2 * B*S*hidden bytes, ~45 us at cfg4 sizes).
+// Numerics: s = qk * scale with causal + length masking, p = exp(s - running max) rounded to fp16 for P.V (the reference
+// rounds its normalised p to fp16 too, K/unfusedAttentionKernels.cu:180-257), normalisation 1/(sum + 1e-6) at the end.
+// Bound: fp16 tensor pipe; algorithmic flops = 4 * Dh * (causal pairs) per head.
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "tmap_host.h"
+
+namespace tb {
+
+constexpr int kAD = 128;                 // head size
+constexpr int kATile = 128;              // query rows per CTA == keys per tile
+constexpr int kASub = kATile * 128;      // bytes of one [128 rows x 64 halfs] swizzled sub-tile (16 KB)
+constexpr int kATileBytes = 2 * kASub;   // a [128 x 128] fp16 operand tile = two sub-tiles along K
+constexpr int kAThreads = 192;
+
+struct FlashTcParams {
+  __half* out;                 // [B, S, H*Dh]
+  const int* input_lengths;    // [B] or nullptr
+  int S, H;
+  float qk_scale;
+};
+
+// [S, Dh] -> [Dh, S_pad] per (b, h): classic 32x32 shared-memory transpose
+__global__ void __launch_bounds__(256) vt_transpose_kernel(const __half* __restrict__ qkv, __half* __restrict__ vt, int S,
+                                                           int S_pad, int H) {
+  __shared__ __half tile[32][34];
+  const int b = blockIdx.z, h = blockIdx.y / (kAD / 32), dblk = blockIdx.y % (kAD / 32), s0 = blockIdx.x * 32;
+  const int hidden = H * kAD;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const __half* src = qkv + (size_t) b * S * 3 * hidden + 2 * hidden + (size_t) h * kAD + dblk * 32;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int s = s0 + r;
+    tile[r][tx] = s < S ? src[(size_t) s * 3 * hidden + tx] : __float2half_rn(0.f);
+  }
+  __syncthreads();
+  __half* dst = vt + ((size_t) (b * H + h) * kAD + dblk * 32) * S_pad;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int s = s0 + tx;
+    if (s < S_pad) dst[(size_t) r * S_pad + s] = tile[tx][r];
+  }
+}
+
+__global__ void __launch_bounds__(kAThreads, 1)
+flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_vt,
+                    const FlashTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+  uint8_t* sQ = smem;                              // 32 KB
+  uint8_t* sK = sQ + kATileBytes;                  // 2 stages x 32 KB
+  uint8_t* sV = sK + 2 * kATileBytes;              // 2 stages x 32 KB   (V^T tile: [Dh rows x keys])
+  uint8_t* sP = sV + 2 * kATileBytes;              // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kATileBytes);
+  uint64_t* q_full = bars;          // [1]
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // [2]
+  uint64_t* p_full = bars + 7;      // [1]
+  uint64_t* o_full = bars + 8;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;       // heavy (late) query tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hidden = p.H * kAD;
+  const int len = p.input_lengths ? min(p.input_lengths[b], p.S) : p.S;
+  const int q0 = qt * kATile;
+
+  if (q0 >= len) {   // whole tile is padding: defined output (zeros); uniform over the CTA, before any barrier
+    __half* obase = p.out + (size_t) b * p.S * hidden + (size_t) h * kAD;
+    for (int i = threadIdx.x; i < kATile * kAD / 8; i += kAThreads) {
+      const int r = i / (kAD / 8), c8 = i % (kAD / 8);
+      if (q0 + r < p.S) *reinterpret_cast<uint4*>(obase + (size_t) (q0 + r) * hidden + c8 * 8) = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+  const int n_kv = min(qt + 1, (len + kATile - 1) / kATile);   // causal: key tiles 0..qt, clipped by the length
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_vt);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 2 * kATile;   // S[2] at columns 0 / 128, O at 256
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kATileBytes);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) tma_load_2d(sQ + kb * kASub, &tmap_qkv, q_full, h * kAD + kb * 64, b * p.S + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1, ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * kATileBytes);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(sK + st * kATileBytes + kb * kASub, &tmap_qkv, &kv_full[st], hidden + h * kAD + kb * 64,
+                      b * p.S + j * kATile);
+          tma_load_2d(sV + st * kATileBytes + kb * kASub, &tmap_vt, &kv_full[st], j * kATile + kb * 64,
+                      (b * p.H + h) * kAD);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer =============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = kIdescF16(kATile, kATile);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t ad = umma_desc_sw128(smem_u32(sQ + kb * kASub));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sK + st * kATileBytes + kb * kASub));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_S0 + (uint32_t) (st * kATile), ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        if (j + 1 < n_kv) issue_s(j + 1);           // overlaps the softmax of tile j
+        mbar_wait(p_full, j & 1);                   // P_j is in shared memory, S_j and O_{j-1} have been read
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t ad = umma_desc_sw128(smem_u32(sP + kb * kASub));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sV + st * kATileBytes + kb * kASub));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_O, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    // =========================== softmax / output (warps 2-5) ==========
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;                  // query row inside the tile == TMEM lane
+    const int qi = q0 + r;
+    const uint32_t lane_addr = (uint32_t) (quarter * 32) << 16;
+    float m_run = -3.0e38f, l_run = 0.f;
+    float o_acc[kAD];
+#pragma unroll
+    for (int c = 0; c < kAD; ++c) o_acc[c] = 0.f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_S0 + lane_addr + (uint32_t) (st * kATile);
+      const int k0 = j * kATile;
+      const int kmax = min(qi, len - 1) - k0;           // columns c <= kmax are attended (causal and length)
+      // pass 1: row maximum
+      float mx = -3.0e38f;
+#pragma unroll 1
+      for (int c16 = 0; c16 < kATile / 16; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(s_addr + c16 * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c16 * 16 + i <= kmax) mx = fmaxf(mx, __uint_as_float(v[i]) * p.qk_scale);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float m_use = m_new <= -1.0e38f ? 0.f : m_new;      // a fully masked row (padding) stays finite
+      const float corr = m_run <= -1.0e38f ? 0.f : __expf(m_run - m_use);
+      l_run *= corr;
+#pragma unroll
+      for (int c = 0; c < kAD; ++c) o_acc[c] *= corr;
+      // pass 2: p = exp(s - m), row sum, fp16 P into the swizzled A tile
+#pragma unroll 1
+      for (int c16 = 0; c16 < kATile / 16; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(s_addr + c16 * 16, v);
+        tmem_ld_wait();
+        uint32_t packed[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const int c = c16 * 16 + i;
+          const float p0 = c <= kmax ? __expf(__uint_as_float(v[i]) * p.qk_scale - m_use) : 0.f;
+          const float p1 = c + 1 <= kmax ? __expf(__uint_as_float(v[i + 1]) * p.qk_scale - m_use) : 0.f;
+          l_run += p0 + p1;
+          const __half2 h2 = __floats2half2_rn(p0, p1);
+          packed[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        // keys c16*16 .. +15 = two 16-byte chunks of sub-tile (c16 / 4), chunk index (c16 % 4) * 2 (+1), XOR (row & 7)
+        uint8_t* rowp = sP + (c16 >> 2) * kASub + r * 128;
+        const int ch = (c16 & 3) * 2;
+        *reinterpret_cast<uint4*>(rowp + (((ch) ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+      m_run = m_new;
+      fence_proxy_async();      // generic-proxy writes of P -> visible to the tensor core
+      tc_fence_before();        // TMEM reads of S_j (and of O_{j-1}) are complete
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // O_j = P_j . V_j : fold into the fp32 output row
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c16 = 0; c16 < kAD / 16; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_O + lane_addr + c16 * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_acc[c16 * 16 + i] += __uint_as_float(v[i]);
+      }
+    }
+    tc_fence_before();
+    if (qi < p.S) {
+      const float inv = __fdividef(1.f, l_run + 1.e-6f);
+      __half* orow = p.out + ((size_t) b * p.S + qi) * hidden + (size_t) h * kAD;
+#pragma unroll
+      for (int c8 = 0; c8 < kAD / 8; ++c8) {
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(o_acc[c8 * 8 + 2 * i] * inv, o_acc[c8 * 8 + 2 * i + 1] * inv);
+        *reinterpret_cast<uint4*>(orow + c8 * 8) = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// launched after ctx_prep_kernel (RoPE in place, KV-cache write): transpose V, then the fused attention
+int launch_flash_ctx_tc(void* out, const void* qkv, void* workspace, const int* input_lengths, int batch, int seq_len,
+                        int num_heads, float qk_scale, cudaStream_t stream) {
+  const int hidden = num_heads * kAD;
+  const int S_pad = (seq_len + 7) & ~7;
+  __half* vt = static_cast<__half*>(workspace);
+  vt_transpose_kernel<<<dim3((S_pad + 31) / 32, num_heads * (kAD / 32), batch), 256, 0, stream>>>(
+      static_cast<const __half*>(qkv), vt, seq_len, S_pad, num_heads);
+  CUtensorMap tq, tv;
+  int rc = make_tmap(&tq, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t) batch * seq_len, (uint64_t) 3 * hidden, kATile, 64,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tmap(&tv, vt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t) batch * num_heads * kAD, (uint64_t) S_pad, kATile, 64,
+                 CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const size_t smem = 6 * (size_t) kATileBytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TB_CHECK_CUDA(cudaFuncSetAttribute(flash_ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    attr_set = true;
+  }
+  FlashTcParams p{static_cast<__half*>(out), input_lengths, seq_len, num_heads, qk_scale};
+  dim3 grid((seq_len + kATile - 1) / kATile, num_heads, batch);
+  flash_ctx_tc_kernel<<<grid, kAThreads, smem, stream>>>(tq, tv, p);
+  return (int) cudaGetLastError();
+}
+
+size_t flash_ctx_tc_workspace_bytes(int batch, int seq_len, int num_heads) {
+  const size_t S_pad = (size_t) ((seq_len + 7) & ~7);
+  return (size_t) batch * num_heads * kAD * S_pad * sizeof(__half) + 256;
+}
+
+}  // namespace tb

@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "tmap_host.h"
 
 namespace tb {
 
@@ -338,36 +339,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
-  return fn;
-}
-
-// 2-D row-major byte/half matrix [rows, cols] -> tensor map with box [box_rows, box_cols]
-static int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt_bytes, uint64_t rows,
-                     uint64_t cols, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) return -10;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * (uint64_t) elt_bytes};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : -11;
-}
-
 template <int KIND, int NT>
 static int launch_gemm_tc(GemmTcParams p, const void* x, const void* w, void* workspace, size_t workspace_bytes,
                           int* counters, int force_splits, cudaStream_t stream) {

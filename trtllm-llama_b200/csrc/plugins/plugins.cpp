@@ -108,9 +108,11 @@ class GPTAttentionPlugin : public BasePlugin {
     return linear(io[pos], (DataType) type_);
   }
   size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
-    // generation: split-L partials.  context: the fused causal kernel needs no scratch (the reference
-    // sizes ~6.4 GB of score buffers here, gptAttentionCommon.cpp:267-305).
-    return align128(tb_mmha_workspace_bytes(in[0].dims.d[0], num_heads_, kMaxSplits));
+    // generation: split-L partials.  context: V^T for the tcgen05 kernel, 2 * B*S*hidden bytes (the reference sizes
+    // ~6.4 GB of score buffers here, gptAttentionCommon.cpp:267-305).
+    const size_t gen = tb_mmha_workspace_bytes(in[0].dims.d[0], num_heads_, kMaxSplits);
+    const size_t ctx = tb_context_attention_workspace_bytes(in[0].dims.d[0], in[0].dims.d[1], num_heads_);
+    return align128(gen > ctx ? gen : ctx);
   }
   int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out,
                   void* workspace, cudaStream_t stream) noexcept override {
@@ -126,8 +128,8 @@ class GPTAttentionPlugin : public BasePlugin {
       const float* s_qo = int8_kv_ ? static_cast<const float*>(in[9]) : nullptr;
       void* cache = out[1] ? out[1] : const_cast<void*>(in[1]);      // in-place: runtime binds one buffer to both
       if (is_context) {
-        return tb_context_attention(out[0], const_cast<void*>(in[0]), cache, static_cast<const int*>(in[5]), s_oq, B, S,
-                                    num_heads_, head_size_, S_max, rotary_dim_, q_scaling_, int8_kv_, stream);
+        return tb_context_attention(out[0], const_cast<void*>(in[0]), cache, static_cast<const int*>(in[5]), s_oq, workspace,
+                                    B, S, num_heads_, head_size_, S_max, rotary_dim_, q_scaling_, int8_kv_, stream);
       }
       TBP_REQUIRE(S == 1, "generation phase expects one token per sequence");
       // device_lengths [ext]: the step position is read from sequence_length on the device so one

@@ -555,6 +555,10 @@ int tbrt_finalize(tbrt_engine* e) {
   }
   // workspace: the maximum any plugin asks for over the shapes this engine runs (TensorRT does the same)
   size_t ws = tb_mmha_workspace_bytes(c.max_batch, e->Hl, 32);
+  {
+    const size_t w = tb_context_attention_workspace_bytes(c.max_batch, c.max_input_len, e->Hl);
+    if (w > ws) ws = w;
+  }
   const int Ns[4] = {3 * e->hid_l, c.hidden, 2 * e->inter_l, e->vocab_l};
   const int Ks[4] = {c.hidden, e->inter_l, c.hidden, c.hidden};
   const int Ms[2] = {c.max_batch, (int) Mmax};

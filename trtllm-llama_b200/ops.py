@@ -196,14 +196,15 @@ def mmha_decode(qkv, kv_cache, past_len, *, num_heads, head_size, max_input_len,
 
 
 def context_attention(qkv, kv_cache, input_lengths, *, num_heads, head_size, kv_scale_orig_quant=None, q_scaling=1.0,
-                      rotary_dim=None):
+                      rotary_dim=None, use_tc=True):
     """GPTAttention plugin, context phase (past_key_value_length = [0, 1]).  qkv [B,S,3*H*Dh] is
     rotated in place; kv_cache written for positions [0, S)."""
     _chk_cuda(qkv, kv_cache, input_lengths, kv_scale_orig_quant)
     B, S = qkv.shape[0], qkv.shape[1]
     rot = head_size if rotary_dim is None else rotary_dim
     out = torch.empty((B, S, num_heads * head_size), dtype=torch.float16, device=qkv.device)
-    check(lib.tb_context_attention(_p(out), _p(qkv), _p(kv_cache), _p(input_lengths), _p(kv_scale_orig_quant), B, S,
+    ws = _workspace(lib.tb_context_attention_workspace_bytes(B, S, num_heads), qkv.device) if use_tc else None
+    check(lib.tb_context_attention(_p(out), _p(qkv), _p(kv_cache), _p(input_lengths), _p(kv_scale_orig_quant), _p(ws), B, S,
                                    num_heads, head_size, kv_cache.shape[3], rot, float(q_scaling),
                                    int(kv_cache.dtype == torch.int8), _stream()), "tb_context_attention")
     return out
