@@ -26,56 +26,81 @@ namespace tb {
 constexpr int kD = 128;
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) ctx_prep_kernel(__half* qkv, void* kv_cache, const int* input_lengths,
-                                                      const float* kv_scale_orig_quant, int S, int H, int S_max,
-                                                      int rotary_dim, int int8_kv) {
-  const int tok = blockIdx.x, h = blockIdx.y;
+// One CTA per token: the rotary angles depend on (position, pair) only, so cos / sin are computed once (64 threads) and
+// reused by all heads; then 256 threads sweep the (head, pair) items of the row.
+constexpr int kPrepThreads = 256;
+__global__ void __launch_bounds__(kPrepThreads) ctx_prep_kernel(__half* qkv, void* kv_cache, const int* input_lengths,
+                                                                const float* kv_scale_orig_quant, int S, int H, int S_max,
+                                                                int rotary_dim, int int8_kv) {
+  __shared__ float cs[kD / 2], sn_s[kD / 2];
+  const int tok = blockIdx.x;
   const int b = tok / S, s = tok % S;
   const int hidden = H * kD;
   const int len = input_lengths ? input_lengths[b] : S;
   const bool valid = s < len;
-  __half* row = qkv + (size_t) tok * 3 * hidden + (size_t) h * kD;
-  const int t = threadIdx.x;  // pair (t, t + 64)
   const int half_rot = rotary_dim / 2;
-  float c = 1.f, sn = 0.f;
-  int i0, i1;
-  if (t < half_rot) {
-    const float ang = (float) s / powf(10000.0f, (2 * t) / (float) rotary_dim);
-    c = cosf(ang);
-    sn = sinf(ang);
-    i0 = t;
-    i1 = t + half_rot;
-  } else {
-    i0 = 2 * t - half_rot;
-    i1 = i0 + 1;
+  if (threadIdx.x < kD / 2) {
+    float c = 1.f, sn = 0.f;
+    if ((int) threadIdx.x < half_rot) {
+      const float ang = (float) s / powf(10000.0f, (2 * threadIdx.x) / (float) rotary_dim);
+      c = cosf(ang);
+      sn = sinf(ang);
+    }
+    cs[threadIdx.x] = c;
+    sn_s[threadIdx.x] = sn;
   }
-  __half k0 = __float2half_rn(0.f), k1 = k0, v0 = k0, v1 = k0;
-  if (valid) {
-    const float qa = __half2float(row[i0]), qb = __half2float(row[i1]);
-    row[i0] = __float2half_rn(c * qa - sn * qb);
-    row[i1] = __float2half_rn(c * qb + sn * qa);
-    const float ka = __half2float(row[hidden + i0]), kb = __half2float(row[hidden + i1]);
-    k0 = __float2half_rn(c * ka - sn * kb);
-    k1 = __float2half_rn(c * kb + sn * ka);
-    row[hidden + i0] = k0;
-    row[hidden + i1] = k1;
-    v0 = row[2 * hidden + i0];
-    v1 = row[2 * hidden + i1];
-  }
+  __syncthreads();
   const size_t elt = int8_kv ? 1 : 2;
-  uint8_t* kc = reinterpret_cast<uint8_t*>(kv_cache) + ((size_t) b * 2 * H + h) * S_max * kD * elt + (size_t) s * kD * elt;
-  uint8_t* vc = kc + (size_t) H * S_max * kD * elt;
-  if (int8_kv) {
-    const float qs = kv_scale_orig_quant[0];
-    kc[i0] = (uint8_t) f2i8(__half2float(k0) * qs);
-    kc[i1] = (uint8_t) f2i8(__half2float(k1) * qs);
-    vc[i0] = (uint8_t) f2i8(__half2float(v0) * qs);
-    vc[i1] = (uint8_t) f2i8(__half2float(v1) * qs);
-  } else {
-    reinterpret_cast<__half*>(kc)[i0] = k0;
-    reinterpret_cast<__half*>(kc)[i1] = k1;
-    reinterpret_cast<__half*>(vc)[i0] = v0;
-    reinterpret_cast<__half*>(vc)[i1] = v1;
+  const float qs = int8_kv ? kv_scale_orig_quant[0] : 1.f;
+  // item = (head, group of 8 pairs): pairs (t, t + 64) for t = 8g .. 8g+7 are two 16-byte chunks of the head row.
+  // rotary_dim is 0 (cos = 1, sin = 0: identity, any pairing) or 128 (neox halves), checked by the host.
+  for (int item = threadIdx.x; item < H * 8; item += kPrepThreads) {
+    const int h = item >> 3, g8 = item & 7;
+    __half* row = qkv + (size_t) tok * 3 * hidden + (size_t) h * kD;
+    uint4 klo = make_uint4(0, 0, 0, 0), khi = klo, vlo = klo, vhi = klo;
+    if (valid) {
+      auto rotate = [&](__half* base, uint4& lo_out, uint4& hi_out) {
+        uint4 lo = *reinterpret_cast<const uint4*>(base + g8 * 8), hi = *reinterpret_cast<const uint4*>(base + 64 + g8 * 8);
+        __half* a = reinterpret_cast<__half*>(&lo);
+        __half* bq = reinterpret_cast<__half*>(&hi);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float c = cs[g8 * 8 + i], sn = sn_s[g8 * 8 + i];
+          const float xa = __half2float(a[i]), xb = __half2float(bq[i]);
+          a[i] = __float2half_rn(c * xa - sn * xb);
+          bq[i] = __float2half_rn(c * xb + sn * xa);
+        }
+        *reinterpret_cast<uint4*>(base + g8 * 8) = lo;
+        *reinterpret_cast<uint4*>(base + 64 + g8 * 8) = hi;
+        lo_out = lo;
+        hi_out = hi;
+      };
+      uint4 qlo, qhi;
+      rotate(row, qlo, qhi);
+      rotate(row + hidden, klo, khi);
+      vlo = *reinterpret_cast<const uint4*>(row + 2 * hidden + g8 * 8);
+      vhi = *reinterpret_cast<const uint4*>(row + 2 * hidden + 64 + g8 * 8);
+    }
+    uint8_t* kc = reinterpret_cast<uint8_t*>(kv_cache) + ((size_t) b * 2 * H + h) * S_max * kD * elt + (size_t) s * kD * elt;
+    uint8_t* vc = kc + (size_t) H * S_max * kD * elt;
+    if (int8_kv) {
+      auto q8 = [&](const uint4& x) {
+        const __half* hx = reinterpret_cast<const __half*>(&x);
+        uint2 o;
+        o.x = pack4_i8(__half2float(hx[0]) * qs, __half2float(hx[1]) * qs, __half2float(hx[2]) * qs, __half2float(hx[3]) * qs);
+        o.y = pack4_i8(__half2float(hx[4]) * qs, __half2float(hx[5]) * qs, __half2float(hx[6]) * qs, __half2float(hx[7]) * qs);
+        return o;
+      };
+      *reinterpret_cast<uint2*>(kc + g8 * 8) = q8(klo);
+      *reinterpret_cast<uint2*>(kc + 64 + g8 * 8) = q8(khi);
+      *reinterpret_cast<uint2*>(vc + g8 * 8) = q8(vlo);
+      *reinterpret_cast<uint2*>(vc + 64 + g8 * 8) = q8(vhi);
+    } else {
+      *reinterpret_cast<uint4*>(kc + (g8 * 8) * 2) = klo;
+      *reinterpret_cast<uint4*>(kc + (64 + g8 * 8) * 2) = khi;
+      *reinterpret_cast<uint4*>(vc + (g8 * 8) * 2) = vlo;
+      *reinterpret_cast<uint4*>(vc + (64 + g8 * 8) * 2) = vhi;
+    }
   }
 }
 
@@ -281,7 +306,7 @@ extern "C" int tb_context_attention(void* out, void* qkv, void* kv_cache, const 
   if (rotary_dim != 0 && rotary_dim != kD) return -1;
   if (seq_len > max_seq_len || batch <= 0 || seq_len <= 0) return -2;
   if (int8_kv && !kv_scale_orig_quant) return -1;
-  ctx_prep_kernel<<<dim3(batch * seq_len, num_heads), 64, 0, stream>>>((__half*) qkv, kv_cache, input_lengths,
+  ctx_prep_kernel<<<dim3(batch * seq_len), kPrepThreads, 0, stream>>>((__half*) qkv, kv_cache, input_lengths,
                                                                       kv_scale_orig_quant, seq_len, num_heads,
                                                                       max_seq_len, rotary_dim, int8_kv);
   const float qk_scale_tc = 1.f / (sqrtf((float) head_size) * q_scaling);

@@ -176,7 +176,8 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const int r = quarter * 32 + lane;                  // query row inside the tile == TMEM lane
     const int qi = q0 + r;
     const uint32_t lane_addr = (uint32_t) (quarter * 32) << 16;
-    float m_run = -3.0e38f, l_run = 0.f;
+    const float scale_log2 = p.qk_scale * 1.4426950408889634f;
+    float m_run = -3.0e38f, l_run = 0.f;     // running max in the log2 domain
     float o_acc[kAD];
 #pragma unroll
     for (int c = 0; c < kAD; ++c) o_acc[c] = 0.f;
@@ -188,24 +189,31 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       const uint32_t s_addr = tmem_S0 + lane_addr + (uint32_t) (st * kATile);
       const int k0 = j * kATile;
       const int kmax = min(qi, len - 1) - k0;           // columns c <= kmax are attended (causal and length)
-      // pass 1: row maximum
+      // pass 1: row maximum of the raw scores (scale > 0 commutes with max); unmasked fast path off the diagonal
+      const bool full = kmax >= kATile - 1;
       float mx = -3.0e38f;
 #pragma unroll 1
       for (int c16 = 0; c16 < kATile / 16; ++c16) {
         uint32_t v[16];
         tmem_ld16(s_addr + c16 * 16, v);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c16 * 16 + i <= kmax) mx = fmaxf(mx, __uint_as_float(v[i]) * p.qk_scale);
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c16 * 16 + i <= kmax) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
-      const float m_new = fmaxf(m_run, mx);
+      // everything below lives in the log2 domain: exp(x * scale - m) == exp2(x * scale_log2 - m2)
+      const float m_new = fmaxf(m_run, mx <= -1.0e38f ? -3.0e38f : mx * scale_log2);
       const float m_use = m_new <= -1.0e38f ? 0.f : m_new;      // a fully masked row (padding) stays finite
-      const float corr = m_run <= -1.0e38f ? 0.f : __expf(m_run - m_use);
+      const float corr = m_run <= -1.0e38f ? 0.f : exp2f(m_run - m_use);
       l_run *= corr;
 #pragma unroll
       for (int c = 0; c < kAD; ++c) o_acc[c] *= corr;
-      // pass 2: p = exp(s - m), row sum, fp16 P into the swizzled A tile
+      // pass 2: p = exp2(s * scale_log2 - m), row sum, fp16 P into the swizzled A tile
 #pragma unroll 1
       for (int c16 = 0; c16 < kATile / 16; ++c16) {
         uint32_t v[16];
@@ -215,8 +223,12 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const int c = c16 * 16 + i;
-          const float p0 = c <= kmax ? __expf(__uint_as_float(v[i]) * p.qk_scale - m_use) : 0.f;
-          const float p1 = c + 1 <= kmax ? __expf(__uint_as_float(v[i + 1]) * p.qk_scale - m_use) : 0.f;
+          float p0 = exp2f(fmaf(__uint_as_float(v[i]), scale_log2, -m_use));
+          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_use));
+          if (!full) {
+            p0 = c <= kmax ? p0 : 0.f;
+            p1 = c + 1 <= kmax ? p1 : 0.f;
+          }
           l_run += p0 + p1;
           const __half2 h2 = __floats2half2_rn(p0, p1);
           packed[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
