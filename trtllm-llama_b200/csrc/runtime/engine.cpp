@@ -103,7 +103,7 @@ struct tbrt_engine {
   // plugins (one instance per distinct configuration, shared by all layers)
   PluginPtr lin, lin_res, lin_swiglu, lm, attn, normq, qpt, allreduce, allgather;
   // decode-shape (M <= 4) variants with the norm / quantiser fused into the projection's prologue ([ext] fields)
-  PluginPtr lin_n, lin_n_swiglu, lin_q_res, lm_n;
+  PluginPtr lin_n, lin_n_swiglu, lin_q_res, lm_n, normq_res;
 
   // device memory
   std::vector<void*> allocs;
@@ -285,6 +285,8 @@ int tbrt_engine::build_plugins() {
     fl.add<int32_t>("dyn_act_scaling", PluginFieldType::kINT32, 1);
     fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
     if (!(normq = make_plugin("RmsnormQuantization", fl))) return -1;
+    fl.add<int32_t>("fused_residual", PluginFieldType::kINT32, 1);      // (x, w, b, scale, residual) -> (q, scales, x + residual)
+    if (!(normq_res = make_plugin("RmsnormQuantization", fl))) return -1;
     FieldList none;
     if (!(qpt = make_plugin("QuantizePerToken", none))) return -1;
   }
@@ -348,10 +350,12 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       PluginTensorDesc id[4] = {desc({M, hid}, DataType::kHALF), desc({hid}, DataType::kHALF), desc({hid}, DataType::kHALF),
                                 desc({1}, DataType::kFLOAT)};
       PluginTensorDesc od[2] = {desc({M, hid}, DataType::kINT8), desc({M, 1}, DataType::kFLOAT)};
-      if (residual) {   // x + residual first (no fused-residual form requested from the plugin here)
-        RT_CALL(tb_add(sum_out, src, residual, (int64_t) M * hid, s));
-        launches += 1;
-        src = sum_out;
+      if (residual) {   // one kernel: h = x + residual (written to sum_out), RMSNorm(h), per-token int8
+        PluginTensorDesc id5[5] = {id[0], id[1], id[2], id[3], desc({M, hid}, DataType::kHALF)};
+        PluginTensorDesc od3[3] = {od[0], od[1], desc({M, hid}, DataType::kHALF)};
+        const void* in5[5] = {src, gamma, nullptr, d_dummy_scale, residual};
+        void* out3[3] = {xq, xs, sum_out};
+        return normq_res->enqueue(id5, od3, in5, out3, workspace, s);
       }
       const void* in[4] = {src, gamma, nullptr, d_dummy_scale};
       void* out[2] = {xq, xs};
@@ -398,9 +402,13 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     const void* dense_in = att;
     if (sq && !(fused && !tp)) { RT_CALL(quant(att, hid_l)); dense_in = xq; }
     (void) row_lin_nores;
-    if (!tp) {
-      RT_CALL(linear(row_lin, l.dense, dense_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, fused && sq));   // nxt = cur + dense(att)
-      if (!fused) RT_CALL(norm(nxt, l.ln_post, nullptr, nullptr));
+    if (!tp && fused) {
+      RT_CALL(linear(row_lin, l.dense, dense_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, sq));   // nxt = cur + dense(att)
+    } else if (!tp) {
+      // prefill shapes: the residual add rides in the norm kernel that follows (one fused add + RMSNorm (+ quantise)
+      // pass) instead of the GEMM epilogue, whose per-element residual loads stall the TMEM drain (ncu: 7 % tensor pipe)
+      RT_CALL(linear(lin.get(), l.dense, dense_in, xs, o, nullptr, M, DataType::kHALF, s));
+      RT_CALL(norm(o, l.ln_post, cur, nxt));                                                     // nxt = o + cur, x = norm(nxt)
     } else if (fused && ar_open) {
       // row-parallel partial straight into the peer-mapped buffer, then one kernel: all-reduce + residual add
       const int set = ar_site++ & 1;
@@ -434,10 +442,18 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     const void* proj_in = act;
     if (sq && !(fused && !tp)) { RT_CALL(quant(act, inter_l)); proj_in = xq; }
     const void* next_gamma = li + 1 < c.layers ? L[li + 1].ln_in : nullptr;
-    if (!tp) {
-      RT_CALL(linear(row_lin, l.proj, proj_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, fused && sq));
+    if (!tp && fused) {
+      RT_CALL(linear(row_lin, l.proj, proj_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, sq));
       std::swap(cur, nxt);
-      if (next_gamma && !fused) RT_CALL(norm(cur, next_gamma, nullptr, nullptr));
+    } else if (!tp) {
+      RT_CALL(linear(lin.get(), l.proj, proj_in, xs, o, nullptr, M, DataType::kHALF, s));
+      if (next_gamma) {
+        RT_CALL(norm(o, next_gamma, cur, nxt));
+      } else {
+        launches += 1;
+        RT_CALL(tb_add(nxt, o, cur, (int64_t) M * hid, s));
+      }
+      std::swap(cur, nxt);
     } else if (fused && ar_open) {
       const int set = ar_site++ & 1;
       RT_CALL(linear(lin.get(), l.proj, proj_in, xs, tb_ar_buffer(ar, set), nullptr, M, DataType::kHALF, s));
