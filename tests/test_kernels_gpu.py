@@ -256,6 +256,55 @@ def test_gemm_tc_residual(ops):
     np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), rtol=2e-3, atol=2e-3)
 
 
+# CTA-pair (cta_group::2) kernel, forced with force_nt=512: ragged token / channel tails, odd tile counts
+PAIR_SHAPES = [(300, 384, 256), (256, 256, 128), (1000, 640, 512), (513, 1408, 1024), (16, 128, 256)]
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+@pytest.mark.parametrize("per_token,per_channel", [(True, True), (False, False)])
+@pytest.mark.parametrize("out", ["float16", "float32", "int32"])
+def test_gemm_tc_pair_sq(ops, M, N, K, per_token, per_channel, out):
+    rng = np.random.default_rng(13)
+    a, b, sa, sb = _sq_inputs(rng, M, N, K, per_token, per_channel)
+    tdt = {"float16": torch.float16, "float32": torch.float32, "int32": torch.int32}[out]
+    ndt = {"float16": np.float16, "float32": np.float32, "int32": np.int32}[out]
+    y = host(ops.gemm_tc(ops.KIND_A8W8, dev(a), dev(b), sc=dev(sb), sr=dev(sa), out_dtype=tdt, force_nt=512))
+    assert np.array_equal(y, R.sq_gemm(a, b, sa, sb, ndt))           # bit-exact
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+@pytest.mark.parametrize("residual", [False, True])
+def test_gemm_tc_pair_f16(ops, M, N, K, residual):
+    rng = np.random.default_rng(14)
+    x = (rng.standard_normal((M, K)) * 0.5).astype(np.float16)
+    w = (rng.standard_normal((N, K)) * 0.05).astype(np.float16)
+    r = rng.standard_normal((M, N)).astype(np.float16) if residual else None
+    y = host(ops.gemm_tc(ops.KIND_F16, dev(x), dev(w), residual=dev(r) if residual else None, force_nt=512))
+    ref = R.gemm_f16(x, w)
+    if residual:
+        ref = R.residual_add(ref, r)
+    np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), rtol=2e-3, atol=2e-3)
+    # same MMA order and epilogue as the one-CTA kernel: identical bits
+    y1 = host(ops.gemm_tc(ops.KIND_F16, dev(x), dev(w), residual=dev(r) if residual else None, force_nt=256))
+    assert np.array_equal(y, y1)
+
+
+def test_gemm_tc_sq_prefill_size_auto_pair(ops):
+    """A prefill-size SmoothQuant GEMM (auto-dispatched to the CTA-pair kernel) equals the forced one-CTA result."""
+    M, N, K = 8192, 4096 + 128, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randint(-127, 128, (M, K), device="cuda", dtype=torch.int8, generator=g)
+    b = torch.randint(-127, 128, (N, K), device="cuda", dtype=torch.int8, generator=g)
+    st = torch.rand(M, 1, device="cuda", generator=g) * 0.01 + 1e-3
+    sc = torch.rand(1, N, device="cuda", generator=g) * 0.01 + 1e-3
+    auto = ops.gemm_tc(ops.KIND_A8W8, a, b, sc=sc, sr=st)
+    one = ops.gemm_tc(ops.KIND_A8W8, a, b, sc=sc, sr=st, force_nt=256)
+    assert torch.equal(auto, one)
+    i32 = ops.gemm_tc(ops.KIND_A8W8, a[:512], b, sc=torch.ones(1, 1, device="cuda"), sr=torch.ones(1, 1, device="cuda"),
+                      out_dtype=torch.int32, force_nt=512)
+    assert torch.equal(i32, (a[:512].double() @ b.double().t()).to(torch.int32))
+
+
 # ------------------------------------------------------------------------------------------------
 def _mmha_case(rng, B, H, S_max, past, max_in, in_lens, int8_kv, scale=1.0):
     Dh = 128

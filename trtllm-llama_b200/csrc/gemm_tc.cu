@@ -24,6 +24,7 @@
 // Roofline: decode shapes are HBM-bound (algorithmic bytes = N*K*bytes_per_weight); prefill shapes
 // are tensor-bound (2*M*N*K ops).
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap_host.h"
@@ -78,7 +79,8 @@ struct GemmCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kThreads = kWO ? 320 : 192;
   static constexpr int kTmemCols = (2 * NT) < 32 ? 32 : 2 * NT;
-  static constexpr size_t kSmemBytes = (size_t) kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t kSmemBytes =
+      (size_t) kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4 * NT * sizeof(float) /*sr stash*/;
 };
 
 template <int KIND, int NT>
@@ -99,6 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   uint64_t* tfull = bars + 3 * ST;       // [2]   MMA -> epilogue
   uint64_t* tempty = bars + 3 * ST + 2;  // [2]   epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * ST + 4);
+  float* sr_stash = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [4 epilogue warps][NT]
   __shared__ int s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,6 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     // =========================== epilogue ===============================
     const int q = warp & 3;                       // TMEM lane quarter owned by this warp
     int acc = 0, acc_phase = 0;
+    float* s_sr = sr_stash + (warp - 2) * NT;     // this warp's copy of the tile's per-token scales
     for (int it = blockIdx.x; it < items; it += gridDim.x) {
       int nt, mt, split;
       item_coords(p, it, nt, mt, split);
@@ -219,15 +223,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       };
 
       if (p.splits == 1) {
+        // per-token scales of this tile into a warp-private stash: a dependent global load per token row inside the
+        // drain loop serialised the epilogue (ncu: 170 cycles/row, the K=4096 int8 GEMMs were epilogue-bound)
+        if constexpr (KIND == kGI8) {
+          __syncwarp();
+          for (int i = lane; i < NT; i += 32)
+            s_sr[i] = p.sr_per_token ? (m0 + i < p.M ? p.sr[m0 + i] : 0.f) : p.sr[0];
+          __syncwarp();
+        }
 #pragma unroll 1
         for (int c = 0; c < NT / 16; ++c) {
           uint32_t v[16];
           tmem_ld16(t_addr + c * 16, v);
           tmem_ld_wait();
+          const int mc = m0 + c * 16;
+          if (n < p.N && mc + 16 <= p.M && p.out_type == 0) {
+            // fast path: a full chunk of fp16 outputs, no per-element branches
+            float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float f = KIND == kGI8 ? (float) (int) v[j] : __uint_as_float(v[j]);
-            finish(f, m0 + c * 16 + j);
+            for (int j = 0; j < 16; ++j) {
+              if constexpr (KIND == kGI8) f[j] = (float) (int) v[j] * (chan * s_sr[c * 16 + j]);
+              else if constexpr (Cfg::kWO) f[j] = __uint_as_float(v[j]) * chan;
+              else f[j] = __uint_as_float(v[j]);
+            }
+            __half* cp = reinterpret_cast<__half*>(p.c) + (size_t) mc * p.N + n;
+            if (p.residual) {
+              const __half* rp = p.residual + (size_t) mc * p.N + n;
+              __half r[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) r[j] = rp[(size_t) j * p.N];
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                cp[(size_t) j * p.N] = __float2half_rn(__half2float(__float2half_rn(f[j])) + __half2float(r[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) cp[(size_t) j * p.N] = __float2half_rn(f[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float f = KIND == kGI8 ? (float) (int) v[j] : __uint_as_float(v[j]);
+              finish(f, mc + j);
+            }
           }
         }
         tc_fence_before();
@@ -420,6 +457,16 @@ static int dispatch_nt(const GemmTcParams& p, const void* x, const void* w, void
   return -1;
 }
 
+// CTA-pair kernel (gemm_tc2.cu)
+int gemm_tc_pair(int kind, void* c, int out_type, const void* x, const void* w, const float* sc, const float* sr,
+                 int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K, cudaStream_t stream);
+
+// TB_GEMM_TC_PAIR=0 keeps every shape on the one-CTA kernel (A/B measurements)
+static bool pair_enabled() {
+  static const bool on = [] { const char* e = getenv("TB_GEMM_TC_PAIR"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 }  // namespace tb
 
 using namespace tb;
@@ -449,6 +496,15 @@ int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, co
   if ((kind == kGW8 || kind == kGW4) && !w_scale) return -1;
   if (kind == kGI8 && (!sc || !sr)) return -1;
   if (residual && out_type != 0) return -1;
+  // prefill-size fp16 / int8 problems (>= 2 full-size tiles per SM): CTA-pair kernel, a third less L2 traffic per MAC
+  if ((kind == kGF16 || kind == kGI8) && force_splits <= 0) {
+    const long tiles256 = (long) ((N + kTileN - 1) / kTileN) * ((M + 255) / 256);
+    // (measured: int8 +7..16 % over the one-CTA kernel at M = 16384; fp16 is no faster, so it stays opt-in)
+    const bool auto_pair =
+        kind == kGI8 && force_nt <= 0 && pair_enabled() && select_nt(M, N) == 256 && tiles256 >= 2 * kNumSMs;
+    if (force_nt == 512 || auto_pair)
+      return gemm_tc_pair(kind, c, out_type, x, w, sc, sr, sc_per_channel, sr_per_token, residual, M, N, K, stream);
+  }
   GemmTcParams p{};
   p.c = c; p.out_type = out_type; p.residual = (const __half*) residual; p.w_scale = (const __half*) w_scale;
   p.sc = sc; p.sr = sr; p.sc_per_channel = sc_per_channel; p.sr_per_token = sr_per_token;
