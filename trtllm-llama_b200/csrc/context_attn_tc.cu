@@ -6,11 +6,12 @@
 //
 // One CTA = 128 query rows of one (batch, head); it walks the key/value tiles 0..diag (causal) of 128 keys:
 //   warp 0      TMA producer: Q tile once, then K_j and V^T_j tiles into a 2-stage ring (128B-swizzled K-major boxes)
-//   warp 1      tcgen05.mma issuer (one lane): S_j = Q.K_j^T into TMEM (double-buffered), O_j = P_j.V_j into TMEM;
+//   warp 1      tcgen05.mma issuer (one lane): S_j = Q.K_j^T into TMEM (double-buffered), O += P_j.V_j into TMEM;
 //               S_{j+1} is issued before P_j is awaited, so the softmax of tile j overlaps the QK^T of tile j+1
 //   warps 2-5   softmax: TMEM lane = query row, so a thread owns a whole row — row max / sum need no shuffles.  Online
-//               softmax in fp32; P_j is written as fp16 into a 128B-swizzled shared tile (the A operand of P.V); the
-//               per-tile product O_j is read back from TMEM and folded into the thread's fp32 output row.
+//               softmax in fp32 (log2 domain) on the score row held in registers; P_j is written as fp16 into a
+//               128B-swizzled shared tile (the A operand of P.V).  O accumulates in TMEM across tiles relative to a stale
+//               running maximum and is rescaled in place (tcgen05.ld / st) only when a row of the warp beats it by 2^8.
 // V is needed as a K-major B operand [Dh x keys]; the activations hold it as [keys x Dh], so a small transpose kernel
 // writes V^T [B, H, Dh, S] into the caller's workspace first (2 * B*S*hidden bytes, ~45 us at cfg4 sizes).
 // Numerics: s = qk * scale with causal + length masking, p = exp(s - running max) rounded to fp16 for P.V (the reference
@@ -157,14 +158,14 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         if (j + 1 < n_kv) issue_s(j + 1);           // overlaps the softmax of tile j
-        mbar_wait(p_full, j & 1);                   // P_j is in shared memory, S_j and O_{j-1} have been read
+        mbar_wait(p_full, j & 1);                   // P_j is in shared memory, S_j has been read, O rescaled if needed
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t ad = umma_desc_sw128(smem_u32(sP + kb * kASub));
           const uint64_t bd = umma_desc_sw128(smem_u32(sV + st * kATileBytes + kb * kASub));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_O, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_O, ad + 2 * k, bd + 2 * k, idesc, (j | kb | k) ? 1u : 0u);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
@@ -177,10 +178,13 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const int qi = q0 + r;
     const uint32_t lane_addr = (uint32_t) (quarter * 32) << 16;
     const float scale_log2 = p.qk_scale * 1.4426950408889634f;
-    float m_run = -3.0e38f, l_run = 0.f;     // running max in the log2 domain
-    float o_acc[kAD];
-#pragma unroll
-    for (int c = 0; c < kAD; ++c) o_acc[c] = 0.f;
+    // The output row accumulates in TMEM (P.V MMAs with accumulate), relative to a STALE running maximum m_run: it is
+    // only raised (and O rescaled in TMEM, l_run with it) when some row of the warp exceeds it by more than 2^8, so
+    // the usual tile costs one read of S, the exponentials and the P store - no read-back of O, no wait for the P.V MMA
+    // inside the softmax chain.  p <= 2^8 keeps fp16 P exact enough (relative rounding) and the fp32 sum far from
+    // overflow; m_true tracks the real maximum for the reference's 1 / (sum + 1e-6) at the end.
+    float m_run = -3.0e38f, m_true = -3.0e38f, l_run = 0.f;     // log2 domain
+    constexpr float kLazy = 8.f;
 
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
@@ -189,42 +193,58 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       const uint32_t s_addr = tmem_S0 + lane_addr + (uint32_t) (st * kATile);
       const int k0 = j * kATile;
       const int kmax = min(qi, len - 1) - k0;           // columns c <= kmax are attended (causal and length)
-      // pass 1: row maximum of the raw scores (scale > 0 commutes with max); unmasked fast path off the diagonal
-      const bool full = kmax >= kATile - 1;
+      const bool full = kmax >= kATile - 1;             // unmasked fast path off the diagonal
+      // the whole score row in registers: one TMEM round trip per tile
+      uint32_t sv[kATile];
+#pragma unroll
+      for (int c16 = 0; c16 < kATile / 16; ++c16) tmem_ld16(s_addr + c16 * 16, sv + c16 * 16);
+      tmem_ld_wait();
       float mx = -3.0e38f;
-#pragma unroll 1
-      for (int c16 = 0; c16 < kATile / 16; ++c16) {
-        uint32_t v[16];
-        tmem_ld16(s_addr + c16 * 16, v);
-        tmem_ld_wait();
-        if (full) {
+      if (full) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int c = 0; c < kATile; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (c16 * 16 + i <= kmax) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
+        for (int c = 0; c < kATile; ++c)
+          if (c <= kmax) mx = fmaxf(mx, __uint_as_float(sv[c]));
       }
       // everything below lives in the log2 domain: exp(x * scale - m) == exp2(x * scale_log2 - m2)
-      const float m_new = fmaxf(m_run, mx <= -1.0e38f ? -3.0e38f : mx * scale_log2);
-      const float m_use = m_new <= -1.0e38f ? 0.f : m_new;      // a fully masked row (padding) stays finite
-      const float corr = m_run <= -1.0e38f ? 0.f : exp2f(m_run - m_use);
-      l_run *= corr;
-#pragma unroll
-      for (int c = 0; c < kAD; ++c) o_acc[c] *= corr;
-      // pass 2: p = exp2(s * scale_log2 - m), row sum, fp16 P into the swizzled A tile
+      const float m_tile = mx <= -1.0e38f ? -3.0e38f : mx * scale_log2;
+      m_true = fmaxf(m_true, m_tile);
+      const bool raise = m_tile > m_run + kLazy;        // (first attended tile: m_run = -3e38)
+      // P.V of tile j-1 must be complete before sP is rewritten and before O may be rescaled
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, raise)) {
+        const float m_new = fmaxf(m_run, m_tile);
+        const float corr = m_run <= -1.0e38f ? 0.f : exp2f(m_run - m_new);   // m_new >= m_run > -inf there
+        if (j > 0) {
 #pragma unroll 1
+          for (int c16 = 0; c16 < kAD / 16; ++c16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_O + lane_addr + c16 * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+            tmem_st16(tmem_O + lane_addr + c16 * 16, v);
+          }
+          tmem_st_wait();
+        }
+        l_run *= corr;
+        m_run = m_new;
+      }
+      const float m_use = m_run <= -1.0e38f ? 0.f : m_run;      // a fully masked row (padding) stays finite
+      // p = exp2(s * scale_log2 - m), row sum, fp16 P into the swizzled A tile
+#pragma unroll
       for (int c16 = 0; c16 < kATile / 16; ++c16) {
-        uint32_t v[16];
-        tmem_ld16(s_addr + c16 * 16, v);
-        tmem_ld_wait();
         uint32_t packed[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const int c = c16 * 16 + i;
-          float p0 = exp2f(fmaf(__uint_as_float(v[i]), scale_log2, -m_use));
-          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_use));
+          float p0 = exp2f(fmaf(__uint_as_float(sv[c]), scale_log2, -m_use));
+          float p1 = exp2f(fmaf(__uint_as_float(sv[c + 1]), scale_log2, -m_use));
           if (!full) {
             p0 = c <= kmax ? p0 : 0.f;
             p1 = c + 1 <= kmax ? p1 : 0.f;
@@ -239,36 +259,37 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         *reinterpret_cast<uint4*>(rowp + (((ch) ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
-      m_run = m_new;
       fence_proxy_async();      // generic-proxy writes of P -> visible to the tensor core
-      tc_fence_before();        // TMEM reads of S_j (and of O_{j-1}) are complete
+      tc_fence_before();        // TMEM reads of S_j and the rescale of O are complete
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      // O_j = P_j . V_j : fold into the fp32 output row
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
+    }
+    // O = sum_j P_j . V_j relative to m_run; bring sum and output to the true maximum, then 1 / (sum + 1e-6)
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    {
+      const float down = m_run <= -1.0e38f ? 0.f : exp2f(m_run - m_true);      // <= 1, >= 2^-8
+      const float inv = down * __fdividef(1.f, l_run * down + 1.e-6f);
+      __half* orow = p.out + ((size_t) b * p.S + qi) * hidden + (size_t) h * kAD;
+#pragma unroll 1
       for (int c16 = 0; c16 < kAD / 16; ++c16) {
         uint32_t v[16];
         tmem_ld16(tmem_O + lane_addr + c16 * 16, v);
         tmem_ld_wait();
+        if (qi < p.S) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[c16 * 16 + i] += __uint_as_float(v[i]);
+          for (int c8 = 0; c8 < 2; ++c8) {
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              oh[i] = __floats2half2_rn(__uint_as_float(v[c8 * 8 + 2 * i]) * inv, __uint_as_float(v[c8 * 8 + 2 * i + 1]) * inv);
+            *reinterpret_cast<uint4*>(orow + c16 * 16 + c8 * 8) = o;
+          }
+        }
       }
     }
     tc_fence_before();
-    if (qi < p.S) {
-      const float inv = __fdividef(1.f, l_run + 1.e-6f);
-      __half* orow = p.out + ((size_t) b * p.S + qi) * hidden + (size_t) h * kAD;
-#pragma unroll
-      for (int c8 = 0; c8 < kAD / 8; ++c8) {
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(o_acc[c8 * 8 + 2 * i] * inv, o_acc[c8 * 8 + 2 * i + 1] * inv);
-        *reinterpret_cast<uint4*>(orow + c8 * 8) = o;
-      }
-    }
   }
 
   tc_fence_before();
