@@ -25,9 +25,16 @@
 namespace tb {
 
 constexpr int kAD = 128;                 // head size
-constexpr int kATile = 128;              // query rows per CTA == keys per tile
+constexpr int kATile = 128;              // query rows per CTA
+constexpr int kAKeys = 64;               // keys per tile: halves the per-CTA footprint so TWO CTAs share an SM (8 softmax
+                                         // warps hide each other's MUFU / TMEM latency) and halves the causal waste
 constexpr int kASub = kATile * 128;      // bytes of one [128 rows x 64 halfs] swizzled sub-tile (16 KB)
-constexpr int kATileBytes = 2 * kASub;   // a [128 x 128] fp16 operand tile = two sub-tiles along K
+constexpr int kATileBytes = 2 * kASub;   // a [128 x 128] fp16 operand tile = two sub-tiles along K (Q)
+constexpr int kAKSub = kAKeys * 128;     // K sub-tile [64 keys x 64 halfs] (8 KB); a K stage is two of them
+constexpr int kAKBytes = 2 * kAKSub;     // 16 KB
+constexpr int kAVBytes = kASub;          // V^T stage [128 dims x 64 keys] = one sub-tile (16 KB)
+constexpr int kAPBytes = kASub;          // P tile [128 rows x 64 keys] = one sub-tile (16 KB)
+constexpr int kATmemCols = 256;          // S double buffer 2 x 64 + O 128
 constexpr int kAThreads = 192;
 
 struct FlashTcParams {
@@ -59,16 +66,15 @@ __global__ void __launch_bounds__(256) vt_transpose_kernel(const __half* __restr
   }
 }
 
-__global__ void __launch_bounds__(kAThreads, 1)
-flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_vt,
-                    const FlashTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+__global__ void __launch_bounds__(kAThreads, 2)
+flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_vt, const FlashTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];   // (no alignment slack: 2 CTAs x 113.25 KB just fit an SM)
   uint8_t* sQ = smem;                              // 32 KB
-  uint8_t* sK = sQ + kATileBytes;                  // 2 stages x 32 KB
-  uint8_t* sV = sK + 2 * kATileBytes;              // 2 stages x 32 KB   (V^T tile: [Dh rows x keys])
-  uint8_t* sP = sV + 2 * kATileBytes;              // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kATileBytes);
+  uint8_t* sK = sQ + kATileBytes;                  // 2 stages x 16 KB
+  uint8_t* sV = sK + 2 * kAKBytes;                 // 2 stages x 16 KB   (V^T tile: [Dh rows x keys])
+  uint8_t* sP = sV + 2 * kAVBytes;                 // 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kAPBytes);
   uint64_t* q_full = bars;          // [1]
   uint64_t* kv_full = bars + 1;     // [2]
   uint64_t* kv_empty = bars + 3;    // [2]
@@ -92,10 +98,12 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     }
     return;
   }
-  const int n_kv = min(qt + 1, (len + kATile - 1) / kATile);   // causal: key tiles 0..qt, clipped by the length
+  // causal: key tiles 0 .. (q0 + 127) / 64, clipped by the length
+  const int n_kv = min(2 * qt + 2, (len + kAKeys - 1) / kAKeys);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_vt);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -108,14 +116,14 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, kATmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 2 * kATile;   // S[2] at columns 0 / 128, O at 256
+  const uint32_t tmem_S0 = tmem_base, tmem_O = tmem_base + 2 * kAKeys;   // S[2] at columns 0 / 64, O at 128
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -126,20 +134,19 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1, ph = (j >> 1) & 1;
         mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * kATileBytes);
+        mbar_expect_tx(&kv_full[st], kAKBytes + kAVBytes);
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          tma_load_2d(sK + st * kATileBytes + kb * kASub, &tmap_qkv, &kv_full[st], hidden + h * kAD + kb * 64,
-                      b * p.S + j * kATile);
-          tma_load_2d(sV + st * kATileBytes + kb * kASub, &tmap_vt, &kv_full[st], j * kATile + kb * 64,
-                      (b * p.H + h) * kAD);
-        }
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_2d(sK + st * kAKBytes + kb * kAKSub, &tmap_k, &kv_full[st], hidden + h * kAD + kb * 64,
+                      b * p.S + j * kAKeys);
+        tma_load_2d(sV + st * kAVBytes, &tmap_vt, &kv_full[st], j * kAKeys, (b * p.H + h) * kAD);
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================
     if (lane == 0) {
-      constexpr uint32_t idesc = kIdescF16(kATile, kATile);
+      constexpr uint32_t idesc_s = kIdescF16(kATile, kAKeys);   // S  [128 q x 64 keys], K = 128 dims
+      constexpr uint32_t idesc_o = kIdescF16(kATile, kAD);      // O  [128 q x 128 dims], K = 64 keys
       auto issue_s = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
@@ -147,9 +154,9 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t ad = umma_desc_sw128(smem_u32(sQ + kb * kASub));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sK + st * kATileBytes + kb * kASub));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sK + st * kAKBytes + kb * kAKSub));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_S0 + (uint32_t) (st * kATile), ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_S0 + (uint32_t) (st * kAKeys), ad + 2 * k, bd + 2 * k, idesc_s, (kb | k) ? 1u : 0u);
         }
         umma_commit(&s_full[st]);
       };
@@ -160,13 +167,10 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         if (j + 1 < n_kv) issue_s(j + 1);           // overlaps the softmax of tile j
         mbar_wait(p_full, j & 1);                   // P_j is in shared memory, S_j has been read, O rescaled if needed
         tc_fence_after();
+        const uint64_t ad = umma_desc_sw128(smem_u32(sP));
+        const uint64_t bd = umma_desc_sw128(smem_u32(sV + st * kAVBytes));
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t ad = umma_desc_sw128(smem_u32(sP + kb * kASub));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sV + st * kATileBytes + kb * kASub));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_O, ad + 2 * k, bd + 2 * k, idesc, (j | kb | k) ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_O, ad + 2 * k, bd + 2 * k, idesc_o, (j | k) ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
       }
@@ -190,22 +194,22 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       const int st = j & 1;
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_S0 + lane_addr + (uint32_t) (st * kATile);
-      const int k0 = j * kATile;
+      const uint32_t s_addr = tmem_S0 + lane_addr + (uint32_t) (st * kAKeys);
+      const int k0 = j * kAKeys;
       const int kmax = min(qi, len - 1) - k0;           // columns c <= kmax are attended (causal and length)
-      const bool full = kmax >= kATile - 1;             // unmasked fast path off the diagonal
+      const bool full = kmax >= kAKeys - 1;             // unmasked fast path off the diagonal
       // the whole score row in registers: one TMEM round trip per tile
-      uint32_t sv[kATile];
+      uint32_t sv[kAKeys];
 #pragma unroll
-      for (int c16 = 0; c16 < kATile / 16; ++c16) tmem_ld16(s_addr + c16 * 16, sv + c16 * 16);
+      for (int c16 = 0; c16 < kAKeys / 16; ++c16) tmem_ld16(s_addr + c16 * 16, sv + c16 * 16);
       tmem_ld_wait();
       float mx = -3.0e38f;
       if (full) {
 #pragma unroll
-        for (int c = 0; c < kATile; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+        for (int c = 0; c < kAKeys; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
       } else {
 #pragma unroll
-        for (int c = 0; c < kATile; ++c)
+        for (int c = 0; c < kAKeys; ++c)
           if (c <= kmax) mx = fmaxf(mx, __uint_as_float(sv[c]));
       }
       // everything below lives in the log2 domain: exp(x * scale - m) == exp2(x * scale_log2 - m2)
@@ -238,7 +242,7 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       const float m_use = m_run <= -1.0e38f ? 0.f : m_run;      // a fully masked row (padding) stays finite
       // p = exp2(s * scale_log2 - m), row sum, fp16 P into the swizzled A tile
 #pragma unroll
-      for (int c16 = 0; c16 < kATile / 16; ++c16) {
+      for (int c16 = 0; c16 < kAKeys / 16; ++c16) {
         uint32_t packed[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
@@ -253,9 +257,9 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
           const __half2 h2 = __floats2half2_rn(p0, p1);
           packed[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
         }
-        // keys c16*16 .. +15 = two 16-byte chunks of sub-tile (c16 / 4), chunk index (c16 % 4) * 2 (+1), XOR (row & 7)
-        uint8_t* rowp = sP + (c16 >> 2) * kASub + r * 128;
-        const int ch = (c16 & 3) * 2;
+        // keys c16*16 .. +15 = two 16-byte chunks of the row, chunk index c16 * 2 (+1), XOR (row & 7)
+        uint8_t* rowp = sP + r * 128;
+        const int ch = c16 * 2;
         *reinterpret_cast<uint4*>(rowp + (((ch) ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
       }
@@ -294,7 +298,7 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, kATmemCols);
 }
 
 // launched after ctx_prep_kernel (RoPE in place, KV-cache write): transpose V, then the fused attention
@@ -305,14 +309,17 @@ int launch_flash_ctx_tc(void* out, const void* qkv, void* workspace, const int* 
   __half* vt = static_cast<__half*>(workspace);
   vt_transpose_kernel<<<dim3((S_pad + 31) / 32, num_heads * (kAD / 32), batch), 256, 0, stream>>>(
       static_cast<const __half*>(qkv), vt, seq_len, S_pad, num_heads);
-  CUtensorMap tq, tv;
+  CUtensorMap tq, tk, tv;
   int rc = make_tmap(&tq, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t) batch * seq_len, (uint64_t) 3 * hidden, kATile, 64,
                      CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tmap(&tk, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t) batch * seq_len, (uint64_t) 3 * hidden, kAKeys, 64,
+                 CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   rc = make_tmap(&tv, vt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t) batch * num_heads * kAD, (uint64_t) S_pad, kATile, 64,
                  CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  const size_t smem = 6 * (size_t) kATileBytes + 1024 + 256;
+  const size_t smem = (size_t) kATileBytes + 2 * kAKBytes + 2 * kAVBytes + kAPBytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
     TB_CHECK_CUDA(cudaFuncSetAttribute(flash_ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -320,7 +327,7 @@ int launch_flash_ctx_tc(void* out, const void* qkv, void* workspace, const int* 
   }
   FlashTcParams p{static_cast<__half*>(out), input_lengths, seq_len, num_heads, qk_scale};
   dim3 grid((seq_len + kATile - 1) / kATile, num_heads, batch);
-  flash_ctx_tc_kernel<<<grid, kAThreads, smem, stream>>>(tq, tv, p);
+  flash_ctx_tc_kernel<<<grid, kAThreads, smem, stream>>>(tq, tk, tv, p);
   return (int) cudaGetLastError();
 }
 
