@@ -111,6 +111,10 @@ int tb_context_attention(void* out, void* qkv, void* kv_cache, const int* input_
 /* ---- glue (TRT-native ops in the reference, k14) ---------------------------------------------- */
 int tb_embedding(void* out, const void* table, const int* ids, int tokens, int hidden, int vocab, tb_stream_t s);
 int tb_swiglu(void* out, const void* gate, const void* up, int rows, int inter, int in_stride, tb_stream_t s);
+/* SwiGLU + QuantizePerToken in one pass (prefill, SmoothQuant): dst int8 [rows, inter], scales fp32 [rows]; bit-identical
+ * to tb_swiglu followed by tb_quantize_per_token (LQ/llama_model.py MLP act + T/quantization/functional.py:135-151). */
+int tb_swiglu_quant(int8_t* dst, float* scales, const void* gate, const void* up, int rows, int inter, int in_stride,
+                    tb_stream_t s);
 int tb_add(void* out, const void* a, const void* b, int64_t n, tb_stream_t s);
 int tb_gather_last_token(void* out, const void* in, const int* last_ids, int batch, int seq, int hidden,
                          tb_stream_t s);

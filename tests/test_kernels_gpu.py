@@ -373,6 +373,20 @@ def test_context_attention(ops, int8_kv, S, lens, use_tc):
         np.testing.assert_allclose(nc.astype(np.float32), cache_ref.astype(np.float32), atol=2e-3)
 
 
+@pytest.mark.parametrize("rows,inter", [(7, 384), (33, 11008), (5, 16384), (3, 8)])
+def test_swiglu_quant_fused(ops, rows, inter):
+    """One-pass SwiGLU + per-token quantisation == the two separate kernels, bit for bit (and the oracle's quantiser on
+    the device's own SwiGLU output; the oracle's SwiGLU itself differs from the device by expf rounding only)."""
+    rng = np.random.default_rng(16)
+    gu = (rng.standard_normal((rows, 2 * inter)) * 2).astype(np.float16)
+    q, sc = ops.swiglu_quant(dev(gu))
+    act = ops.swiglu(dev(gu))
+    q2, sc2 = ops.quantize_per_token(act)
+    assert np.array_equal(host(q), host(q2)) and np.array_equal(host(sc), host(sc2))
+    rq, rs = R.quantize_per_token(host(act))
+    assert np.array_equal(host(q), rq) and np.array_equal(host(sc).reshape(-1), rs.reshape(-1))
+
+
 # ------------------------------------------------------------------------------------------------
 def test_glue(ops):
     rng = np.random.default_rng(15)

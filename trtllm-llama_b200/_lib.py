@@ -44,6 +44,7 @@ SIGNATURES = {
     "tb_context_attention": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp]),
     "tb_embedding": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "tb_swiglu": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "tb_swiglu_quant": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     "tb_add": (i32, [vp, vp, vp, i64, vp]),
     "tb_gather_last_token": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "tb_argmax": (i32, [vp, vp, i32, i32, i32, vp]),

@@ -430,17 +430,25 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       }
     }
     std::swap(cur, nxt);
+    bool act_quantised = false;
     if (fused) {
       RT_CALL(linear(lin_n_swiglu.get(), l.fc_gate, cur, xs, act, nullptr, M, DataType::kHALF, s, l.ln_post, true));
     } else if (fuse_swiglu) {
       RT_CALL(linear(lin_swiglu.get(), l.fc_gate, lin_in, xs, act, nullptr, M, DataType::kHALF, s));
+    } else if (sq && inter_l <= 16384) {
+      // SmoothQuant prefill: SwiGLU and the per-token quantisation of its output in one pass over the GEMM output
+      RT_CALL(linear(lin.get(), l.fc_gate, lin_in, xs, gu, nullptr, M, DataType::kHALF, s));
+      launches += 1;
+      RT_CALL(tb_swiglu_quant(xq, xs, gu, gu + inter_l, M, inter_l, 2 * inter_l, s));
+      act_quantised = true;
     } else {
       RT_CALL(linear(lin.get(), l.fc_gate, lin_in, xs, gu, nullptr, M, DataType::kHALF, s));
       launches += 1;
       RT_CALL(tb_swiglu(act, gu, gu + inter_l, M, inter_l, 2 * inter_l, s));
     }
     const void* proj_in = act;
-    if (sq && !(fused && !tp)) { RT_CALL(quant(act, inter_l)); proj_in = xq; }
+    if (act_quantised) proj_in = xq;
+    else if (sq && !(fused && !tp)) { RT_CALL(quant(act, inter_l)); proj_in = xq; }
     const void* next_gamma = li + 1 < c.layers ? L[li + 1].ln_in : nullptr;
     if (!tp && fused) {
       RT_CALL(linear(row_lin, l.proj, proj_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, sq));

@@ -230,6 +230,19 @@ def swiglu(gate_up):
     return out
 
 
+def swiglu_quant(gate_up):
+    """SwiGLU + per-token int8 quantisation in one pass: gate_up [..., 2*inter] -> (int8 [..., inter], fp32 scales [..., 1])."""
+    _chk_cuda(gate_up)
+    inter = gate_up.shape[-1] // 2
+    rows = gate_up.numel() // gate_up.shape[-1]
+    q = torch.empty(gate_up.shape[:-1] + (inter,), dtype=torch.int8, device=gate_up.device)
+    sc = torch.empty(gate_up.shape[:-1] + (1,), dtype=torch.float32, device=gate_up.device)
+    g = gate_up.view(rows, 2 * inter)
+    check(lib.tb_swiglu_quant(_p(q), _p(sc), g.data_ptr(), g.data_ptr() + inter * 2, rows, inter, 2 * inter, _stream()),
+          "tb_swiglu_quant")
+    return q, sc
+
+
 def add(a, b):
     _chk_cuda(a, b)
     out = torch.empty_like(a)
