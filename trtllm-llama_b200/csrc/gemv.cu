@@ -54,6 +54,7 @@ struct GemvParams {
 constexpr int kGemvThreads = 256;
 constexpr int kGemvWarps = kGemvThreads / 32;
 constexpr int kGemvU = 8;                                     // 16-byte weight loads in flight per lane
+constexpr int kProRegIters = 6;                               // prologue: a row of up to 6 x 2048 halves stays in registers
 
 template <int KIND> struct KTraits;
 template <> struct KTraits<kF16>  { static constexpr int kElemsPer16B = 8;  };
@@ -196,6 +197,88 @@ __global__ void __launch_bounds__(kGemvThreads, (MB >= 4 ? 2 : 4)) gemv_kernel(c
         continue;
       }
       const __half* xr = xin + (size_t) m * K;
+      if (K <= kProRegIters * kGemvThreads * 8) {
+        // the row in registers: ONE trip to L2 for the whole prologue instead of one per pass (norm: 2, norm + quantise:
+        // 3); same arithmetic in the same order as the streaming version below, which stays for longer rows
+        uint4 raw[kProRegIters];
+#pragma unroll
+        for (int it = 0; it < kProRegIters; ++it) {
+          const int i = (it * kGemvThreads + tid) * 8;
+          if (i < K) raw[it] = *reinterpret_cast<const uint4*>(xr + i);
+        }
+        if (p.prologue != kProQuant) {
+          float sq = 0.f;
+#pragma unroll
+          for (int it = 0; it < kProRegIters; ++it) {
+            if ((it * kGemvThreads + tid) * 8 < K) {
+              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h[j]);
+                sq += f.x * f.x + f.y * f.y;
+              }
+            }
+          }
+          sq = cta_reduce(sq, red, false);
+          const float inv = rsqrtf(sq / K + p.eps);
+#pragma unroll
+          for (int it = 0; it < kProRegIters; ++it) {
+            const int i = (it * kGemvThreads + tid) * 8;
+            if (i < K) {
+              const uint4 g4 = *reinterpret_cast<const uint4*>(p.gamma + i);
+              const __half2* g = reinterpret_cast<const __half2*>(&g4);
+              __half2* h = reinterpret_cast<__half2*>(&raw[it]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h[j]), gg = __half22float2(g[j]);
+                h[j] = __floats2half2_rn(f.x * inv * gg.x, f.y * inv * gg.y);
+              }
+            }
+          }
+        }
+        if constexpr (KIND == kA8W8) {
+          float amax = 0.f;
+#pragma unroll
+          for (int it = 0; it < kProRegIters; ++it) {
+            if ((it * kGemvThreads + tid) * 8 < K) {
+              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h[j]);
+                amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+              }
+            }
+          }
+          amax = fmaxf(cta_reduce(amax, red, true), __half2float(__float2half_rn(1e-6f)));
+          const float qs = 127.f / amax;
+          if (tid == 0) srow[m] = amax / 127.f;
+#pragma unroll
+          for (int it = 0; it < kProRegIters; ++it) {
+            const int i = (it * kGemvThreads + tid) * 8;
+            if (i < K) {
+              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 t = __half22float2(h[j]);
+                f[2 * j] = t.x * qs;
+                f[2 * j + 1] = t.y * qs;
+              }
+              uint2 o;
+              o.x = pack4_i8(f[0], f[1], f[2], f[3]);
+              o.y = pack4_i8(f[4], f[5], f[6], f[7]);
+              *reinterpret_cast<uint2*>(xs + (size_t) m * xstride + i) = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < kProRegIters; ++it) {
+            const int i = (it * kGemvThreads + tid) * 8;
+            if (i < K) *reinterpret_cast<uint4*>(xs + (size_t) m * xstride + (size_t) i * 2) = raw[it];
+          }
+        }
+        continue;
+      }
       float inv = 1.f;
       if (p.prologue != kProQuant) {
         float sq = 0.f;
