@@ -135,8 +135,87 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
     // one warp per token row (M <= 8 rows, 8 warps): every row's statistics are warp-local reductions, so the rows
     // proceed in parallel and the whole prologue costs two L2 round trips instead of 2 x M block-wide ones
     const __half* xin = reinterpret_cast<const __half*>(p.x);
+    constexpr int kRegIters = 16;                          // rows up to 16 x 256 halves stay in registers
+    // (only for M <= 4: with all 8 warps bursting a whole row each the projections got slower, 16.2 -> 17.9 us on QKV)
+    const bool in_regs = (K % 256 == 0) && K / 256 <= kRegIters && M <= 4;
     for (int m = warp; m < M; m += kMmaWarps) {
       const __half* xr = xin + (size_t) m * K;
+      if (in_regs) {
+        // the row in registers: one L2 round trip for the whole prologue; same arithmetic, same order as below
+        const int nit = K / 256;
+        uint4 raw[kRegIters];
+#pragma unroll
+        for (int it = 0; it < kRegIters; ++it)
+          if (it < nit) raw[it] = *reinterpret_cast<const uint4*>(xr + it * 256 + lane * 8);
+        if (p.prologue != kMProQuant) {
+          float sq = 0.f;
+#pragma unroll
+          for (int it = 0; it < kRegIters; ++it) {
+            if (it < nit) {
+              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h[j]);
+                sq += f.x * f.x + f.y * f.y;
+              }
+            }
+          }
+          sq = warp_sum(sq);
+          const float inv = rsqrtf(sq / K + p.eps);
+#pragma unroll
+          for (int it = 0; it < kRegIters; ++it) {
+            if (it < nit) {
+              __half2* h = reinterpret_cast<__half2*>(&raw[it]);
+              const uint4 g4 = *reinterpret_cast<const uint4*>(p.gamma + it * 256 + lane * 8);
+              const __half2* gm = reinterpret_cast<const __half2*>(&g4);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h[j]), gg = __half22float2(gm[j]);
+                h[j] = __floats2half2_rn(f.x * inv * gg.x, f.y * inv * gg.y);
+              }
+            }
+          }
+        }
+        if constexpr (INT) {
+          float amax = 0.f;
+#pragma unroll
+          for (int it = 0; it < kRegIters; ++it) {
+            if (it < nit) {
+              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(h[j]);
+                amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+              }
+            }
+          }
+          amax = fmaxf(warp_max(amax), __half2float(__float2half_rn(1e-6f)));
+          const float qs = 127.f / amax;
+          if (lane == 0) srow[m] = amax / 127.f;
+#pragma unroll
+          for (int it = 0; it < kRegIters; ++it) {
+            if (it < nit) {
+              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 v = __half22float2(h[j]);
+                f[2 * j] = v.x * qs;
+                f[2 * j + 1] = v.y * qs;
+              }
+              uint2 o;
+              o.x = pack4_i8(f[0], f[1], f[2], f[3]);
+              o.y = pack4_i8(f[4], f[5], f[6], f[7]);
+              *reinterpret_cast<uint2*>(xs + (size_t) m * xstride + it * 256 + lane * 8) = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < kRegIters; ++it)
+            if (it < nit) *reinterpret_cast<uint4*>(xs + (size_t) m * xstride + (size_t) (it * 256 + lane * 8) * 2) = raw[it];
+        }
+        continue;
+      }
       float inv = 1.f;
       if (p.prologue != kMProQuant) {
         float sq = 0.f;
