@@ -245,6 +245,24 @@ def test_gemm_tc_weight_only(ops, bits, M, N, K):
     np.testing.assert_allclose(y.astype(np.float32), ref.astype(np.float32), atol=_wo_tol(ref, bits))
 
 
+@pytest.mark.parametrize("bits", [8, 4])
+def test_gemm_tc_weight_only_prefill_dequant_route(ops, bits):
+    """Prefill-size weight-only GEMMs dequantise the matrix to fp16 once and run the fp16 kernel: identical bits to the
+    fused converter kernel (forced with force_nt), and within tolerance of the oracle."""
+    rng = np.random.default_rng(17)
+    M, N, K = 2100, 384, 512
+    x, wp, scales, ref = _wo_inputs(rng, M, N, K, bits)
+    kind = ops.KIND_W8 if bits == 8 else ops.KIND_W4
+    r = (rng.standard_normal((M, N))).astype(np.float16)
+    auto = host(ops.gemm_tc(kind, dev(x), dev(wp), w_scale=dev(scales)))
+    fused = host(ops.gemm_tc(kind, dev(x), dev(wp), w_scale=dev(scales), force_nt=256))
+    assert np.array_equal(auto, fused)
+    np.testing.assert_allclose(auto.astype(np.float32), ref.astype(np.float32), atol=_wo_tol(ref, bits))
+    auto_r = host(ops.gemm_tc(kind, dev(x), dev(wp), w_scale=dev(scales), residual=dev(r)))
+    fused_r = host(ops.gemm_tc(kind, dev(x), dev(wp), w_scale=dev(scales), residual=dev(r), force_nt=256))
+    assert np.array_equal(auto_r, fused_r)
+
+
 def test_gemm_tc_residual(ops):
     rng = np.random.default_rng(12)
     M, N, K = 8, 256, 512

@@ -24,6 +24,7 @@
 // Roofline: decode shapes are HBM-bound (algorithmic bytes = N*K*bytes_per_weight); prefill shapes
 // are tensor-bound (2*M*N*K ops).
 #include <cuda.h>
+#include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
@@ -202,14 +203,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       const uint32_t t_addr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * NT);
 
       float chan = 1.f;
+      const bool f16_scaled = KIND == kGF16 && p.w_scale != nullptr;   // weight-only weights dequantised to fp16 up front
       if (n < p.N) {
-        if constexpr (Cfg::kWO) chan = __half2float(p.w_scale[n]);
+        if (Cfg::kWO || f16_scaled) chan = __half2float(p.w_scale[n]);
         if constexpr (KIND == kGI8) chan = p.sc[p.sc_per_channel ? n : 0];
       }
       auto finish = [&](float v, int m) {   // v: accumulated value as float, before scaling
         if (n >= p.N || m >= p.M) return;
         if constexpr (KIND == kGI8) v = v * (chan * p.sr[p.sr_per_token ? m : 0]);
-        if constexpr (Cfg::kWO) v = v * chan;
+        if (Cfg::kWO || f16_scaled) v = v * chan;
         const size_t oi = (size_t) m * p.N + n;
         if (p.out_type == 0) {
           __half h = __float2half_rn(v);
@@ -244,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             for (int j = 0; j < 16; ++j) {
               if constexpr (KIND == kGI8) f[j] = (float) (int) v[j] * (chan * s_sr[c * 16 + j]);
               else if constexpr (Cfg::kWO) f[j] = __uint_as_float(v[j]) * chan;
-              else f[j] = __uint_as_float(v[j]);
+              else f[j] = f16_scaled ? __uint_as_float(v[j]) * chan : __uint_as_float(v[j]);
             }
             __half* cp = reinterpret_cast<__half*>(p.c) + (size_t) mc * p.N + n;
             if (p.residual) {
@@ -434,6 +436,43 @@ static int launch_gemm_tc(GemmTcParams p, const void* x, const void* w, void* wo
   return (int) cudaGetLastError();
 }
 
+// Weight-only weights -> plain fp16 [N, K] (exact: |w| <= 127 / 7), unscaled; the per-channel scale stays in the GEMM
+// epilogue.  One thread per 16 raw bytes, same element order as the converter warps of the fused kernel.
+template <int KIND>
+__global__ void dequant_weights_kernel(__half* __restrict__ out, const uint8_t* __restrict__ w, int64_t chunks) {
+  for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < chunks; i += (int64_t) gridDim.x * blockDim.x) {
+    const uint4 raw = ldg_nc_v4(w + i * 16);
+    if constexpr (KIND == kGW8) {
+      __half2 h[8];
+      i8x4_to_h2x2(raw.x, h[0], h[1]);
+      i8x4_to_h2x2(raw.y, h[2], h[3]);
+      i8x4_to_h2x2(raw.z, h[4], h[5]);
+      i8x4_to_h2x2(raw.w, h[6], h[7]);
+      uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+      o[0] = *reinterpret_cast<uint4*>(&h[0]);
+      o[1] = *reinterpret_cast<uint4*>(&h[4]);
+    } else {
+      __half2 h[16];
+      i4x8_to_h2x4(raw.x, h + 0);
+      i4x8_to_h2x4(raw.y, h + 4);
+      i4x8_to_h2x4(raw.z, h + 8);
+      i4x8_to_h2x4(raw.w, h + 12);
+      uint4* o = reinterpret_cast<uint4*>(out + i * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[c] = *reinterpret_cast<uint4*>(&h[4 * c]);
+    }
+  }
+}
+
+// Prefill-size weight-only problems: the fused kernel's converter stage costs 20-30 % against the plain fp16 kernel
+// (1.0-1.2 vs 1.3-1.4 PFLOP/s at M = 15360: one pipeline stage less and a longer stage latency), while dequantising the
+// whole matrix once is a 25-60 us HBM-bound pass.  Same MMA inputs in the same order -> bit-identical results.
+constexpr int kDequantMinM = 2048;
+static bool wo_dequant_enabled() {
+  static const bool on = [] { const char* e = getenv("TB_GEMM_WO_DEQUANT"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // token-tile width: the smallest of 16..256 covering M; prefill-like shapes shrink it until the grid covers the SMs
 static int select_nt(int M, int N) {
   int nt = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256)));
@@ -481,7 +520,10 @@ size_t tb_gemm_tc_workspace_bytes(int M, int N, int K) {
   const int m_tiles = (M + nt - 1) / nt;
   const size_t base = (size_t) n_tiles * m_tiles;
   size_t splits = (base < (size_t) kNumSMs && nt <= 16) ? (2 * kNumSMs + base - 1) / base : 1;
-  return base * splits * nt * kTileN * sizeof(float) + 256;
+  size_t bytes = base * splits * nt * kTileN * sizeof(float) + 256;
+  // prefill sizes: room for a weight-only matrix dequantised to fp16 (the function does not know the weight kind)
+  if (M >= kDequantMinM) bytes = std::max(bytes, (size_t) N * K * sizeof(__half) + 256);
+  return bytes;
 }
 size_t tb_gemm_tc_counter_bytes(void) { return (size_t) kGemmMaxCounters * sizeof(int); }
 
@@ -496,6 +538,19 @@ int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, co
   if ((kind == kGW8 || kind == kGW4) && !w_scale) return -1;
   if (kind == kGI8 && (!sc || !sr)) return -1;
   if (residual && out_type != 0) return -1;
+  if ((kind == kGW8 || kind == kGW4) && M >= kDequantMinM && force_splits <= 0 && force_nt <= 0 && wo_dequant_enabled() &&
+      workspace && workspace_bytes >= (size_t) N * K * sizeof(__half)) {
+    __half* w16 = static_cast<__half*>(workspace);
+    const int64_t chunks = (int64_t) N * K / (kind == kGW8 ? 16 : 32);
+    const int blocks = (int) std::min<int64_t>((chunks + 255) / 256, (int64_t) kNumSMs * 16);
+    if (kind == kGW8) dequant_weights_kernel<kGW8><<<blocks, 256, 0, stream>>>(w16, static_cast<const uint8_t*>(w), chunks);
+    else dequant_weights_kernel<kGW4><<<blocks, 256, 0, stream>>>(w16, static_cast<const uint8_t*>(w), chunks);
+    if (cudaGetLastError() != cudaSuccess) return -13;
+    GemmTcParams pd{};
+    pd.c = c; pd.out_type = out_type; pd.residual = (const __half*) residual; pd.w_scale = (const __half*) w_scale;
+    pd.M = M; pd.N = N; pd.K = K;
+    return dispatch_nt<kGF16>(pd, x, w16, nullptr, 0, counters, 0, 0, stream);
+  }
   // prefill-size fp16 / int8 problems (>= 2 full-size tiles per SM): CTA-pair kernel, a third less L2 traffic per MAC
   if ((kind == kGF16 || kind == kGI8) && force_splits <= 0) {
     const long tiles256 = (long) ((N + kTileN - 1) / kTileN) * ((M + 255) / 256);
