@@ -76,7 +76,9 @@ __device__ __forceinline__ void unpack16(const uint4& r, float* f) {
 }
 
 template <bool INT8>
-__global__ void __launch_bounds__(kMmhaThreads) mmha_decode_kernel(MmhaParams p) {
+// fp16 caches: capped at 64 registers so that four CTAs share an SM (76 registers = three CTAs: the 512 CTAs of cfg3 no
+// longer fit one wave, 1332 -> 1428 tokens/s); the int8 variant is at 64 already and loses with the explicit bound
+__global__ void __launch_bounds__(kMmhaThreads, INT8 ? 0 : 4) mmha_decode_kernel(MmhaParams p) {
   using TR = KvTraits<INT8>;
   constexpr int LPK = TR::kLanesPerKey, DPL = TR::kDimsPerLane, KPI = TR::kKeysPerIter;
   constexpr int ELT = INT8 ? 1 : 2;
