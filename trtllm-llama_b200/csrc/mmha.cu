@@ -17,6 +17,7 @@
 //   * int8 dequantisation scale is folded: s*(q.K_int8) instead of q.fp16(s*K_int8);
 //   * with nsplit > 1 the probabilities are normalised after the combine (flash-decoding) rather
 //     than before P.V; with nsplit == 1 the reference order (p * 1/(sum+1e-6) -> fp16 -> P.V) is kept.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -75,10 +76,29 @@ __device__ __forceinline__ void unpack16(const uint4& r, float* f) {
   }
 }
 
-template <bool INT8>
-// fp16 caches: capped at 64 registers so that four CTAs share an SM (76 registers = three CTAs: the 512 CTAs of cfg3 no
-// longer fit one wave, 1332 -> 1428 tokens/s); the int8 variant is at 64 already and loses with the explicit bound
-__global__ void __launch_bounds__(kMmhaThreads, INT8 ? 0 : 4) mmha_decode_kernel(MmhaParams p) {
+__device__ __forceinline__ void mmha_mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t mmha_h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ uint32_t mmha_pack_h2(float a, float b) { return mmha_h2u(__floats2half2_rn(a, b)); }
+
+// Launch bounds.  fp16 caches: capped at 64 registers so that four CTAs share an SM (76 registers = three CTAs: the 512
+// CTAs of cfg3 no longer fit one wave, 1332 -> 1428 tokens/s); the int8 FMA variant is at 64 already and loses with an
+// explicit bound.
+// MMA = true (int8 caches, long contexts): the two streaming loops run on tensor cores (mma.sync m16n8k16, fp32
+// accumulate).  The FMA loops spend PRMT + FSUB + FFMA per cached element and are issue-bound at 2048-token contexts
+// (ncu: smsp__issue_active 63 %, 3.4 TB/s); here an element costs 1.25 instructions of exact int8 -> fp16 expansion and
+// the multiply-adds ride in the MMA.  Q.K^T: a 16-key block is the A operand (lane (g, t) loads 16 contiguous bytes of
+// keys g and g + 8 per 64-dim step; the k order inside an MMA is a fixed permutation applied to q as well), q sits in
+// column 0 of B.  P.V: A = V^T with lane g owning dims [16g, 16g + 16) (row g of MMA m = dim 16g + m, row g + 8 = dim
+// 16g + 8 + m), so a lane loads 16 contiguous bytes of 4 keys; key pairs are interleaved with PRMT before the
+// expansion; the fp16 probabilities sit in column 0 of B.
+template <bool INT8, bool MMA = false>
+__global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_decode_kernel(MmhaParams p) {
+  static_assert(!MMA || INT8, "the tensor-core loops are for int8 caches");
   using TR = KvTraits<INT8>;
   constexpr int LPK = TR::kLanesPerKey, DPL = TR::kDimsPerLane, KPI = TR::kKeysPerIter;
   constexpr int ELT = INT8 ? 1 : 2;
@@ -188,6 +208,67 @@ __global__ void __launch_bounds__(kMmhaThreads, INT8 ? 0 : 4) mmha_decode_kernel
 
   float lmax = -3.0e38f;
   constexpr int UN = INT8 ? 4 : 8;   // 16-byte loads in flight per thread (the int8 variant is register-bound at 64)
+  if constexpr (MMA) {
+    const int g = lane >> 2, t = lane & 3;
+    // q as the B operand of the 8 MMAs of a key block: column 0 only (lanes with g == 0), same k permutation as A
+    uint32_t bq[2][4][2];
+#pragma unroll
+    for (int st = 0; st < 2; ++st)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = 64 * st + 16 * t + 4 * j;
+        bq[st][j][0] = g == 0 ? mmha_pack_h2(q_s[d], q_s[d + 1]) : 0u;
+        bq[st][j][1] = g == 0 ? mmha_pack_h2(q_s[d + 2], q_s[d + 3]) : 0u;
+      }
+    const int nblk = (len + 15) >> 4;
+    for (int kb = warp; kb < nblk; kb += 2 * (kMmhaThreads / 32)) {   // two key blocks in flight per warp
+      uint4 lo[2][2], hi[2][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k0 = (kb + u * (kMmhaThreads / 32)) * 16;
+        const bool okl = k0 + g < len, okh = k0 + g + 8 < len;
+        const uint8_t* rl = kbase + (size_t) (l0 + k0 + g) * kDh + t * 16;
+        const uint8_t* rh = rl + 8 * kDh;
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          lo[u][st] = okl ? ldg_nc_v4(rl + 64 * st) : make_uint4(0, 0, 0, 0);
+          hi[u][st] = okh ? ldg_nc_v4(rh + 64 * st) : make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k0 = (kb + u * (kMmhaThreads / 32)) * 16;
+        if (k0 < len) {                                                 // warp-uniform
+          float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int st = 0; st < 2; ++st) {
+            const uint32_t wl[4] = {lo[u][st].x, lo[u][st].y, lo[u][st].z, lo[u][st].w};
+            const uint32_t wh[4] = {hi[u][st].x, hi[u][st].y, hi[u][st].z, hi[u][st].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __half2 l0h, l1h, h0h, h1h;
+              i8x4_to_h2x2(wl[j], l0h, l1h);
+              i8x4_to_h2x2(wh[j], h0h, h1h);
+              mmha_mma_f16(c, mmha_h2u(l0h), mmha_h2u(h0h), mmha_h2u(l1h), mmha_h2u(h1h), bq[st][j][0], bq[st][j][1]);
+            }
+          }
+          if (t == 0) {                                                 // column 0: c[0] = key g, c[2] = key g + 8
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int ii = k0 + g + 8 * hh;
+              if (ii < len) {
+                float d = c[2 * hh] * qk_scale;
+                const bool masked = mrow ? (mrow[l0 + ii] != 0) : (l0 + ii >= in_len && l0 + ii < p.max_input_len);
+                if (masked) d = -3.0e38f;
+                s_s[ii] = d;
+                lmax = fmaxf(lmax, d);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else
   for (int i = grp; i - grp < len; i += KPI * UN) {   // trip count uniform across the warp (shuffles)
     uint4 raw[UN];
 #pragma unroll
@@ -254,6 +335,67 @@ __global__ void __launch_bounds__(kMmhaThreads, INT8 ? 0 : 4) mmha_decode_kernel
   __syncthreads();
 
   // ---- P.V --------------------------------------------------------------------------------------
+  if constexpr (MMA) {
+    const int g = lane >> 2, t = lane & 3;
+    float oacc[8][4];
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) oacc[m][i] = 0.f;
+    const int nblk = (len + 15) >> 4;
+    // keys of this lane's k slots {2t, 2t+1, 2t+8, 2t+9}: 16 contiguous dims [16g, 16g+16) of each; the next block's
+    // rows are requested before the current block is expanded (two blocks = 8 loads in flight per lane)
+    auto load_block = [&](int kb, uint4 (&r)[4], float (&pk)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ii = kb * 16 + 2 * t + (i & 1) + 8 * (i >> 1);
+        const bool ok = kb < nblk && ii < len;
+        r[i] = ok ? ldg_nc_v4(vbase + (size_t) (l0 + ii) * kDh + g * 16) : make_uint4(0, 0, 0, 0);
+        pk[i] = ok ? s_s[ii] : 0.f;
+      }
+    };
+    uint4 r[4], rn[4];
+    float pk[4], pkn[4];
+    load_block(warp, r, pk);
+    for (int kb = warp; kb < nblk; kb += kMmhaThreads / 32) {
+      load_block(kb + kMmhaThreads / 32, rn, pkn);
+      const uint32_t b0 = g == 0 ? mmha_pack_h2(pk[0], pk[1]) : 0u, b1 = g == 0 ? mmha_pack_h2(pk[2], pk[3]) : 0u;
+      const uint32_t w0[4] = {r[0].x, r[0].y, r[0].z, r[0].w}, w1[4] = {r[1].x, r[1].y, r[1].z, r[1].w};
+      const uint32_t w2[4] = {r[2].x, r[2].y, r[2].z, r[2].w}, w3[4] = {r[3].x, r[3].y, r[3].z, r[3].w};
+      // word w holds dims 4w..4w+3 (rows g of MMAs 4w..4w+3), word w + 2 dims 8+4w.. (rows g + 8 of the same MMAs)
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        // e01[x][d] / e23[x][d]: half2 {V[k_even][dim], V[k_odd][dim]}, x = 0: dim 16g + 4w + d, x = 1: dim 16g + 8 + 4w + d
+        uint32_t e01[2][4], e23[2][4];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const int ww = w + 2 * x;
+          uint32_t ga, gb;
+          __half2 x0, x1;
+          asm("prmt.b32 %0, %1, %2, 0x5140;" : "=r"(ga) : "r"(w0[ww]), "r"(w1[ww]));   // {k0.b0, k1.b0, k0.b1, k1.b1}
+          asm("prmt.b32 %0, %1, %2, 0x7362;" : "=r"(gb) : "r"(w0[ww]), "r"(w1[ww]));   // {k0.b2, k1.b2, k0.b3, k1.b3}
+          i8x4_to_h2x2(ga, x0, x1); e01[x][0] = mmha_h2u(x0); e01[x][1] = mmha_h2u(x1);
+          i8x4_to_h2x2(gb, x0, x1); e01[x][2] = mmha_h2u(x0); e01[x][3] = mmha_h2u(x1);
+          asm("prmt.b32 %0, %1, %2, 0x5140;" : "=r"(ga) : "r"(w2[ww]), "r"(w3[ww]));
+          asm("prmt.b32 %0, %1, %2, 0x7362;" : "=r"(gb) : "r"(w2[ww]), "r"(w3[ww]));
+          i8x4_to_h2x2(ga, x0, x1); e23[x][0] = mmha_h2u(x0); e23[x][1] = mmha_h2u(x1);
+          i8x4_to_h2x2(gb, x0, x1); e23[x][2] = mmha_h2u(x0); e23[x][3] = mmha_h2u(x1);
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) mmha_mma_f16(oacc[4 * w + d], e01[0][d], e01[1][d], e23[0][d], e23[1][d], b0, b1);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { r[i] = rn[i]; pk[i] = pkn[i]; }
+    }
+    // column 0 (lanes t == 0): oacc[m][0] = dim 16g + m, oacc[m][2] = dim 16g + 8 + m; one partial row per warp
+    if (t == 0) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        o_red[warp * kDh + 16 * g + m] = oacc[m][0] * kv_dq;
+        o_red[warp * kDh + 16 * g + 8 + m] = oacc[m][2] * kv_dq;
+      }
+    }
+  } else {
   float acc[DPL];
 #pragma unroll
   for (int j = 0; j < DPL; ++j) acc[j] = 0.f;
@@ -277,13 +419,15 @@ __global__ void __launch_bounds__(kMmhaThreads, INT8 ? 0 : 4) mmha_decode_kernel
   }
 #pragma unroll
   for (int j = 0; j < DPL; ++j) o_red[grp * kDh + gl * DPL + j] = acc[j] * kv_dq;
+  }
   __syncthreads();
+  constexpr int NRED = MMA ? kMmhaThreads / 32 : KPI;    // partial output rows in o_red
 
   if (nsplit == 1) {
     if (tid < kDh) {
       float o = 0.f;
 #pragma unroll 8
-      for (int g = 0; g < KPI; ++g) o += o_red[g * kDh + tid];
+      for (int g = 0; g < NRED; ++g) o += o_red[g * kDh + tid];
       if (has_cur) o = fmaf(s_s[len], __half2float(vcur_s[tid]), o);
       p.out[(size_t) b * hidden + h * kDh + tid] = __float2half_rn(o);
     }
@@ -296,7 +440,7 @@ __global__ void __launch_bounds__(kMmhaThreads, INT8 ? 0 : 4) mmha_decode_kernel
   if (tid < kDh) {
     float o = 0.f;
 #pragma unroll 8
-    for (int g = 0; g < KPI; ++g) o += o_red[g * kDh + tid];
+    for (int g = 0; g < NRED; ++g) o += o_red[g * kDh + tid];
     if (has_cur) o = fmaf(s_s[len], __half2float(vcur_s[tid]), o);
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&c_o[split][tid])), "r"(0));
@@ -365,6 +509,13 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
   p.partial = reinterpret_cast<float*>(workspace);
   p.past_len = past_len; p.max_input_len = max_input_len; p.S_max = max_seq_len; p.H = num_heads;
   p.rotary_dim = rotary_dim; p.inv_sqrt_dh = 1.f / (sqrtf((float) head_size) * q_scaling);
+  // int8 caches with long contexts: tensor-core loops, two CTAs per SM, so no more splits than fit one wave
+  static const int mma_env = getenv("TB_MMHA_MMA") ? atoi(getenv("TB_MMHA_MMA")) : -1;   // A/B switch: 0 off, 1 always
+  const bool use_mma = int8_kv && (mma_env == 1 || (mma_env != 0 && len_cap >= 512));
+  if (use_mma) {
+    const int fit = (2 * kNumSMs) / (batch * num_heads);
+    if (nsplit > fit) nsplit = fit < 1 ? 1 : fit;
+  }
   // shared memory sized for the longest possible split (len_cap = upper bound on any tlength)
   const int kpi = int8_kv ? KvTraits<true>::kKeysPerIter : KvTraits<false>::kKeysPerIter;
   int chunk = (len_cap + nsplit - 1) / nsplit;
@@ -383,6 +534,10 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
   attr[0].val.clusterDim.z = nsplit;
   cfg.attrs = attr;
   cfg.numAttrs = nsplit > 1 ? 1 : 0;
+  if (use_mma) {
+    if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<true, true>, p);
+  }
   if (int8_kv) {
     if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<true>, p);
