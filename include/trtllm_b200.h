@@ -100,8 +100,8 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
                    tb_stream_t stream);
 /* context phase: replaces GPTAttentionPluginCommon::enqueueContext (gptAttentionCommon.cpp:361-620).
  * qkv [B,S,3*H*Dh] fp16 is rotated in place (q,k), out [B,S,H*Dh].
- * workspace: tb_context_attention_workspace_bytes() of scratch (V^T) selects the tcgen05 kernel; NULL selects the
- * workspace-free warp-MMA kernel.                                                                   */
+ * workspace: non-NULL (tb_context_attention_workspace_bytes(), a nominal 256 bytes since V is consumed in place as an
+ * MN-major tcgen05 operand) selects the tcgen05 kernel; NULL selects the older warp-MMA kernel.       */
 size_t tb_context_attention_workspace_bytes(int batch, int seq_len, int num_heads);
 int tb_context_attention(void* out, void* qkv, void* kv_cache, const int* input_lengths,
                          const float* kv_scale_orig_quant, void* workspace, int batch, int seq_len, int num_heads,

@@ -5,19 +5,22 @@
 // B = 8, S = 2048) and this repo's own round-1 warp-MMA flash kernel (context_attn.cu, 79 TFLOP/s).
 //
 // One CTA = 128 query rows of one (batch, head); it walks the key/value tiles 0..diag (causal) of 128 keys:
-//   warp 0      TMA producer: Q tile once, then K_j and V^T_j tiles into a 2-stage ring (128B-swizzled K-major boxes)
+//   warp 0      TMA producer: Q tile once, then K_j and V_j tiles into a 2-stage ring (128B-swizzled boxes)
 //   warp 1      tcgen05.mma issuer (one lane): S_j = Q.K_j^T into TMEM (double-buffered), O += P_j.V_j into TMEM;
 //               S_{j+1} is issued before P_j is awaited, so the softmax of tile j overlaps the QK^T of tile j+1
 //   warps 2-5   softmax: TMEM lane = query row, so a thread owns a whole row — row max / sum need no shuffles.  Online
 //               softmax in fp32 (log2 domain) on the score row held in registers; P_j is written as fp16 into a
 //               128B-swizzled shared tile (the A operand of P.V).  O accumulates in TMEM across tiles relative to a stale
 //               running maximum and is rescaled in place (tcgen05.ld / st) only when a row of the warp beats it by 2^8.
-// V is needed as a K-major B operand [Dh x keys]; the activations hold it as [keys x Dh], so a small transpose kernel
-// writes V^T [B, H, Dh, S] into the caller's workspace first (2 * B*S*hidden bytes, ~45 us at cfg4 sizes).
+// V is consumed as stored: [keys, Dh] with Dh contiguous is an MN-major B operand of P.V (instruction-descriptor bit 16;
+// 128-byte rows of 64 dims, 8 keys per 1024-byte swizzle atom = SBO, the second 64 dims 8 KB further = LBO, a k-step of
+// 16 keys = 2048 bytes), so the K and V tiles come from the same qkv tensor map and no transposed copy is made (the
+// first version wrote V^T through a 93 us transpose kernel and a 2 * B*S*hidden workspace).
 // Numerics: s = qk * scale with causal + length masking, p = exp(s - running max) rounded to fp16 for P.V (the reference
 // rounds its normalised p to fp16 too, K/unfusedAttentionKernels.cu:180-257), normalisation 1/(sum + 1e-6) at the end.
 // Bound: fp16 tensor pipe; algorithmic flops = 4 * Dh * (causal pairs) per head.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "tmap_host.h"
@@ -32,7 +35,7 @@ constexpr int kASub = kATile * 128;      // bytes of one [128 rows x 64 halfs] s
 constexpr int kATileBytes = 2 * kASub;   // a [128 x 128] fp16 operand tile = two sub-tiles along K (Q)
 constexpr int kAKSub = kAKeys * 128;     // K sub-tile [64 keys x 64 halfs] (8 KB); a K stage is two of them
 constexpr int kAKBytes = 2 * kAKSub;     // 16 KB
-constexpr int kAVBytes = kASub;          // V^T stage [128 dims x 64 keys] = one sub-tile (16 KB)
+constexpr int kAVBytes = 2 * kAKSub;      // V stage [64 keys x 128 dims] = two sub-tiles of 64 dims (16 KB)
 constexpr int kAPBytes = kASub;          // P tile [128 rows x 64 keys] = one sub-tile (16 KB)
 constexpr int kATmemCols = 256;          // S double buffer 2 x 64 + O 128
 constexpr int kAThreads = 192;
@@ -44,35 +47,13 @@ struct FlashTcParams {
   float qk_scale;
 };
 
-// [S, Dh] -> [Dh, S_pad] per (b, h): classic 32x32 shared-memory transpose
-__global__ void __launch_bounds__(256) vt_transpose_kernel(const __half* __restrict__ qkv, __half* __restrict__ vt, int S,
-                                                           int S_pad, int H) {
-  __shared__ __half tile[32][34];
-  const int b = blockIdx.z, h = blockIdx.y / (kAD / 32), dblk = blockIdx.y % (kAD / 32), s0 = blockIdx.x * 32;
-  const int hidden = H * kAD;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const __half* src = qkv + (size_t) b * S * 3 * hidden + 2 * hidden + (size_t) h * kAD + dblk * 32;
-#pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int s = s0 + r;
-    tile[r][tx] = s < S ? src[(size_t) s * 3 * hidden + tx] : __float2half_rn(0.f);
-  }
-  __syncthreads();
-  __half* dst = vt + ((size_t) (b * H + h) * kAD + dblk * 32) * S_pad;
-#pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int s = s0 + tx;
-    if (s < S_pad) dst[(size_t) r * S_pad + s] = tile[tx][r];
-  }
-}
-
 __global__ void __launch_bounds__(kAThreads, 2)
 flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_k,
-                    const __grid_constant__ CUtensorMap tmap_vt, const FlashTcParams p) {
+                    const FlashTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];   // (no alignment slack: 2 CTAs x 113.25 KB just fit an SM)
   uint8_t* sQ = smem;                              // 32 KB
   uint8_t* sK = sQ + kATileBytes;                  // 2 stages x 16 KB
-  uint8_t* sV = sK + 2 * kAKBytes;                 // 2 stages x 16 KB   (V^T tile: [Dh rows x keys])
+  uint8_t* sV = sK + 2 * kAKBytes;                 // 2 stages x 16 KB   (V tile as stored: [keys x Dh])
   uint8_t* sP = sV + 2 * kAVBytes;                 // 16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kAPBytes);
   uint64_t* q_full = bars;          // [1]
@@ -104,7 +85,6 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_vt);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -139,7 +119,10 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         for (int kb = 0; kb < 2; ++kb)
           tma_load_2d(sK + st * kAKBytes + kb * kAKSub, &tmap_k, &kv_full[st], hidden + h * kAD + kb * 64,
                       b * p.S + j * kAKeys);
-        tma_load_2d(sV + st * kAVBytes, &tmap_vt, &kv_full[st], j * kAKeys, (b * p.H + h) * kAD);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)      // V: [64 keys x 64 dims] sub-tiles, dims 0-63 then 64-127
+          tma_load_2d(sV + st * kAVBytes + kb * kAKSub, &tmap_k, &kv_full[st], 2 * hidden + h * kAD + kb * 64,
+                      b * p.S + j * kAKeys);
       }
     }
   } else if (warp == 1) {
@@ -168,9 +151,16 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         mbar_wait(p_full, j & 1);                   // P_j is in shared memory, S_j has been read, O rescaled if needed
         tc_fence_after();
         const uint64_t ad = umma_desc_sw128(smem_u32(sP));
-        const uint64_t bd = umma_desc_sw128(smem_u32(sV + st * kAVBytes));
+        // V tile as an MN-major B operand (see the header): LBO = sub-tile stride along dims, SBO = 8-key atom stride
+        uint64_t bd = 0;
+        bd |= (uint64_t) ((smem_u32(sV + st * kAVBytes) & 0x3FFFFu) >> 4);
+        bd |= (uint64_t) (kAKSub >> 4) << 16;
+        bd |= (uint64_t) (1024 >> 4) << 32;
+        bd |= (uint64_t) 1 << 46;
+        bd |= (uint64_t) 2 << 61;
+        constexpr uint32_t idesc_o_mn = idesc_o | (1u << 16);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_O, ad + 2 * k, bd + 2 * k, idesc_o, (j | k) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_O, ad + 2 * k, bd + (uint64_t) (k * (2048 >> 4)), idesc_o_mn, (j | k) ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
       }
@@ -301,22 +291,16 @@ flash_ctx_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, kATmemCols);
 }
 
-// launched after ctx_prep_kernel (RoPE in place, KV-cache write): transpose V, then the fused attention
+// launched after ctx_prep_kernel (RoPE in place, KV-cache write)
 int launch_flash_ctx_tc(void* out, const void* qkv, void* workspace, const int* input_lengths, int batch, int seq_len,
                         int num_heads, float qk_scale, cudaStream_t stream) {
+  (void) workspace;   // kept in the signature: no scratch is needed any more
   const int hidden = num_heads * kAD;
-  const int S_pad = (seq_len + 7) & ~7;
-  __half* vt = static_cast<__half*>(workspace);
-  vt_transpose_kernel<<<dim3((S_pad + 31) / 32, num_heads * (kAD / 32), batch), 256, 0, stream>>>(
-      static_cast<const __half*>(qkv), vt, seq_len, S_pad, num_heads);
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk;
   int rc = make_tmap(&tq, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t) batch * seq_len, (uint64_t) 3 * hidden, kATile, 64,
                      CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   rc = make_tmap(&tk, qkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t) batch * seq_len, (uint64_t) 3 * hidden, kAKeys, 64,
-                 CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  rc = make_tmap(&tv, vt, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t) batch * num_heads * kAD, (uint64_t) S_pad, kATile, 64,
                  CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const size_t smem = (size_t) kATileBytes + 2 * kAKBytes + 2 * kAVBytes + kAPBytes + 256;
@@ -327,13 +311,14 @@ int launch_flash_ctx_tc(void* out, const void* qkv, void* workspace, const int* 
   }
   FlashTcParams p{static_cast<__half*>(out), input_lengths, seq_len, num_heads, qk_scale};
   dim3 grid((seq_len + kATile - 1) / kATile, num_heads, batch);
-  flash_ctx_tc_kernel<<<grid, kAThreads, smem, stream>>>(tq, tk, tv, p);
+  flash_ctx_tc_kernel<<<grid, kAThreads, smem, stream>>>(tq, tk, p);
   return (int) cudaGetLastError();
 }
 
+// (a non-NULL workspace still selects this kernel in tb_context_attention; its size is nominal now)
 size_t flash_ctx_tc_workspace_bytes(int batch, int seq_len, int num_heads) {
-  const size_t S_pad = (size_t) ((seq_len + 7) & ~7);
-  return (size_t) batch * num_heads * kAD * S_pad * sizeof(__half) + 256;
+  (void) batch; (void) seq_len; (void) num_heads;
+  return 256;
 }
 
 }  // namespace tb
