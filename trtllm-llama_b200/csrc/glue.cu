@@ -75,9 +75,34 @@ __global__ void __launch_bounds__(1024) argmax_kernel(int* out, const float* log
   const float* row = logits + (size_t) blockIdx.x * vocab_stride;
   float bv = -3.4e38f;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
-    const float v = row[i];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  if ((vocab & 3) == 0 && (vocab_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    // 8 independent 16-byte loads per thread per pass: one memory round trip for a 32k vocabulary instead of a chain
+    // of 32 scalar loads (17 us -> a few us per decode step)
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int n4 = vocab >> 2;
+    for (int base = 0; base < n4; base += 8 * blockDim.x) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i4 = base + u * blockDim.x + threadIdx.x;
+        v[u] = i4 < n4 ? row4[i4] : make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i4 = base + u * blockDim.x + threadIdx.x, i = i4 * 4;
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        if (i4 < n4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (e[j] > bv || (e[j] == bv && i + j < bi)) { bv = e[j]; bi = i + j; }
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+      const float v = row[i];
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
