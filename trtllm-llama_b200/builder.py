@@ -108,27 +108,67 @@ def random_llama_weights(mc: ModelConfig, seed=0, device="cuda"):
 
 
 def load_from_ft_llama(model_dir: str, mc: ModelConfig, device="cuda"):
-    """FT-format fp16 checkpoint written by LQ/hf_llama_convert.py (file names of LQ/weight_quant.py:172-437, the
-    unsharded ``.0.bin`` / ``.bin`` variants; [in, out] matrices are transposed to this library's [out, in])."""
-    def ff(name, shape=None):
+    """FT-format checkpoint written by ``examples/llama_quant/hf_llama_convert.py`` (file names of
+    LQ/weight_quant.py:172-446; unsharded ``.bin`` / ``.0.bin`` variants; [in, out] matrices are transposed to this
+    library's [out, in]).  Besides the fp16 weights it picks up, when present,
+
+      * ``attention.query_key_value.scale_y_quant_orig.bin`` -> per-layer ``kv_scale`` (int8 KV cache,
+        LQ/weight_quant.py:439-446: kv_quant_orig_scale = t, kv_orig_quant_scale = 1 / t)
+      * for a SmoothQuant per-channel ModelConfig the converter's ``.weight.int8.col.0.bin`` + ``scale_w_quant_orig.col``
+        (LQ/weight_quant.py:116-147,239-262) -> per-layer ``sq`` = {name: (int8 [out, in], fp32 scale [out])}, which
+        ``build_engine_tensors`` uses instead of re-quantising the fp16 weights."""
+    def raw(name, dtype, shape=None, required=True):
         p = os.path.join(model_dir, name)
         if not os.path.exists(p):
-            raise FileNotFoundError(p)
-        a = np.fromfile(p, dtype=np.float16)
+            if required:
+                raise FileNotFoundError(p)
+            return None
+        a = np.fromfile(p, dtype=dtype)
         return torch.from_numpy(a.reshape(shape) if shape else a).to(device)
+
+    def ff(name, shape=None):
+        return raw(name, np.float16, shape)
+
+    def first(names, shape):
+        for n in names:
+            t = raw(n, np.float16, shape, required=False)
+            if t is not None:
+                return t
+        raise FileNotFoundError(os.path.join(model_dir, names[0]))
+
     hid, inter = mc.hidden_size, mc.inter_size
+    want_sq = mc.quant_mode.has_act_and_weight_quant() and mc.quant_mode.has_per_channel_scaling()
     w = {"vocab_embedding": ff("model.wte.weight.bin", [mc.vocab_size, hid]), "ln_f": ff("model.final_layernorm.weight.bin"),
          "lm_head": ff("model.lm_head.weight.bin", [mc.vocab_size, hid]), "layers": []}
     for i in range(mc.num_layers):
         p = f"model.model.layers.{i}."
-        w["layers"].append({
+        qkv_base = p + "attention.query_key_value."
+        lw = {
             "input_layernorm": ff(p + "input_layernorm.weight.bin"),
-            "qkv": ff(p + "attention.query_key_value.weight.0.bin", [hid, 3 * hid]).t().contiguous(),
+            # the converter writes QKV whole as ``.weight.bin`` ([in, 3, out/3]); older trees have ``.weight.0.bin``
+            "qkv": first([qkv_base + "weight.bin", qkv_base + "weight.0.bin"], [hid, 3 * hid]).t().contiguous(),
             "dense": ff(p + "attention.dense.weight.0.bin", [hid, hid]).t().contiguous(),
             "post_layernorm": ff(p + "post_attention_layernorm.weight.bin"),
             "gate": ff(p + "mlp.gate_proj.weight.0.bin", [hid, inter]).t().contiguous(),
             "up": ff(p + "mlp.up_proj.weight.0.bin", [hid, inter]).t().contiguous(),
-            "down": ff(p + "mlp.down_proj.weight.0.bin", [inter, hid]).t().contiguous()})
+            "down": ff(p + "mlp.down_proj.weight.0.bin", [inter, hid]).t().contiguous()}
+        kv = raw(qkv_base + "scale_y_quant_orig.bin", np.float32, required=False)
+        if kv is not None:
+            lw["kv_scale"] = float(kv.reshape(-1)[0])
+        if want_sq:
+            sq = {}
+            for name, base, k_in, n_out, col_suffix in (("qkv", qkv_base, hid, 3 * hid, "col.0.bin"),
+                                                        ("dense", p + "attention.dense.", hid, hid, "col.bin"),
+                                                        ("gate", p + "mlp.gate_proj.", hid, inter, "col.0.bin"),
+                                                        ("up", p + "mlp.up_proj.", hid, inter, "col.0.bin"),
+                                                        ("down", p + "mlp.down_proj.", inter, hid, "col.bin")):
+                q = raw(base + "weight.int8.col.0.bin", np.int8, [k_in, n_out], required=False)
+                sc = raw(base + "scale_w_quant_orig." + col_suffix, np.float32, [n_out], required=False)
+                if q is not None and sc is not None:
+                    sq[name] = (q.t().contiguous(), sc.contiguous())
+            if len(sq) == 5:
+                lw["sq"] = sq
+        w["layers"].append(lw)
     return w
 
 

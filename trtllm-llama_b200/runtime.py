@@ -88,6 +88,8 @@ def shard_weights(w, tp_size, rank, num_heads):
              "gate": lw["gate"].chunk(tp_size, dim=0)[rank].contiguous(),
              "up": lw["up"].chunk(tp_size, dim=0)[rank].contiguous(),
              "down": lw["down"].chunk(tp_size, dim=1)[rank].contiguous()}
+        if "kv_scale" in lw:
+            e["kv_scale"] = lw["kv_scale"]
         out["layers"].append(e)
     return out
 
@@ -117,11 +119,19 @@ def build_engine_tensors(w, cfg: ModelConfig, kv_scale: float = 4.0 / 127.0):
         # fc = gate_proj, gate = up_proj (LQ/weight_quant.py:343-404); fused as one [2*inter, K] projection
         named = {"attention.qkv": lw["qkv"], "attention.dense": lw["dense"],
                  "mlp.fc_gate": torch.cat([lw["gate"], lw["up"]], dim=0), "mlp.proj": lw["down"]}
+        pre_q = lw.get("sq") if mode == MODE_SQ else None   # converter-made int8 weights + per-channel scales
         for name, wt in named.items():
+            if pre_q is not None:
+                parts = {"attention.qkv": ["qkv"], "attention.dense": ["dense"], "mlp.fc_gate": ["gate", "up"],
+                         "mlp.proj": ["down"]}[name]
+                t[p + name + ".weight"] = torch.cat([pre_q[n][0] for n in parts], dim=0)
+                t[p + name + ".per_channel_scale"] = torch.cat([pre_q[n][1] for n in parts], dim=0)
+                continue
             for k, v in quantize_linear(wt, mode).items():
                 t[p + name + "." + k] = v
         if cfg.quant_mode.has_int8_kv_cache():
             dev = lw["qkv"].device
+            kv_scale = lw.get("kv_scale", kv_scale)
             # LQ/weight_quant.py:439-446: kv_orig_quant_scale = 1/t, kv_quant_orig_scale = t
             t[p + "attention.kv_orig_quant_scale"] = torch.tensor([1.0 / kv_scale], dtype=torch.float32, device=dev)
             t[p + "attention.kv_quant_orig_scale"] = torch.tensor([kv_scale], dtype=torch.float32, device=dev)
