@@ -358,3 +358,13 @@ def test_product_path_fails_loudly_without_gpu():
     assert _lib.load_library().tb_check_device() != 0
     with pytest.raises(RuntimeError):
         rt.GenerationSession(rt.ModelConfig(), {})
+
+
+def test_pad_finished_after_end_id():
+    """GenerationSession.decode(..., sampling_config): positions after a sequence's first end_id hold end_id."""
+    import torch
+    import trtllm_llama_b200  # noqa: F401
+    from trtllm_llama_b200.runtime import pad_finished
+    ids = torch.tensor([[5, 2, 7, 8, 2, 9], [4, 6, 8, 1, 3, 5], [2, 9, 9, 9, 9, 9], [7, 7, 7, 7, 7, 2]], dtype=torch.int32)
+    got = pad_finished(ids.clone(), 2)
+    assert got.tolist() == [[5, 2, 2, 2, 2, 2], [4, 6, 8, 1, 3, 5], [2, 2, 2, 2, 2, 2], [7, 7, 7, 7, 7, 2]]

@@ -261,7 +261,20 @@ class GenerationSession:
         if lib.tbrt_generate(self._e, input_ids.data_ptr(), lens.data_ptr(), B, S, n, out.data_ptr(), self._stream()):
             raise _err("tbrt_generate")
         self._B = B
+        if sampling_config is not None and sampling_config.end_id is not None:
+            pad_finished(out, sampling_config.end_id)
         return out
+
+
+def pad_finished(output_ids: torch.Tensor, end_id: int) -> torch.Tensor:
+    """In place on HOST ids [B, T]: once a sequence has produced ``end_id`` it is finished and every later position holds
+    ``end_id`` — what the reference's decoder leaves in ``output_ids`` (finished sequences are skipped by its sampling
+    kernels and keep emitting ``end_id``, generation.py:782-997).  This engine always runs all T steps (no early stop), so
+    the positions after the first ``end_id`` are overwritten here; ids up to and including it are untouched."""
+    hit = output_ids == end_id
+    finished_before = (hit.cumsum(dim=1) - hit.to(hit.cumsum(dim=1).dtype)) > 0      # an end_id strictly earlier in the row
+    output_ids[finished_before] = end_id
+    return output_ids
 
 
 def _memcpy_d2d(dst, src, nbytes, stream):
