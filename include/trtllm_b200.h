@@ -121,6 +121,11 @@ int tb_gather_last_token(void* out, const void* in, const int* last_ids, int bat
 int tb_argmax(int* out, const float* logits, int rows, int vocab, int vocab_stride, tb_stream_t s);
 int tb_advance_step(const int* new_ids, int* input_ids, int* output_ids, int* seq_lens, int* step_pos, int batch,
                     int out_stride, tb_stream_t s);
+/* greedy stop criterion (replaces K/stopCriteriaKernels.cu for top_k = 1): *all_done = every sequence of out_ids
+ * [batch, out_stride] has end_id among its first n_done ids; pad != 0 also overwrites the positions after a sequence's
+ * first end_id, up to n_pad, with end_id (the reference's output for finished sequences). all_done may be NULL. */
+int tb_finished(int* all_done, int* out_ids, int batch, int out_stride, int n_done, int n_pad, int end_id, int pad,
+                tb_stream_t s);
 int tb_half_to_float(float* out, const void* in, int64_t n, tb_stream_t s);
 int tb_fill_int(int* p, int value, int n, tb_stream_t s);
 int tb_copy(void* dst, const void* src, size_t bytes, tb_stream_t s); /* device-to-device */

@@ -67,7 +67,9 @@ void* tbrt_kv_cache(const tbrt_engine* e, int layer);
 
 /* Whole request with HOST buffers (pinned for async copies): H2D ids/lengths, context, max_new-1
  * steps, D2H of out_ids [B, max_new]; returns after the stream is synchronised.
- * This is GenerationSession.decode (generation.py:782-997) for greedy sampling without early stop. */
+ * This is GenerationSession.decode (generation.py:782-997) for greedy sampling.  With tbrt_set_end_id(e, id >= 0) the
+ * loop checks every 16 steps whether every sequence has produced end_id and stops early, and finished sequences are
+ * padded with end_id, as the reference's decoder does; id < 0 (default) always runs max_new - 1 steps. */
 int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_lengths, int batch, int seq, int max_new,
                   int32_t* host_out_ids, tb_stream_t s);
 /* Tensor parallel only: peer-memory all-reduce of the decode path (tb_ar_*).  After tbrt_finalize every rank reads its
@@ -75,6 +77,9 @@ int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_l
  * uses the NCCL AllReduce plugin for every message size. */
 int tbrt_ar_handle(tbrt_engine* e, void* out64);
 int tbrt_ar_open(tbrt_engine* e, const void* handles);
+int tbrt_set_end_id(tbrt_engine* e, int end_id);
+/* generation steps (incl. the context phase) the last tbrt_generate actually ran */
+int tbrt_last_steps(const tbrt_engine* e);
 /* kernels launched by the last tbrt_context / tbrt_step / tbrt_generate call */
 int64_t tbrt_last_launches(const tbrt_engine* e);
 

@@ -110,3 +110,37 @@ def test_generate_host_api_matches_stepwise():
     out2 = sess.decode(torch.from_numpy(ids).pin_memory(), torch.from_numpy(lens).pin_memory())
     assert np.array_equal(out2.numpy(), out.numpy())
     assert sess.last_launches > 0
+
+
+def test_decode_stop_criterion_and_end_id_padding():
+    """decode(..., sampling_config): once every sequence has produced end_id the engine stops (checked every 16 steps)
+    and finished sequences are padded with end_id, as the reference's decoder leaves them (generation.py:782-997);
+    ids up to a sequence's first end_id are those of the unconstrained run."""
+    from trtllm_llama_b200.runtime import SamplingConfig, pad_finished
+    cfg = RM.LlamaCfg.tiny(layers=2, hidden=256, inter=384, vocab=512)
+    w = RM.random_weights(cfg, seed=9, std=0.05)
+    B, S, new = 2, 10, 48
+    rng = np.random.default_rng(8)
+    ids, lens = _prompts(rng, cfg, B, S, [S, 7])
+    sess, _ = _session(cfg, w, "fp16", True, B, S, new)
+    sess.setup(B, S, new)
+    host = lambda a: torch.from_numpy(a).pin_memory()   # noqa: E731
+    free = sess.decode(host(ids), host(lens)).numpy().copy()
+    assert sess.last_steps == new
+    # (1) an end_id only row 0 produces early: no early stop (row 1 is not finished), row 0 padded after its first hit
+    e = int(free[0, 3])
+    got = sess.decode(host(ids), host(lens), SamplingConfig(end_id=e, pad_id=e)).numpy()
+    assert np.array_equal(got, pad_finished(torch.from_numpy(free.copy()), e).numpy())
+    if e not in free[1]:
+        assert sess.last_steps == new
+    # (2) single sequence: finished at position 3 -> the check at step 16 stops the loop, the tail is end_id
+    ids1, lens1 = ids[:1].copy(), lens[:1].copy()
+    free1 = sess.decode(host(ids1), host(lens1)).numpy().copy()
+    e1 = int(free1[0, 3])
+    first = int(np.argmax(free1[0] == e1))
+    got1 = sess.decode(host(ids1), host(lens1), SamplingConfig(end_id=e1, pad_id=e1)).numpy()
+    assert np.array_equal(got1[0, :first + 1], free1[0, :first + 1]) and (got1[0, first + 1:] == e1).all()
+    assert sess.last_steps == 16
+    # (3) without a sampling config the engine runs every step again
+    again = sess.decode(host(ids1), host(lens1)).numpy()
+    assert np.array_equal(again, free1) and sess.last_steps == new

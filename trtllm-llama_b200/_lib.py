@@ -121,6 +121,9 @@ SIGNATURES.update({
     "tbrt_kv_cache": (vp, [vp, i32]),
     "tbrt_generate": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
     "tbrt_last_launches": (i64, [vp]),
+    "tbrt_set_end_id": (i32, [vp, i32]),
+    "tbrt_last_steps": (i32, [vp]),
+    "tb_finished": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "tbrt_ar_handle": (i32, [vp, vp]),
     "tbrt_ar_open": (i32, [vp, vp]),
     "tb_ar_create": (i32, [_P(vp), i32, i32, sz]),

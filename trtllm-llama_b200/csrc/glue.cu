@@ -142,6 +142,27 @@ __global__ void advance_step_kernel(const int* new_ids, int* input_ids, int* out
   if (b == 0) *step_pos = pos + 1;
 }
 
+// Stop criterion of greedy decoding (replaces K/stopCriteriaKernels.cu + the `finished` bookkeeping of the dynamic
+// decoder for the greedy case): one thread per sequence scans its generated ids [0, n_done).  *all_done = 1 when every
+// sequence has produced end_id; with pad != 0 every position after a sequence's first end_id, up to n_pad, is
+// overwritten with end_id (what the reference leaves in output_ids for finished sequences).
+__global__ void finished_kernel(int* all_done, int* out_ids, int batch, int out_stride, int n_done, int n_pad, int end_id,
+                                int pad) {
+  const int b = threadIdx.x;
+  int done = 1;
+  if (b < batch) {
+    int* row = out_ids + (size_t) b * out_stride;
+    int first = -1;
+    for (int i = 0; i < n_done; ++i)
+      if (row[i] == end_id) { first = i; break; }
+    done = first >= 0;
+    if (pad && done)
+      for (int i = first + 1; i < n_pad; ++i) row[i] = end_id;
+  }
+  const int all = __syncthreads_and(done);
+  if (threadIdx.x == 0 && all_done) *all_done = all;
+}
+
 __global__ void half_to_float_kernel(float* out, const __half* in, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t) blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x)
     out[i] = __half2float(in[i]);
@@ -212,6 +233,13 @@ int tb_advance_step(const int* new_ids, int* input_ids, int* output_ids, int* se
   if (batch > 1024) return -1;
   advance_step_kernel<<<1, ((batch + 31) / 32) * 32, 0, s>>>(new_ids, input_ids, output_ids, seq_lens, step_pos, batch,
                                                              out_stride);
+  return (int) cudaGetLastError();
+}
+
+int tb_finished(int* all_done, int* out_ids, int batch, int out_stride, int n_done, int n_pad, int end_id, int pad,
+                cudaStream_t s) {
+  if (batch < 1 || batch > 1024 || n_done < 0 || n_pad > out_stride) return -1;
+  finished_kernel<<<1, ((batch + 31) / 32) * 32, 0, s>>>(all_done, out_ids, batch, out_stride, n_done, n_pad, end_id, pad);
   return (int) cudaGetLastError();
 }
 

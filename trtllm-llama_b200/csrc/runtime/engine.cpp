@@ -117,7 +117,10 @@ struct tbrt_engine {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int *d_ids = nullptr, *d_in_lens = nullptr, *d_seq_lens = nullptr, *d_step_pos = nullptr, *d_next = nullptr,
-      *d_out_ids = nullptr, *d_prompt = nullptr;
+      *d_out_ids = nullptr, *d_prompt = nullptr, *d_flag = nullptr;
+  int* h_flag = nullptr;        // pinned
+  int end_id = -1;              // >= 0: greedy stop criterion + end_id padding in tbrt_generate
+  int last_steps = 0;
   float* d_dummy_scale = nullptr;
 
   // session state
@@ -144,6 +147,7 @@ struct tbrt_engine {
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (ar) tb_ar_destroy(ar);
     for (void* p : allocs) cudaFree(p);
+    if (h_flag) cudaFreeHost(h_flag);
   }
 
   int bind();
@@ -600,6 +604,7 @@ int tbrt_finalize(tbrt_engine* e) {
   if (e->alloc(e->d_ids, (size_t) c.max_batch * 4) || e->alloc(e->d_in_lens, (size_t) c.max_batch * 4) ||
       e->alloc(e->d_seq_lens, (size_t) c.max_batch * 4) || e->alloc(e->d_step_pos, 4) ||
       e->alloc(e->d_next, (size_t) c.max_batch * 4) || e->alloc(e->d_out_ids, (size_t) c.max_batch * c.max_output_len * 4) ||
+      e->alloc(e->d_flag, 4) || cudaMallocHost(reinterpret_cast<void**>(&e->h_flag), 4) != cudaSuccess ||
       e->alloc(e->d_prompt, Mmax * 4) || e->alloc(e->d_dummy_scale, 4))
     return -1;
   RT_CUDA(cudaMemset(e->d_dummy_scale, 0, 4));
@@ -612,6 +617,8 @@ int tbrt_finalize(tbrt_engine* e) {
 size_t tbrt_device_bytes(const tbrt_engine* e) { return e->dev_bytes; }
 const float* tbrt_logits(const tbrt_engine* e) { return e->logits; }
 const int32_t* tbrt_output_ids(const tbrt_engine* e) { return e->d_out_ids; }
+int tbrt_set_end_id(tbrt_engine* e, int end_id) { e->end_id = end_id; return 0; }
+int tbrt_last_steps(const tbrt_engine* e) { return e->last_steps; }
 void* tbrt_kv_cache(const tbrt_engine* e, int layer) { return (layer >= 0 && layer < (int) e->kv.size()) ? e->kv[layer] : nullptr; }
 int64_t tbrt_last_launches(const tbrt_engine* e) { return e->launches; }
 int tbrt_ar_handle(tbrt_engine* e, void* out64) {
@@ -690,9 +697,24 @@ int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_l
   RT_CUDA(cudaMemcpyAsync(e->d_next, host_lengths, (size_t) batch * 4, cudaMemcpyHostToDevice, s));
   if (tbrt_context(e, e->d_prompt, e->d_next, batch, seq, st)) return -1;
   int64_t total = e->launches;
+  int steps = 1;
   for (int i = 1; i < max_new; ++i) {
+    if (e->end_id >= 0 && (i % 16) == 0) {
+      // stop criterion: every sequence has produced end_id (checked every 16 steps: one tiny kernel + a 4-byte read)
+      if (tb_finished(e->d_flag, e->d_out_ids, batch, e->c.max_output_len, i, i, e->end_id, 0, s)) return fail("tb_finished");
+      RT_CUDA(cudaMemcpyAsync(e->h_flag, e->d_flag, 4, cudaMemcpyDeviceToHost, s));
+      RT_CUDA(cudaStreamSynchronize(s));
+      total += 1;
+      if (*e->h_flag) break;
+    }
     if (tbrt_step(e, st)) return -1;
     total += e->launches;
+    ++steps;
+  }
+  e->last_steps = steps;
+  if (e->end_id >= 0) {
+    if (tb_finished(nullptr, e->d_out_ids, batch, e->c.max_output_len, steps, max_new, e->end_id, 1, s)) return fail("tb_finished");
+    total += 1;
   }
   RT_CUDA(cudaMemcpy2DAsync(host_out_ids, (size_t) max_new * 4, e->d_out_ids, (size_t) e->c.max_output_len * 4,
                             (size_t) max_new * 4, batch, cudaMemcpyDeviceToHost, s));

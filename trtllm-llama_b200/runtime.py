@@ -258,11 +258,14 @@ class GenerationSession:
         if out is None:
             out = torch.empty((B, n), dtype=torch.int32, pin_memory=True)
         lens = input_lengths.to(dtype=torch.int32).contiguous()
+        # with an explicit sampling config the engine applies the reference's stop criterion: it checks every 16 steps
+        # whether every sequence has produced end_id, stops early, and pads finished sequences with end_id
+        end_id = sampling_config.end_id if (sampling_config is not None and sampling_config.end_id is not None) else -1
+        lib.tbrt_set_end_id(self._e, int(end_id))
         if lib.tbrt_generate(self._e, input_ids.data_ptr(), lens.data_ptr(), B, S, n, out.data_ptr(), self._stream()):
             raise _err("tbrt_generate")
         self._B = B
-        if sampling_config is not None and sampling_config.end_id is not None:
-            pad_finished(out, sampling_config.end_id)
+        self.last_steps = lib.tbrt_last_steps(self._e)
         return out
 
 
