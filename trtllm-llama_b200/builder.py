@@ -136,6 +136,19 @@ def load_from_ft_llama(model_dir: str, mc: ModelConfig, device="cuda"):
                 return t
         raise FileNotFoundError(os.path.join(model_dir, names[0]))
 
+    def pieces(stem, rows, cols, axis):
+        """a matrix the converter wrote as ``<stem>.<r>.bin`` pieces of a <tp>-gpu tree ([in, out], split along ``axis``):
+        every piece present is read and they are joined again, so any tensor-parallel tree loads (sharding for the
+        engine's own tp is redone by ``shard_weights``)"""
+        n = 0
+        while os.path.exists(os.path.join(model_dir, f"{stem}.{n}.bin")):
+            n += 1
+        if n == 0:
+            raise FileNotFoundError(os.path.join(model_dir, f"{stem}.0.bin"))
+        shape = [rows // n, cols] if axis == 0 else [rows, cols // n]
+        parts = [ff(f"{stem}.{r}.bin", shape) for r in range(n)]
+        return parts[0] if n == 1 else torch.cat(parts, dim=axis)
+
     hid, inter = mc.hidden_size, mc.inter_size
     want_sq = mc.quant_mode.has_act_and_weight_quant() and mc.quant_mode.has_per_channel_scaling()
     w = {"vocab_embedding": ff("model.wte.weight.bin", [mc.vocab_size, hid]), "ln_f": ff("model.final_layernorm.weight.bin"),
@@ -147,11 +160,11 @@ def load_from_ft_llama(model_dir: str, mc: ModelConfig, device="cuda"):
             "input_layernorm": ff(p + "input_layernorm.weight.bin"),
             # the converter writes QKV whole as ``.weight.bin`` ([in, 3, out/3]); older trees have ``.weight.0.bin``
             "qkv": first([qkv_base + "weight.bin", qkv_base + "weight.0.bin"], [hid, 3 * hid]).t().contiguous(),
-            "dense": ff(p + "attention.dense.weight.0.bin", [hid, hid]).t().contiguous(),
+            "dense": pieces(p + "attention.dense.weight", hid, hid, 0).t().contiguous(),
             "post_layernorm": ff(p + "post_attention_layernorm.weight.bin"),
-            "gate": ff(p + "mlp.gate_proj.weight.0.bin", [hid, inter]).t().contiguous(),
-            "up": ff(p + "mlp.up_proj.weight.0.bin", [hid, inter]).t().contiguous(),
-            "down": ff(p + "mlp.down_proj.weight.0.bin", [inter, hid]).t().contiguous()}
+            "gate": pieces(p + "mlp.gate_proj.weight", hid, inter, 1).t().contiguous(),
+            "up": pieces(p + "mlp.up_proj.weight", hid, inter, 1).t().contiguous(),
+            "down": pieces(p + "mlp.down_proj.weight", inter, hid, 0).t().contiguous()}
         kv = raw(qkv_base + "scale_y_quant_orig.bin", np.float32, required=False)
         if kv is not None:
             lw["kv_scale"] = float(kv.reshape(-1)[0])
