@@ -368,3 +368,28 @@ def test_pad_finished_after_end_id():
     ids = torch.tensor([[5, 2, 7, 8, 2, 9], [4, 6, 8, 1, 3, 5], [2, 9, 9, 9, 9, 9], [7, 7, 7, 7, 7, 2]], dtype=torch.int32)
     got = pad_finished(ids.clone(), 2)
     assert got.tolist() == [[5, 2, 2, 2, 2, 2], [4, 6, 8, 1, 3, 5], [2, 2, 2, 2, 2, 2], [7, 7, 7, 7, 7, 2]]
+
+
+def test_host_side_sizing_functions():
+    """Host-only entry points of the kernel ABI (no device work): workspace sizing and launch heuristics."""
+    from trtllm_llama_b200 import _lib
+    h = _lib.load_library()
+    # decode rows per kind: tensor-core GEMV takes up to 8 rows when K is a whole number of k-steps, else the FMA kernel's 4
+    for kind in (0, 1, 2, 3):
+        assert h.tb_gemv_max_rows(kind, 4096) == 8 and h.tb_gemv_max_rows(kind, 11008) == 8
+    assert h.tb_gemv_max_rows(0, 136) == 4
+    # GEMM scratch: split-K partials for decode sizes; from 2048 rows on also one weight-only matrix expanded to fp16
+    small = h.tb_gemm_tc_workspace_bytes(8, 4096, 4096)
+    assert 0 < small < 64 << 20
+    for (N, K) in ((12288, 4096), (22016, 4096), (4096, 11008)):
+        assert h.tb_gemm_tc_workspace_bytes(2048, N, K) >= N * K * 2
+        assert h.tb_gemm_tc_workspace_bytes(16384, N, K) >= N * K * 2
+        assert h.tb_gemm_tc_workspace_bytes(128, N, K) < N * K * 2
+    assert h.tb_gemm_tc_counter_bytes() >= 4096 * 4
+    # decode attention: the splits of one (batch, head) form a thread-block cluster (<= 8), >= 64 cached keys each
+    for (b, heads, length) in ((1, 32, 130), (1, 32, 4096), (8, 32, 2048), (64, 32, 2048), (1, 4, 100000)):
+        n = h.tb_mmha_num_splits(b, heads, length, 32)
+        assert 1 <= n <= 8 and (n == 1 or length // n >= 64)
+    assert h.tb_mmha_num_splits(1, 32, 10, 32) == 1
+    # prefill attention consumes V in place: nominal scratch only
+    assert h.tb_context_attention_workspace_bytes(8, 2048, 32) == 256
