@@ -74,7 +74,7 @@ def main():
     weights = (B.load_from_ft_llama(args.model_dir, mc, dev) if args.model_dir
                else B.random_llama_weights(mc, seed=args.random_seed or 0, device=dev))
     for rank in range(args.world_size):
-        tensors = B.build_rank_engine(weights, mc, rank)
+        tensors = B.build_rank_engine(weights, mc, rank, require_kv_scale=bool(args.model_dir))
         name = B.get_engine_name(MODEL_NAME, args.dtype, args.world_size, rank)
         B.serialize_engine(tensors, os.path.join(args.output_dir, name))
         print(f"[build] serialized {name}: {sum(t.numel() * t.element_size() for t in tensors.values()) / 2**30:.2f} GiB")

@@ -9,12 +9,15 @@ Flags of the reference (LQ/hf_llama_convert.py:27-98) are kept.  Differences, al
     ``--calib-ids file.npy`` (int token ids [samples, seq]) or let the script fall back to seeded random ids (a warning is
     printed: ranges from random ids are only good for plumbing tests).
   * the reference calibrates unconditionally (twice without flags); here only when ``-sq`` or ``-kv`` ask for ranges.
-  * QKV ranges: as in the reference the fused ``attention.query_key_value`` entry repeats q_proj's x / y / w ranges three
-    times (LQ/hf_llama_convert.py:311-323), so the int8 KV scale is q_proj's output range.  ``--kv-range kv`` uses the
-    k_proj / v_proj output ranges for the K and V thirds instead.
+  * QKV ranges: the reference's fused ``attention.query_key_value`` entry repeats q_proj's x / y / w ranges three
+    times (LQ/hf_llama_convert.py:311-323), so its int8 KV scale is q_proj's output range (``--kv-range q``, kept for
+    parity checks).  The default ``--kv-range kv`` takes the K and V thirds from k_proj / v_proj and leaves q_proj's
+    output OUT of the y range, so ``scale_y_quant_orig`` — the int8 KV-cache scale — is max(|K|, |V|) / 127.
   * ``-sq``: the reference computes its smoothers on temporary copies, rescales the recorded ranges and writes the
-    UNsmoothed weights (LQ/hf_llama_convert.py:106-227).  ``--smooth-mode reference`` (default) reproduces exactly that
-    bookkeeping; ``--smooth-mode folded`` writes smoothed q/k/v and gate/up weights and folds 1/s into the two norms
+    UNsmoothed weights (LQ/hf_llama_convert.py:106-227): the written int8 columns are clipped wherever the smoothed
+    range is smaller than the real one and ``scale_x_orig_quant`` does not match the runtime activations.
+    ``--smooth-mode reference`` reproduces exactly that bookkeeping (parity / debugging only); the default
+    ``--smooth-mode folded`` writes smoothed q/k/v and gate/up weights and folds 1/s into the two norms
     (the mathematically consistent SmoothQuant for the inputs that follow a norm).
   * tensor parallel splits of gate/up are along the output axis (the reference flattens the matrix before splitting,
     which only coincides for ``-tp 1``).
@@ -49,8 +52,8 @@ class ProgArgs:
     calib_ids: str = None
     calib_samples: int = 512
     calib_seq_len: int = 512
-    smooth_mode: str = "reference"
-    kv_range: str = "q"
+    smooth_mode: str = "folded"
+    kv_range: str = "kv"
     device: str = None
 
     @staticmethod
@@ -71,8 +74,11 @@ class ProgArgs:
         p.add_argument("--calib-ids", type=str, default=None, help=".npy of int token ids [samples, seq] (offline calibration)")
         p.add_argument("--calib-samples", type=int, default=512)
         p.add_argument("--calib-seq-len", type=int, default=512)
-        p.add_argument("--smooth-mode", choices=["reference", "folded"], default="reference")
-        p.add_argument("--kv-range", choices=["q", "kv"], default="q")
+        p.add_argument("--smooth-mode", choices=["reference", "folded"], default="folded",
+                       help="folded (default): write smoothed weights, fold 1/s into the norms; reference: the upstream "
+                            "script's bookkeeping (lossy; parity/debug only)")
+        p.add_argument("--kv-range", choices=["q", "kv"], default="kv",
+                       help="kv (default): int8 KV scale from the k_proj / v_proj output ranges; q: q_proj's (upstream)")
         p.add_argument("--device", type=str, default=None, help="cuda / cpu (default: cuda when available)")
         ns = p.parse_args(args)
         if ns.smoothquant is not None and not 0.0 <= ns.smoothquant <= 1.0:
@@ -106,7 +112,8 @@ def _fused_ranges(act_range, num_layers, kv_range):
         parts = {"x": [q["x"]] * 3, "y": [q["y"]] * 3, "w": [q["w"]] * 3}
         if kv_range == "kv":
             k, v = act_range[f'model.layers.{l}.self_attn.k_proj'], act_range[f'model.layers.{l}.self_attn.v_proj']
-            parts["y"] = [q["y"], k["y"], v["y"]]
+            # generate_int8 reduces y with one max() over Q|K|V: keep q_proj's output out of it
+            parts["y"] = [torch.zeros_like(q["y"]), k["y"], v["y"]]
         act_range[f'model.layers.{l}.attention.query_key_value'] = {n: torch.cat(p, dim=-1) for n, p in parts.items()}
         o = act_range[f'model.layers.{l}.self_attn.o_proj']
         act_range[f'model.layers.{l}.attention.dense'] = {"x": o["x"], "y": o["y"], "w": o["w"]}

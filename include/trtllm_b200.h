@@ -98,6 +98,13 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
                    int past_len,
                    int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv, int nsplit,
                    tb_stream_t stream);
+/* same, with max_input_len read from a device int when max_input_len_dev != NULL (together with seq_lens this leaves
+ * no per-request value in the launch arguments: one captured CUDA graph serves every step of every prompt length). */
+int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
+                       const int* masked_tokens, const int* max_input_len_dev, const float* kv_scale_orig_quant,
+                       const float* kv_scale_quant_orig, void* workspace, int* counters, int batch, int num_heads,
+                       int head_size, int max_seq_len, int past_len, int max_input_len, int len_cap, int rotary_dim,
+                       float q_scaling, int int8_kv, int nsplit, tb_stream_t stream);
 /* context phase: replaces GPTAttentionPluginCommon::enqueueContext (gptAttentionCommon.cpp:361-620).
  * qkv [B,S,3*H*Dh] fp16 is rotated in place (q,k), out [B,S,H*Dh].
  * workspace: non-NULL (tb_context_attention_workspace_bytes(), a nominal 256 bytes since V is consumed in place as an

@@ -144,3 +144,24 @@ def test_decode_stop_criterion_and_end_id_padding():
     # (3) without a sampling config the engine runs every step again
     again = sess.decode(host(ids1), host(lens1)).numpy()
     assert np.array_equal(again, free1) and sess.last_steps == new
+
+
+def test_graph_replay_survives_a_change_of_prompt_length_and_batch():
+    """The captured step graph must not bake the padded prompt length (RoPE positions and the padding mask come from
+    device-resident max_input_len / sequence_length) and growing plugin counters for a larger batch must not invalidate a
+    graph captured at a smaller one: decode at (B, S1), (B, S2), (B2, S1), (B, S1) with graphs == without graphs."""
+    cfg = RM.LlamaCfg.tiny(layers=2, hidden=256, inter=384, vocab=512)
+    w = RM.random_weights(cfg, seed=11, std=0.05)
+    new = 8
+    host = lambda a: torch.from_numpy(a).pin_memory()   # noqa: E731
+    for mode, int8_kv in (("fp16", True), ("sq", False), ("w8", True)):
+        sg, _ = _session(cfg, w, mode, int8_kv, max_batch=4, max_in=16, max_out=new, graph=True)
+        se, _ = _session(cfg, w, mode, int8_kv, max_batch=4, max_in=16, max_out=new, graph=False)
+        rng = np.random.default_rng(12)
+        for B, S, lens in ((2, 16, [16, 9]), (2, 11, [7, 11]), (4, 16, [16, 3, 12, 8]), (2, 16, [16, 9]), (2, 7, [7, 2])):
+            ids, lens = _prompts(rng, cfg, B, S, lens)
+            for s in (sg, se):
+                s.setup(B, S, new)
+            a = sg.decode(host(ids), host(lens)).numpy().copy()
+            b = se.decode(host(ids), host(lens)).numpy().copy()
+            assert np.array_equal(a, b), f"{mode}: graph replay differs from eager at B={B}, S={S}"

@@ -40,6 +40,8 @@ SIGNATURES = {
     "tb_mmha_counter_bytes": (sz, [i32, i32]),
     "tb_mmha_decode": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32,
                              i32, vp]),
+    "tb_mmha_decode_dev": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32,
+                                 i32, i32, vp]),
     "tb_context_attention_workspace_bytes": (sz, [i32, i32, i32]),
     "tb_context_attention": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp]),
     "tb_embedding": (i32, [vp, vp, vp, i32, i32, i32, vp]),

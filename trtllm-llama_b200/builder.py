@@ -170,23 +170,45 @@ def load_from_ft_llama(model_dir: str, mc: ModelConfig, device="cuda"):
             lw["kv_scale"] = float(kv.reshape(-1)[0])
         if want_sq:
             sq = {}
-            for name, base, k_in, n_out, col_suffix in (("qkv", qkv_base, hid, 3 * hid, "col.0.bin"),
-                                                        ("dense", p + "attention.dense.", hid, hid, "col.bin"),
-                                                        ("gate", p + "mlp.gate_proj.", hid, inter, "col.0.bin"),
-                                                        ("up", p + "mlp.up_proj.", hid, inter, "col.0.bin"),
-                                                        ("down", p + "mlp.down_proj.", inter, hid, "col.bin")):
-                q = raw(base + "weight.int8.col.0.bin", np.int8, [k_in, n_out], required=False)
-                sc = raw(base + "scale_w_quant_orig." + col_suffix, np.float32, [n_out], required=False)
+
+            def joined(stem, dtype, full_shape, axis):
+                """``<stem>.<r>.bin`` pieces of a <tp>-gpu tree (split along ``axis`` of ``full_shape``), or the unsplit
+                ``<stem>.bin``; None when neither exists"""
+                n = 0
+                while os.path.exists(os.path.join(model_dir, f"{stem}.{n}.bin")):
+                    n += 1
+                if n == 0:
+                    return raw(f"{stem}.bin", dtype, list(full_shape), required=False)
+                shp = list(full_shape)
+                shp[axis] //= n
+                parts = [raw(f"{stem}.{r}.bin", dtype, shp) for r in range(n)]
+                return parts[0] if n == 1 else torch.cat(parts, dim=axis)
+
+            # (name, file stem, [in, out] view the converter split, split axis, scale shape, scale split axis or None)
+            for name, base, wshape, waxis, sshape, saxis in (
+                    ("qkv", qkv_base, (hid, 3, hid), 2, (3, hid), 1),
+                    ("dense", p + "attention.dense.", (hid, hid), 0, (hid,), None),
+                    ("gate", p + "mlp.gate_proj.", (hid, inter), 1, (inter,), 0),
+                    ("up", p + "mlp.up_proj.", (hid, inter), 1, (inter,), 0),
+                    ("down", p + "mlp.down_proj.", (inter, hid), 0, (hid,), None)):
+                q = joined(base + "weight.int8.col", np.int8, wshape, waxis)
+                if saxis is None:
+                    sc = raw(base + "scale_w_quant_orig.col.bin", np.float32, list(sshape), required=False)
+                else:
+                    sc = joined(base + "scale_w_quant_orig.col", np.float32, sshape, saxis)
                 if q is not None and sc is not None:
-                    sq[name] = (q.t().contiguous(), sc.contiguous())
+                    q = q.reshape(wshape[0], -1)
+                    sq[name] = (q.t().contiguous(), sc.reshape(-1).contiguous())
             if len(sq) == 5:
                 lw["sq"] = sq
         w["layers"].append(lw)
     return w
 
 
-def build_rank_engine(weights, mc: ModelConfig, rank: int, kv_scale=4.0 / 127.0):
-    """LQ/build.py:276-390: shard -> quantise -> processed tensors for one rank."""
+def build_rank_engine(weights, mc: ModelConfig, rank: int, kv_scale=4.0 / 127.0, require_kv_scale=False):
+    """LQ/build.py:276-390: shard -> quantise -> processed tensors for one rank.  ``require_kv_scale``: the weights come
+    from a checkpoint, so an int8 KV cache needs its calibrated per-layer scale (no placeholder)."""
     import dataclasses
     mcr = dataclasses.replace(mc, tp_rank=rank)
-    return build_engine_tensors(shard_weights(weights, mc.tp_size, rank, mc.num_heads), mcr, kv_scale=kv_scale)
+    return build_engine_tensors(shard_weights(weights, mc.tp_size, rank, mc.num_heads), mcr, kv_scale=kv_scale,
+                                require_kv_scale=require_kv_scale)

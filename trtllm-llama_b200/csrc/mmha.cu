@@ -34,6 +34,7 @@ struct MmhaParams {
   const int* seq_lens;       // [B] tlength per sequence (device); nullptr -> past_len for all
   const int* input_lengths;  // [B] real prompt lengths (device); nullptr -> no padding
   const int* masked_tokens;  // [B, S_max] optional
+  const int* max_in_dev;     // optional device int: overrides max_input_len (one captured graph serves any prompt length)
   const float* kv_scale_orig_quant;
   const float* kv_scale_quant_orig;
   float* partial;            // [B*H*nsplit*(Dh+2)] fp32 workspace
@@ -114,8 +115,9 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, hidden = H * kDh;
   const int tlen = p.seq_lens ? p.seq_lens[b] : p.past_len;              // positions [0, tlen) are cached
-  const int in_len = p.input_lengths ? p.input_lengths[b] : p.max_input_len;
-  const int pad = p.max_input_len - in_len;
+  const int max_in = p.max_in_dev ? p.max_in_dev[0] : p.max_input_len;
+  const int in_len = p.input_lengths ? p.input_lengths[b] : max_in;
+  const int pad = max_in - in_len;
   const int pos = tlen - pad;
 
   // balanced split of the cached positions, multiples of KPI
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
               const int ii = k0 + g + 8 * hh;
               if (ii < len) {
                 float d = c[2 * hh] * qk_scale;
-                const bool masked = mrow ? (mrow[l0 + ii] != 0) : (l0 + ii >= in_len && l0 + ii < p.max_input_len);
+                const bool masked = mrow ? (mrow[l0 + ii] != 0) : (l0 + ii >= in_len && l0 + ii < max_in);
                 if (masked) d = -3.0e38f;
                 s_s[ii] = d;
                 lmax = fmaxf(lmax, d);
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
       for (int o = LPK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
       if (ii < len && gl == 0) {
         d *= qk_scale;
-        const bool masked = mrow ? (mrow[l0 + ii] != 0) : (l0 + ii >= in_len && l0 + ii < p.max_input_len);
+        const bool masked = mrow ? (mrow[l0 + ii] != 0) : (l0 + ii >= in_len && l0 + ii < max_in);
         if (masked) d = -3.0e38f;
         s_s[ii] = d;
         lmax = fmaxf(lmax, d);
@@ -494,6 +496,16 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
                    void* workspace, int* counters, int batch, int num_heads, int head_size, int max_seq_len, int past_len,
                    int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv, int nsplit,
                    cudaStream_t stream) {
+  return tb_mmha_decode_dev(out, qkv, kv_cache, seq_lens, input_lengths, masked_tokens, nullptr, kv_scale_orig_quant,
+                            kv_scale_quant_orig, workspace, counters, batch, num_heads, head_size, max_seq_len, past_len,
+                            max_input_len, len_cap, rotary_dim, q_scaling, int8_kv, nsplit, stream);
+}
+
+int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
+                       const int* masked_tokens, const int* max_input_len_dev, const float* kv_scale_orig_quant,
+                       const float* kv_scale_quant_orig, void* workspace, int* counters, int batch, int num_heads,
+                       int head_size, int max_seq_len, int past_len, int max_input_len, int len_cap, int rotary_dim,
+                       float q_scaling, int int8_kv, int nsplit, cudaStream_t stream) {
   if (head_size != kDh) return -1;                 // LLaMA-7B head size; other sizes are not built
   if (rotary_dim != 0 && rotary_dim != kDh) return -1;
   if (past_len + 1 > max_seq_len || len_cap + 1 > max_seq_len + 1) return -2;
@@ -503,7 +515,7 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
   (void) workspace; (void) counters;   // kept in the ABI: split partials now live in distributed shared memory
   MmhaParams p{};
   p.qkv = (const __half*) qkv; p.kv_cache = kv_cache; p.out = (__half*) out; p.seq_lens = seq_lens;
-  p.input_lengths = input_lengths; p.masked_tokens = masked_tokens;
+  p.input_lengths = input_lengths; p.masked_tokens = masked_tokens; p.max_in_dev = max_input_len_dev;
   p.kv_scale_orig_quant = kv_scale_orig_quant; p.kv_scale_quant_orig = kv_scale_quant_orig;
   p.counters = counters;
   p.partial = reinterpret_cast<float*>(workspace);

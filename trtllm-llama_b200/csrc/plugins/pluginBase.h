@@ -138,6 +138,7 @@ class DeviceCounters {
  private:
   void* ptr_ = nullptr;
   size_t bytes_ = 0;
+  std::vector<void*> retired_;   // outgrown buffers, kept alive for graphs captured with them
 };
 
 // ---- base plugin -----------------------------------------------------------------------------------------

@@ -88,9 +88,7 @@ class GPTAttentionPlugin : public BasePlugin {
     w.put(ifb_); w.put(device_lengths_);
   }
   GPTAttentionPlugin* clone() const noexcept override {
-    auto* p = new GPTAttentionPlugin(*this);
-    p->counters_ = DeviceCounters();   // a clone owns its own counters (the reference clone re-initialises too)
-    return p;
+    return new GPTAttentionPlugin(*this);
   }
   const char* getPluginType() const noexcept override { return type_name(); }
   int32_t getNbOutputs() const noexcept override { return 2; }
@@ -136,11 +134,14 @@ class GPTAttentionPlugin : public BasePlugin {
       // captured CUDA graph serves every step; shared memory is then sized for S_max.
       const int cap = device_lengths_ ? S_max - 1 : past_len;
       const int nsplit = tb_mmha_num_splits(B, num_heads_, cap, kMaxSplits);
-      int* cnt = counters_.get(tb_mmha_counter_bytes(B, num_heads_));
-      return tb_mmha_decode(out[0], in[0], cache, static_cast<const int*>(in[2]), static_cast<const int*>(in[5]),
-                            static_cast<const int*>(in[4]), s_oq, s_qo, workspace, cnt, B, num_heads_, head_size_, S_max,
-                            device_lengths_ ? 0 : past_len, max_in, cap, rotary_dim_, q_scaling_, int8_kv_, nsplit,
-                            stream);
+      // device_lengths [ext]: a non-NULL input 6 then holds max_input_length as ONE device int (the reference only uses
+      // its shape), so no per-request value is baked into a captured launch.  Split partials live in distributed
+      // shared memory: the kernel needs no counters.
+      const int* max_in_dev = device_lengths_ ? static_cast<const int*>(in[6]) : nullptr;
+      return tb_mmha_decode_dev(out[0], in[0], cache, static_cast<const int*>(in[2]), static_cast<const int*>(in[5]),
+                                static_cast<const int*>(in[4]), max_in_dev, s_oq, s_qo, workspace, nullptr, B, num_heads_,
+                                head_size_, S_max, device_lengths_ ? 0 : past_len, max_in, cap, rotary_dim_, q_scaling_,
+                                int8_kv_, nsplit, stream);
     });
   }
 
@@ -160,7 +161,6 @@ class GPTAttentionPlugin : public BasePlugin {
   float q_scaling_ = 1.f;
   bool neox_ = true, multi_block_ = false, multi_query_ = false, int8_kv_ = false, fp8_kv_ = false;
   bool remove_padding_ = false, paged_kv_ = false, ifb_ = false, device_lengths_ = false;
-  DeviceCounters counters_;
 };
 
 // =====================================================================================================

@@ -39,9 +39,12 @@ void Fields::report_unused(const char* plugin) const {
 }
 
 // ---- device counters ------------------------------------------------------------------------------------
+// Growing never frees the smaller buffer: a CUDA graph captured earlier may still hold its address (its kernels
+// keep using the old, still valid, self-resetting counters); everything is freed when the plugin is destroyed.
 int* DeviceCounters::get(size_t bytes) {
   if (ptr_ && bytes_ >= bytes) return static_cast<int*>(ptr_);
-  release();
+  if (ptr_) retired_.push_back(ptr_);
+  ptr_ = nullptr;
   if (cudaMalloc(&ptr_, bytes) != cudaSuccess) throw PluginError("cudaMalloc of plugin counters failed");
   if (cudaMemset(ptr_, 0, bytes) != cudaSuccess) throw PluginError("cudaMemset of plugin counters failed");
   bytes_ = bytes;
@@ -49,6 +52,8 @@ int* DeviceCounters::get(size_t bytes) {
 }
 void DeviceCounters::release() {
   if (ptr_) cudaFree(ptr_);
+  for (void* p : retired_) cudaFree(p);
+  retired_.clear();
   ptr_ = nullptr;
   bytes_ = 0;
 }

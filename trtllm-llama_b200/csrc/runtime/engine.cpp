@@ -117,7 +117,7 @@ struct tbrt_engine {
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
   int *d_ids = nullptr, *d_in_lens = nullptr, *d_seq_lens = nullptr, *d_step_pos = nullptr, *d_next = nullptr,
-      *d_out_ids = nullptr, *d_prompt = nullptr, *d_flag = nullptr;
+      *d_out_ids = nullptr, *d_prompt = nullptr, *d_flag = nullptr, *d_max_in = nullptr;
   int* h_flag = nullptr;        // pinned
   int end_id = -1;              // >= 0: greedy stop criterion + end_id padding in tbrt_generate
   int last_steps = 0;
@@ -396,7 +396,9 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
                                  desc({1}, DataType::kFLOAT), desc({1}, DataType::kFLOAT)};
       PluginTensorDesc od[2] = {desc({Bq, context ? S : 1, hid_l}, DataType::kHALF), id[1]};
       // masked_tokens = NULL: derived from input_lengths / max_input_length on the device ([ext])
-      const void* in[10] = {qkv, kv[li], d_seq_lens, host_len, nullptr, d_in_lens, nullptr, nullptr, l.kv_oq, l.kv_qo};
+      // input 6: max_input_length as one device int (device_lengths [ext]) — a replayed step graph must not bake S_in
+      const void* in[10] = {qkv, kv[li], d_seq_lens, host_len, nullptr, d_in_lens, context ? nullptr : d_max_in, nullptr,
+                            l.kv_oq, l.kv_qo};
       void* out[2] = {att, kv[li]};
       launches += context ? 2 : 1;
       RT_CALL(attn->enqueue(id, od, in, out, workspace, s));
@@ -604,7 +606,7 @@ int tbrt_finalize(tbrt_engine* e) {
   if (e->alloc(e->d_ids, (size_t) c.max_batch * 4) || e->alloc(e->d_in_lens, (size_t) c.max_batch * 4) ||
       e->alloc(e->d_seq_lens, (size_t) c.max_batch * 4) || e->alloc(e->d_step_pos, 4) ||
       e->alloc(e->d_next, (size_t) c.max_batch * 4) || e->alloc(e->d_out_ids, (size_t) c.max_batch * c.max_output_len * 4) ||
-      e->alloc(e->d_flag, 4) || cudaMallocHost(reinterpret_cast<void**>(&e->h_flag), 4) != cudaSuccess ||
+      e->alloc(e->d_flag, 4) || e->alloc(e->d_max_in, 4) || cudaMallocHost(reinterpret_cast<void**>(&e->h_flag), 4) != cudaSuccess ||
       e->alloc(e->d_prompt, Mmax * 4) || e->alloc(e->d_dummy_scale, 4))
     return -1;
   RT_CUDA(cudaMemset(e->d_dummy_scale, 0, 4));
@@ -643,6 +645,7 @@ int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_length
   // position seq afterwards (sequence_length = max_input_len + step, generation.py:686-687)
   RT_CUDA(cudaMemsetAsync(e->d_step_pos, 0, 4, s));
   RT_CALL(tb_fill_int(e->d_seq_lens, seq - 1, batch, s));
+  RT_CALL(tb_fill_int(e->d_max_in, seq, 1, s));
   RT_CUDA(cudaMemcpyAsync(e->d_in_lens, input_lengths, (size_t) batch * 4, cudaMemcpyDeviceToDevice, s));
   e->launches += 1;
   RT_CALL(tb_embedding(e->h, e->emb, ids, M, e->c.hidden, e->c.vocab, s));

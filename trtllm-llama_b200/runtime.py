@@ -106,8 +106,12 @@ def quantize_linear(w_nk: torch.Tensor, mode: int):
     return {"weight": q, "per_channel_scale": s}
 
 
-def build_engine_tensors(w, cfg: ModelConfig, kv_scale: float = 4.0 / 127.0):
-    """fp16 weights (this rank's shard, see ``shard_weights``) -> {engine tensor name: device tensor}."""
+def build_engine_tensors(w, cfg: ModelConfig, kv_scale: float = 4.0 / 127.0, require_kv_scale: bool = False):
+    """fp16 weights (this rank's shard, see ``shard_weights``) -> {engine tensor name: device tensor}.
+
+    ``kv_scale`` is the int8-KV placeholder for random-init builds; a layer's own calibrated ``kv_scale`` wins.  With
+    ``require_kv_scale`` (real checkpoints: ``--model_dir`` given) a layer without one raises, as the reference loader
+    does on the missing ``scale_y_quant_orig`` file (LQ/weight_quant.py:439-446)."""
     mode = cfg.mode
     t = {"vocab_embedding.weight": w["vocab_embedding"], "ln_f.weight": w["ln_f"], "lm_head.weight": w["lm_head"]}
     for i, lw in enumerate(w["layers"]):
@@ -131,10 +135,14 @@ def build_engine_tensors(w, cfg: ModelConfig, kv_scale: float = 4.0 / 127.0):
                 t[p + name + "." + k] = v
         if cfg.quant_mode.has_int8_kv_cache():
             dev = lw["qkv"].device
-            kv_scale = lw.get("kv_scale", kv_scale)
+            if require_kv_scale and "kv_scale" not in lw:
+                raise FileNotFoundError(
+                    f"layer {i}: int8 KV cache requested but the checkpoint has no calibrated "
+                    "attention.query_key_value.scale_y_quant_orig (run hf_llama_convert.py with -kv or -sq)")
+            layer_scale = float(lw.get("kv_scale", kv_scale))
             # LQ/weight_quant.py:439-446: kv_orig_quant_scale = 1/t, kv_quant_orig_scale = t
-            t[p + "attention.kv_orig_quant_scale"] = torch.tensor([1.0 / kv_scale], dtype=torch.float32, device=dev)
-            t[p + "attention.kv_quant_orig_scale"] = torch.tensor([kv_scale], dtype=torch.float32, device=dev)
+            t[p + "attention.kv_orig_quant_scale"] = torch.tensor([1.0 / layer_scale], dtype=torch.float32, device=dev)
+            t[p + "attention.kv_quant_orig_scale"] = torch.tensor([layer_scale], dtype=torch.float32, device=dev)
     return {k: v.contiguous() for k, v in t.items()}
 
 
