@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """Headline benchmark (driver contract): LLaMA-7B decode tokens/s on B200 through the plugin engine.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|cfg3_int8kv|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--only-headline]
 
-Workload (BASELINE.json configs[1], the N=1 default): LLaMA-7B, fp16 weights, GPTAttention plugin + int8 KV cache,
-batch 1, 128-token prompt, 128 generated tokens, synthetic prompt ids and seeded random-init weights.
+Headline workload (BASELINE.json configs[1], the N=1 default): LLaMA-7B, fp16 weights, GPTAttention plugin + int8 KV
+cache, batch 1, 128-token prompt, 128 generated tokens, synthetic prompt ids and seeded random-init weights.
 A "step" is one whole request (context phase + 127 generation steps).  Metric = batch * out_len / latency, the
 reference's own definition (T/benchmarks/gpt_benchmark.py:339; LQ/run.py:117-198 times setup+decode).
   value : requests driven with device-resident prompt ids, timed with CUDA events on the launching stream
   e2e   : GenerationSession.decode() with pinned HOST buffers (H2D prompt, D2H output ids inside the timed region)
-  roofline : the weight-streaming GEMV (dominant kernel: > 90 % of a decode step) timed alone with CUDA events over
-             all 32 layers' projections (13 GB of distinct weights, far beyond L2), algorithmic bytes = weight bytes
+  roofline : the dominant kernel class of a decode step (the weight-streaming projections) timed alone with CUDA events
+             over all 32 layers' projections (distinct weights, far beyond L2), algorithmic bytes = weight bytes
+  workloads : the SAME measurements for the other configurations BASELINE.json's metric names — SmoothQuant + int8 KV
+             (north_star target), weight-only int8 at batch 8 / 2048-token context (fp16 and int8 KV), int4 + int8 KV at
+             batch 1 and 8, and the SmoothQuant prefill at batch 8 x 2048 (int8 tensor-core roofline against a tcgen05
+             kind::i8 peak measured in the same run) — each with value, decode_step / prefill_ms, roofline.frac, clocks
+  reference_kernels : the reference's own CUDA kernels (oracle/_ref/libref_cuda.so, recompiled for sm_100a) timed in
+             the same CUDA-event harness beside this library's kernel for the same shape
   cpu_baseline / --impl reference : the reference's run_hf.py path (HF fp32 generate on the host cores), bounded sample
-N > 1 (torchrun): tensor parallel over N GPUs (strong scaling: one request sharded across ranks).
+N > 1 (torchrun): tensor parallel over N GPUs (strong scaling: one request sharded across ranks); rank 0 also runs the
+first request on a tp = 1 engine and asserts the generated ids agree ("tp_parity").
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -28,15 +36,23 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 LLAMA7B = dict(hidden=4096, heads=32, inter=11008, layers=32, vocab=32000)
+GEMM_WEIGHT_ELEMS = 6476005376          # 32 layers x 202,375,168
+LM_HEAD_BYTES = 262144000
 WORKLOADS = {
     # name: (mode, int8_kv, batch, in_len, out_len, description)
     "cfg2": ("fp16", True, 1, 128, 128, "LLaMA-7B fp16 GPTAttentionPlugin + int8 KV-cache, batch=1, 128-in/128-out"),
     "cfg3": ("w8", False, 8, 1920, 128, "LLaMA-7B weight-only int8, batch=8, 2048-ctx decode (1920-in/128-out), fp16 KV"),
     "cfg3_int8kv": ("w8", True, 8, 1920, 128, "LLaMA-7B weight-only int8 + int8 KV, batch=8, 2048-ctx decode"),
     "cfg5": ("w4", True, 1, 128, 128, "LLaMA-7B int4 weight-only + int8 KV-cache, batch=1, 128-in/128-out"),
+    "cfg5_b8": ("w4", True, 8, 128, 128, "LLaMA-7B int4 weight-only + int8 KV-cache, batch=8, 128-in/128-out"),
     "w8_b1": ("w8", True, 1, 128, 128, "LLaMA-7B weight-only int8 + int8 KV-cache, batch=1, 128-in/128-out"),
     "sq": ("sq", True, 1, 128, 128, "LLaMA-7B SmoothQuant per-token/per-channel int8 + int8 KV, batch=1, 128-in/128-out"),
+    "sq_b8": ("sq", True, 8, 128, 128, "LLaMA-7B SmoothQuant per-token/per-channel int8 + int8 KV, batch=8, 128-in/128-out"),
 }
+SIDE_N1 = ["sq", "sq_b8", "cfg3", "cfg3_int8kv", "cfg5", "cfg5_b8"]     # + cfg4_prefill, at N = 1
+SIDE_TP = ["cfg5", "cfg5_b8"]                                            # BASELINE configs[4], at N > 1
+BPW = {"fp16": 2.0, "w8": 1.0, "w4": 0.5, "sq": 1.0}
+DTYPE = {"fp16": "fp16", "w8": "fp16 x int8", "w4": "fp16 x int4", "sq": "int8"}
 
 
 def peaks():
@@ -44,7 +60,7 @@ def peaks():
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return json.load(f), "measured"
     except Exception:
-        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
 class ClockSampler:
@@ -61,6 +77,7 @@ class ClockSampler:
                                        "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
+        return self
 
     def stop(self):
         if not self.p:
@@ -109,12 +126,16 @@ def make_weights(torch, cfg, rank, tp, seed=0):
     return w
 
 
-def ncu_traffic_per_launch():
-    """dram__bytes_read + dram__bytes_write per GEMV launch from the committed `ncu --set full` capture
-    (profiles/r01_gemv_full.txt): one launch of each of the four projection shapes of a layer, averaged."""
+def ncu_traffic_per_launch(mode, rows, tp):
+    """dram__bytes_read + dram__bytes_write per projection launch from the committed `ncu --set full` capture of THIS
+    round's kernels (profiles/r02_gemv_<mode>_full.txt: one launch of each of the four projection shapes of a layer,
+    averaged).  None when no capture of this exact configuration (mode, rows, tp = 1) is committed."""
     import re
+    if tp != 1:
+        return None
+    path = os.path.join(ROOT, "profiles", f"r02_gemv_{mode}_m{rows}_full.txt")
     try:
-        txt = open(os.path.join(ROOT, "profiles", "r01_gemv_full.txt")).read()
+        txt = open(path).read()
     except OSError:
         return None
     per_grid = {}
@@ -131,13 +152,13 @@ def ncu_traffic_per_launch():
     return int(sum(per_grid.values()) / len(per_grid))
 
 
-def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which, rows=1):
+def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which, rows=1, tp=1):
     """Time the dominant kernel class alone: one weight-streaming decode projection launch per projection of every
     layer (`rows` token rows), replayed as ONE CUDA graph (no host launch gaps), CUDA events on the launching stream;
     every launch reads weights no other launch touched (13 GB of distinct weights for fp16: far beyond L2)."""
     from trtllm_llama_b200 import ops
     kind = {"fp16": ops.KIND_F16, "w8": ops.KIND_W8, "w4": ops.KIND_W4, "sq": ops.KIND_A8W8}[mode]
-    bpw = {"fp16": 2.0, "w8": 1.0, "w4": 0.5, "sq": 1.0}[mode]
+    bpw = BPW[mode]
     hid = cfg["hidden"]
     x16 = (torch.randn(rows, max(hid, cfg["inter"]), device="cuda") * 0.1).half()
     x8 = torch.randint(-127, 127, (rows, max(hid, cfg["inter"])), device="cuda", dtype=torch.int8)
@@ -190,8 +211,320 @@ def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which, rows=1):
             "achieved": round(achieved, 1), "peak": hbm_peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
             "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "bytes_per_launch": bytes_total // n_launch,
             "us_per_launch": round(ms * 1e3 / n_launch, 2), "launches_timed": n_launch * reps,
-            "traffic": ncu_traffic_per_launch() if (mode == "fp16" and rows == 1) else None,
+            "traffic": ncu_traffic_per_launch(mode, rows, tp),
             "timing": "one CUDA graph of the %d launches, replayed %d times" % (n_launch, reps) if graphed else "eager launches"}
+
+
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    """process-wide state shared by the workloads of one bench run"""
+
+    def __init__(self, args):
+        import torch
+        self.torch, self.args = torch, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        import trtllm_llama_b200  # noqa: F401
+        from trtllm_llama_b200._lib import lib
+        self.lib = lib
+        assert lib.tb_check_device() == 0
+        if self.world > 1:
+            import ctypes as C
+            idbuf = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                assert lib.tb_comm_unique_id(idbuf.data_ptr()) == 0
+            idd = idbuf.cuda()
+            self.dist.broadcast(idd, 0)
+            idbuf = idd.cpu()
+            group = (C.c_int32 * self.world)(*range(self.world))
+            rc = lib.tb_comm_init(idbuf.data_ptr(), group, self.world, self.rank)
+            assert rc == 0, f"tb_comm_init failed: {rc}"
+        self.pk, self.which = peaks()
+        self.hbm = float(self.pk["hbm_gbs"])
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        t = self.torch.tensor(vals, device="cuda", dtype=self.torch.float64)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+
+def build_session(cx, mode, int8_kv, B, in_len, out_len, tp, rank, graph=True, peer_ar=True):
+    from trtllm_llama_b200 import runtime as rt
+    from trtllm_llama_b200.quantization import QuantMode
+    torch = cx.torch
+    qm = {"fp16": QuantMode(0), "w8": QuantMode.use_weight_only(False), "w4": QuantMode.use_weight_only(True),
+          "sq": QuantMode.use_smooth_quant(True, True)}[mode]
+    if int8_kv:
+        qm |= QuantMode.INT8_KV_CACHE
+    mc = rt.ModelConfig(vocab_size=LLAMA7B["vocab"], num_layers=LLAMA7B["layers"], num_heads=LLAMA7B["heads"],
+                        hidden_size=LLAMA7B["hidden"], inter_size=LLAMA7B["inter"], quant_mode=qm, max_batch_size=B,
+                        max_input_len=in_len, max_output_len=out_len, tp_size=tp, tp_rank=rank)
+    w = make_weights(torch, LLAMA7B, rank, tp)
+    tensors = rt.build_engine_tensors(w, mc)
+    del w
+    torch.cuda.empty_cache()
+    sess = rt.GenerationSession(mc, tensors, use_cuda_graph=graph)
+    if tp > 1 and peer_ar:
+        sess.enable_peer_allreduce()
+    sess.setup(B, in_len, out_len)
+    return sess, tensors
+
+
+def step_bytes_of(mode, int8_kv, B, in_len, out_len, tp):
+    L_mid = in_len + out_len // 2
+    return (GEMM_WEIGHT_ELEMS * BPW[mode] + LM_HEAD_BYTES) / tp + 2 * 32 * B * L_mid * 4096 * (1 if int8_kv else 2) / tp
+
+
+def run_decode_workload(cx, name, steps, warmup, with_e2e=True, with_roofline=True, return_ids=False):
+    """one decode workload on this process group: builds weights + engine, times requests; rank 0 gets the result dict"""
+    torch, lib = cx.torch, cx.lib
+    mode, int8_kv, B, in_len, out_len, desc = WORKLOADS[name]
+    tp, rank = cx.world, cx.rank
+    sess, tensors = build_session(cx, mode, int8_kv, B, in_len, out_len, tp, rank, graph=not cx.args.no_graph,
+                                  peer_ar=not cx.args.nccl_only)
+    g = torch.Generator().manual_seed(1234)
+    host_ids = torch.randint(3, LLAMA7B["vocab"], (B, in_len), generator=g, dtype=torch.int32).pin_memory()
+    host_lens = torch.full((B,), in_len, dtype=torch.int32).pin_memory()
+    host_out = torch.empty((B, out_len), dtype=torch.int32).pin_memory()
+    dev_ids, dev_lens = host_ids.cuda(), host_lens.cuda()
+    st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+
+    def request_device():
+        if lib.tbrt_context(sess._e, dev_ids.data_ptr(), dev_lens.data_ptr(), B, in_len, st()):
+            raise RuntimeError(lib.tbrt_last_error().decode())
+        for _ in range(out_len - 1):
+            if lib.tbrt_step(sess._e, st()):
+                raise RuntimeError(lib.tbrt_last_error().decode())
+
+    # ---- value: device-resident inputs, CUDA events, max over ranks --------------------------------
+    for _ in range(max(warmup, 3)):
+        request_device()
+    clocks = ClockSampler(cx.local)
+    cx.barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        request_device()
+    e1.record()
+    cx.barrier()
+    dev_ms = e0.elapsed_time(e1)
+    # ---- context phase alone and decode-only step time (graph replays), for the step-level roofline ------------------
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    lib.tbrt_context(sess._e, dev_ids.data_ptr(), dev_lens.data_ptr(), B, in_len, st())
+    c1.record()
+    for _ in range(3):
+        lib.tbrt_step(sess._e, st())
+    torch.cuda.synchronize()
+    ctx_ms = c0.elapsed_time(c1)
+    n_dec = out_len - 4
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(n_dec):
+        lib.tbrt_step(sess._e, st())
+    d1.record()
+    torch.cuda.synchronize()
+    step_ms = d0.elapsed_time(d1) / n_dec
+    step_launches = int(sess.last_launches)
+    # ---- e2e: public API with pinned host buffers ----------------------------------------------------------
+    e2e_ms, launches = 0.0, 0
+    if with_e2e:
+        for _ in range(2):
+            sess.decode(host_ids, host_lens, out=host_out)
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sess.decode(host_ids, host_lens, out=host_out)
+        launches = int(sess.last_launches)
+        cx.barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+    else:
+        sess.decode(host_ids, host_lens, out=host_out)
+        launches = int(sess.last_launches)
+    clk = clocks.stop()
+    dev_ms, e2e_ms, step_ms, ctx_ms = cx.max_over_ranks([dev_ms, e2e_ms, step_ms, ctx_ms])
+    ids = host_out.clone().numpy() if return_ids else None
+
+    step_bytes = step_bytes_of(mode, int8_kv, B, in_len, out_len, tp)
+    roof = None
+    if with_roofline and rank == 0:
+        roof = gemv_roofline(torch, tensors, LLAMA7B, mode, cx.hbm, cx.which, rows=min(B, 8), tp=tp)
+    res = None
+    if rank == 0:
+        hbm_ms = step_bytes / (cx.hbm * 1e9) * 1e3
+        res = {"workload": desc, "value": round(B * out_len * steps / (dev_ms * 1e-3), 2), "unit": "tokens/s",
+               "ms_per_request": round(dev_ms / steps, 3), "steps": steps, "warmup": max(warmup, 3),
+               "dtype": DTYPE[mode], "batch": B, "in_len": in_len, "out_len": out_len, "parallelism": f"tp{tp}",
+               "context_ms": round(ctx_ms, 3),
+               "decode_step": {"ms": round(step_ms, 4), "tokens_per_sec": round(B / (step_ms * 1e-3), 1),
+                               "kernels": step_launches, "algorithmic_bytes": int(step_bytes),
+                               "achieved_gbs": round(step_bytes / (step_ms * 1e-3) / 1e9, 1),
+                               "frac_of_hbm_peak": round(step_bytes / (step_ms * 1e-3) / 1e9 / cx.hbm, 4),
+                               "hbm_floor_ms": round(hbm_ms, 4)},
+               "roofline": roof, "clocks": clk, "gpu_launches": launches * (steps if with_e2e else 1)}
+        if with_e2e:
+            res["e2e"] = {"value": round(B * out_len * steps / (e2e_ms * 1e-3), 2), "unit": "tokens/s",
+                          "h2d_bytes_per_step": int(B * in_len * 4 + B * 4), "d2h_bytes_per_step": int(B * out_len * 4)}
+        if tp > 1:
+            # which term bounds a step at this tp: HBM (per-rank bytes), NVLink (64 one-shot all-reduces: every rank reads
+            # world x M x hidden x 2 bytes from its peers at the measured 770 GB/s), or the dependent-kernel chain
+            nvl_ms = 64 * (tp - 1) * B * 4096 * 2 / 770e9 * 1e3
+            chain_ms = step_ms - max(hbm_ms, nvl_ms)
+            res["limits"] = {"hbm_ms": round(hbm_ms, 4), "nvlink_ms": round(nvl_ms, 4),
+                             "dependent_kernel_chain_ms": round(chain_ms, 4), "kernels": step_launches,
+                             "us_per_kernel": round(step_ms * 1e3 / max(step_launches, 1), 2),
+                             "limiter": "dependent-kernel chain (launch + sync latency)" if chain_ms > max(hbm_ms, nvl_ms)
+                             else ("hbm" if hbm_ms >= nvl_ms else "nvlink")}
+    del sess, tensors
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res, ids
+
+
+def tp_parity(cx, name, tp_ids):
+    """rank 0: the same request on a tp = 1 engine of the same weights; ids must agree up to the first step at which the
+    tp = 1 top-2 logit margin is below the logit tolerance (a near-tie may legitimately break differently: the
+    all-reduce sums partials in a different order than one GEMV does)."""
+    torch = cx.torch
+    import numpy as np
+    mode, int8_kv, B, in_len, out_len, _ = WORKLOADS[name]
+    sess, tensors = build_session(cx, mode, int8_kv, B, in_len, out_len, 1, 0, graph=True, peer_ar=False)
+    g = torch.Generator().manual_seed(1234)
+    ids = torch.randint(3, LLAMA7B["vocab"], (B, in_len), generator=g, dtype=torch.int32)
+    lens = torch.full((B,), in_len, dtype=torch.int32)
+    margins, toks = [], []
+    lg = sess.context(ids, lens)
+    for s in range(out_len):
+        top2 = torch.topk(lg, 2, dim=-1).values
+        margins.append((top2[:, 0] - top2[:, 1]).cpu().numpy())
+        toks.append(lg.argmax(-1).cpu().numpy())
+        if s + 1 < out_len:
+            lg = sess.step()
+    scale = float(lg.abs().max())
+    one = sess.output_ids(out_len).cpu().numpy()
+    del sess, tensors
+    gc.collect()
+    torch.cuda.empty_cache()
+    tol = 2e-2 * max(1.0, scale)
+    agree, first_diff, ok = 0, None, True
+    for s in range(out_len):
+        if np.array_equal(one[:, s], tp_ids[:, s]):
+            agree += 1
+            continue
+        first_diff = s
+        rows = one[:, s] != tp_ids[:, s]
+        ok = bool((np.stack(margins, 1)[rows, s] <= tol).all())
+        break
+    return {"ok": ok, "ids_equal_steps": agree, "of": out_len, "first_difference_step": first_diff,
+            "rule": f"ids identical until a step whose tp=1 top-2 margin <= {tol:.3g} (2e-2 x |logits|max)"}
+
+
+def int8_peak(cx):
+    """tcgen05 kind::i8 tensor-pipe peak of this GPU at its sustained clock: back-to-back MMAs on resident operands,
+    one CTA per SM, CUDA events (csrc/peak.cu).  Also kind::f16 the same way, for calibration against cuBLAS bf16."""
+    import ctypes as C
+    torch, lib = cx.torch, cx.lib
+    sink = torch.zeros(4, dtype=torch.int32, device="cuda")
+    out = {}
+    for kind, key in ((0, "int8_tops"), (1, "f16_tflops")):
+        ops = C.c_double(0)
+        best = None
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = lib.tb_mma_peak(kind, 20000, 148, sink.data_ptr(), C.byref(ops), torch.cuda.current_stream().cuda_stream)
+            e1.record()
+            torch.cuda.synchronize()
+            assert rc == 0, f"tb_mma_peak failed: {rc}"
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        out[key] = round(ops.value / (best * 1e-3) / 1e12, 1)
+    out["how"] = ("148 CTAs x 20000 x 4 back-to-back tcgen05.mma 128x256x(32 int8 | 16 fp16) on resident smem tiles, "
+                  "best of 6, CUDA events (csrc/peak.cu)")
+    return out
+
+
+def run_prefill_workload(cx, steps, warmup):
+    """BASELINE configs[3]: SmoothQuant per-token int8, batch 8, prefill 2048 (M = 16384 rows) through tbrt_context."""
+    torch, lib = cx.torch, cx.lib
+    B, S = 8, 2048
+    sess, tensors = build_session(cx, "sq", True, B, S, 8, 1, 0)
+    g = torch.Generator().manual_seed(1234)
+    ids = torch.randint(3, LLAMA7B["vocab"], (B, S), generator=g, dtype=torch.int32).cuda()
+    lens = torch.full((B,), S, dtype=torch.int32).cuda()
+    st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    for _ in range(max(warmup, 3)):
+        lib.tbrt_context(sess._e, ids.data_ptr(), lens.data_ptr(), B, S, st())
+    torch.cuda.synchronize()
+    clocks = ClockSampler(cx.local).start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        lib.tbrt_context(sess._e, ids.data_ptr(), lens.data_ptr(), B, S, st())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = int(sess.last_launches)
+    # the dominant kernel class alone: the four projection GEMMs of every layer (distinct weights), one pass
+    from trtllm_llama_b200 import ops
+    M = B * S
+    xq = torch.randint(-127, 128, (M, LLAMA7B["inter"]), device="cuda", dtype=torch.int8)
+    sr = torch.rand(M, 1, device="cuda") * 0.01 + 1e-3
+    calls = []
+    for i in range(LLAMA7B["layers"]):
+        for nm in ("attention.qkv", "attention.dense", "mlp.fc_gate", "mlp.proj"):
+            wt = tensors[f"layers.{i}.{nm}.weight"]
+            calls.append((wt, tensors[f"layers.{i}.{nm}.per_channel_scale"].view(1, -1), wt.shape[1]))
+    xs = {K: xq[:, :K].contiguous() for K in {c[2] for c in calls}}
+    def run_gemms(n):
+        for wt, sc, K in calls[:n]:
+            ops.gemm_tc(ops.KIND_A8W8, xs[K], wt, sc=sc, sr=sr)
+    run_gemms(8)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    run_gemms(len(calls))
+    g1.record()
+    torch.cuda.synchronize()
+    gemm_ms = g0.elapsed_time(g1)
+    clk = clocks.stop()
+    pk = int8_peak(cx)
+    gemm_ops = 2.0 * M * GEMM_WEIGHT_ELEMS
+    attn_flops = 2.0 * S * S * 4096 * 32 * B            # causal QK^T + PV, fp16 (SURVEY 8d)
+    tops = gemm_ops / (gemm_ms * 1e-3) / 1e12
+    res = {"workload": "LLaMA-7B SmoothQuant per-token int8 (sq GEMM + RmsnormQuant), batch=8, prefill 2048",
+           "prefill_ms": round(ms, 3), "value": round(B * S / (ms * 1e-3), 1), "unit": "prefill tokens/s", "steps": steps,
+           "warmup": max(warmup, 3), "kernels": launches, "dtype": "int8",
+           "int8_ops": gemm_ops, "attention_fp16_flops": attn_flops,
+           "whole_context_int8_tops": round(gemm_ops / (ms * 1e-3) / 1e12, 1),
+           "roofline": {"bound": "tensor", "kernel": "SmoothQuant projection GEMMs at M = 16384 (gemm_tc2_kernel, tcgen05 "
+                                                     "kind::i8 cta_group::2), all 128 launches of the model, timed alone",
+                        "achieved": round(tops, 1), "peak": pk["int8_tops"], "unit": "TOP/s",
+                        "frac": round(tops / pk["int8_tops"], 4),
+                        "peak_source": "measured in this run: " + pk["how"],
+                        "frac_of_2x_bf16_sustained": round(tops / (2 * float(cx.pk.get("bf16_tflops_sustained", 1400.0))), 4),
+                        "frac_of_datasheet_4500": round(tops / 4500.0, 4), "ms": round(gemm_ms, 3), "traffic": None},
+           "roofline_floor_ms": {"gemm_at_measured_int8_peak": round(gemm_ops / (pk["int8_tops"] * 1e12) * 1e3, 2),
+                                 "attention_at_bf16_sustained": round(attn_flops / (float(cx.pk.get("bf16_tflops_sustained", 1400.0)) * 1e12) * 1e3, 2)},
+           "measured_peaks": pk, "clocks": clk}
+    del sess, tensors, xq, xs
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference(args):
@@ -199,7 +532,6 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.hf_baseline import time_hf_cpu
     mode, int8_kv, B, in_len, out_len, desc = WORKLOADS[args.workload]
     vals, last = [], None
     t_all = time.perf_counter()
@@ -226,7 +558,6 @@ def run_reference(args):
         return tp, ts
     for _ in range(max(1, min(args.warmup, 1))):
         sample()
-    t0 = time.perf_counter()
     for _ in range(args.steps):
         last = sample()
         vals.append(B * out_len / (last[0] + out_len * last[1]))
@@ -253,8 +584,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--only-headline", action="store_true", help="skip the `workloads` / `reference_kernels` blocks")
+    ap.add_argument("--side", default=None, help="comma list of side workloads (default: the BASELINE set for this N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-tp-parity", action="store_true")
     ap.add_argument("--nccl-only", action="store_true", help="tensor parallel: use the NCCL AllReduce plugin on the decode path too")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -263,155 +597,79 @@ def main():
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200 (sm_100a): the product path has no CPU fallback")
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import trtllm_llama_b200  # noqa: F401
-    from trtllm_llama_b200 import runtime as rt
-    from trtllm_llama_b200._lib import lib
-    from trtllm_llama_b200.quantization import QuantMode
-    assert lib.tb_check_device() == 0
+    cx = Ctx(args)
+    rank, world = cx.rank, cx.world
+    name = args.workload
+    mode, int8_kv, B, in_len, out_len, desc = WORKLOADS[name]
 
-    mode, int8_kv, B, in_len, out_len, desc = WORKLOADS[args.workload]
-    tp = world
-    if tp > 1:
-        import ctypes as C
-        idbuf = torch.zeros(128, dtype=torch.uint8)
+    head, ids = run_decode_workload(cx, name, args.steps, args.warmup, return_ids=True)
+    parity = None
+    if world > 1 and not args.no_tp_parity:
         if rank == 0:
-            assert lib.tb_comm_unique_id(idbuf.data_ptr()) == 0
-        idd = idbuf.cuda()
-        dist.broadcast(idd, 0)
-        idbuf = idd.cpu()
-        group = (C.c_int32 * tp)(*range(tp))
-        rc = lib.tb_comm_init(idbuf.data_ptr(), group, tp, rank)
-        assert rc == 0, f"tb_comm_init failed: {rc}"
+            parity = tp_parity(cx, name, ids)
+        cx.barrier()
 
-    qm = {"fp16": QuantMode(0), "w8": QuantMode.use_weight_only(False), "w4": QuantMode.use_weight_only(True),
-          "sq": QuantMode.use_smooth_quant(True, True)}[mode]
-    if int8_kv:
-        qm |= QuantMode.INT8_KV_CACHE
-    mc = rt.ModelConfig(vocab_size=LLAMA7B["vocab"], num_layers=LLAMA7B["layers"], num_heads=LLAMA7B["heads"],
-                        hidden_size=LLAMA7B["hidden"], inter_size=LLAMA7B["inter"], quant_mode=qm, max_batch_size=B,
-                        max_input_len=in_len, max_output_len=out_len, tp_size=tp, tp_rank=rank)
-    w = make_weights(torch, LLAMA7B, rank, tp)
-    tensors = rt.build_engine_tensors(w, mc)
-    del w
-    torch.cuda.empty_cache()
-    sess = rt.GenerationSession(mc, tensors, use_cuda_graph=not args.no_graph)
-    if tp > 1 and not args.nccl_only:
-        sess.enable_peer_allreduce()
-    sess.setup(B, in_len, out_len)
+    side = {}
+    if not args.only_headline:
+        names = args.side.split(",") if args.side else (SIDE_N1 if world == 1 else SIDE_TP)
+        for nm in [n for n in names if n and n != name]:
+            if nm == "cfg4_prefill":
+                continue
+            try:
+                r, _ = run_decode_workload(cx, nm, steps=max(3, min(args.steps, 5)), warmup=3, with_e2e=False)
+            except Exception as ex:  # noqa: BLE001  (one side workload must not take the headline down)
+                r = {"error": f"{type(ex).__name__}: {ex}"}
+                cx.barrier()
+            if rank == 0:
+                side[nm] = r
+        if world == 1 and (args.side is None or "cfg4_prefill" in args.side):
+            try:
+                side["cfg4_prefill"] = run_prefill_workload(cx, steps=max(3, min(args.steps, 5)), warmup=3)
+            except Exception as ex:  # noqa: BLE001
+                side["cfg4_prefill"] = {"error": f"{type(ex).__name__}: {ex}"}
 
-    g = torch.Generator().manual_seed(1234)
-    host_ids = torch.randint(3, LLAMA7B["vocab"], (B, in_len), generator=g, dtype=torch.int32).pin_memory()
-    host_lens = torch.full((B,), in_len, dtype=torch.int32).pin_memory()
-    host_out = torch.empty((B, out_len), dtype=torch.int32).pin_memory()
-    dev_ids, dev_lens = host_ids.cuda(), host_lens.cuda()
-
-    def request_device():
-        st = torch.cuda.current_stream().cuda_stream
-        if lib.tbrt_context(sess._e, dev_ids.data_ptr(), dev_lens.data_ptr(), B, in_len, st):
-            raise RuntimeError(lib.tbrt_last_error().decode())
-        for _ in range(out_len - 1):
-            if lib.tbrt_step(sess._e, st):
-                raise RuntimeError(lib.tbrt_last_error().decode())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- value: device-resident inputs, CUDA events, max over ranks --------------------------------
-    for _ in range(max(args.warmup, 3)):
-        request_device()
-    launches = 0
-    clocks = ClockSampler(local)
-    barrier()
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        request_device()
-    e1.record()
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    # ---- decode-only step time (graph replays), for the step-level roofline ---------------------------
-    lib.tbrt_context(sess._e, dev_ids.data_ptr(), dev_lens.data_ptr(), B, in_len, torch.cuda.current_stream().cuda_stream)
-    for _ in range(3):
-        lib.tbrt_step(sess._e, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    n_dec = out_len - 4
-    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    d0.record()
-    for _ in range(n_dec):
-        lib.tbrt_step(sess._e, torch.cuda.current_stream().cuda_stream)
-    d1.record()
-    torch.cuda.synchronize()
-    step_ms = d0.elapsed_time(d1) / n_dec
-    step_launches = int(sess.last_launches)
-    # ---- e2e: public API with pinned host buffers ----------------------------------------------------------
-    for _ in range(2):
-        sess.decode(host_ids, host_lens, out=host_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sess.decode(host_ids, host_lens, out=host_out)
-    launches = int(sess.last_launches)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clk = clocks.stop()
-
-    t = torch.tensor([dev_ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = t.tolist()
-    value = B * out_len * args.steps / (dev_ms * 1e-3)
-    e2e_value = B * out_len * args.steps / (e2e_ms * 1e-3)
-
-    pk, which = peaks()
-    hbm = float(pk["hbm_gbs"])
-    bpw = {"fp16": 2.0, "w8": 1.0, "w4": 0.5, "sq": 1.0}[mode]
-    L_mid = in_len + out_len // 2
-    step_bytes = (6476005376 * bpw + 262144000) / tp + 2 * 32 * B * L_mid * 4096 * (1 if int8_kv else 2) / tp
-    roof = gemv_roofline(torch, tensors, LLAMA7B, mode, hbm, which, rows=min(B, 8)) if rank == 0 else None
     if rank != 0:
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            cx.dist.barrier()
+            cx.dist.destroy_process_group()
         return
-    line = {"metric": "decode_tokens_per_sec", "value": round(value, 2), "unit": "tokens/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(dev_ms / args.steps, 3),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": {"fp16": "fp16", "w8": "fp16 x int8",
-            "w4": "fp16 x int4", "sq": "int8"}[mode], "data": "synthetic",
-            "config": {"workload": desc, "batch": B, "in_len": in_len, "out_len": out_len, "parallelism": f"tp{tp}",
-                       "l2": "inputs larger than L2: every step streams %.1f GB of weights (L2 = 126 MB)" % (step_bytes / 1e9),
+    line = {"metric": "decode_tokens_per_sec", "value": head["value"], "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_request"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE[mode], "data": "synthetic",
+            "config": {"workload": desc, "batch": B, "in_len": in_len, "out_len": out_len, "parallelism": f"tp{world}",
+                       "l2": "inputs larger than L2: every step streams %.1f GB of weights (L2 = 126 MB)"
+                             % (head["decode_step"]["algorithmic_bytes"] / 1e9),
                        "step_definition": "one request = context phase + out_len-1 generation steps (CUDA-graph replays)"},
-            "e2e": {"value": round(e2e_value, 2), "unit": "tokens/s", "h2d_bytes_per_step": int(B * in_len * 4 + B * 4),
-                    "d2h_bytes_per_step": int(B * out_len * 4)},
-            "gpu_launches": launches * args.steps,
-            "decode_step": {"ms": round(step_ms, 4), "tokens_per_sec": round(B / (step_ms * 1e-3), 1), "kernels": step_launches,
-                            "algorithmic_bytes": int(step_bytes), "achieved_gbs": round(step_bytes / (step_ms * 1e-3) / 1e9, 1),
-                            "frac_of_hbm_peak": round(step_bytes / (step_ms * 1e-3) / 1e9 / hbm, 4)},
-            "roofline": roof, "clocks": clk}
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "decode_step": head["decode_step"],
+            "context_ms": head["context_ms"], "roofline": head["roofline"], "clocks": head["clocks"]}
+    if "limits" in head:
+        line["limits"] = head["limits"]
+    if parity is not None:
+        line["tp_parity"] = parity["ok"]
+        line["tp_parity_detail"] = parity
+    if side:
+        line["workloads"] = side
+    if not args.only_headline and world == 1:
+        try:
+            from tools.ref_kernel_bench import reference_kernels
+            line["reference_kernels"] = reference_kernels()
+        except Exception as ex:  # noqa: BLE001
+            line["reference_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle.hf_baseline import time_hf_cpu
-            r = time_hf_cpu(batch=B, in_len=min(in_len, 128), out_len=out_len, new_tokens=6,
+            r = time_hf_cpu(batch=B, in_len=in_len, out_len=out_len, new_tokens=6,
                             **{k: LLAMA7B[k] for k in ("hidden", "inter", "layers", "heads", "vocab")})
             line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tokens/s", "cores": r["cores"], "kind": "port",
-                                    "sample": r["sample"], "t_prefill_s": round(r["t_prefill_s"], 2),
+                                    "sample": r["sample"], "in_len": in_len, "t_prefill_s": round(r["t_prefill_s"], 2),
                                     "t_step_s": round(r["t_step_s"], 3)}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {type(ex).__name__}: {ex}"}
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

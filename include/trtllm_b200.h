@@ -98,6 +98,9 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
                    int past_len,
                    int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv, int nsplit,
                    tb_stream_t stream);
+/* test / A-B hook: which streaming loops an int8 cache uses: -1 automatic (tensor-core loops from 512 cached positions),
+ * 0 FMA loops, 1 tensor-core loops.  Returns the previous mode.  Process-wide; not for concurrent use.            */
+int tb_mmha_set_mode(int mode);
 /* same, with max_input_len read from a device int when max_input_len_dev != NULL (together with seq_lens this leaves
  * no per-request value in the launch arguments: one captured CUDA graph serves every step of every prompt length). */
 int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
@@ -138,6 +141,12 @@ int tb_fill_int(int* p, int value, int n, tb_stream_t s);
 int tb_copy(void* dst, const void* src, size_t bytes, tb_stream_t s); /* device-to-device */
 /* in [tp, rows, vocab_local] fp16 (all-gathered vocab-parallel lm_head) -> out [rows, tp*vocab_local] fp32 */
 int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int tp, tb_stream_t s);
+
+/* ---- measurement support: tensor-pipe ceiling of this GPU at the clock it sustains (SURVEY 8d asks for a measured
+ * tcgen05 kind::i8 peak; MEASURED_PEAKS.json has HBM and cuBLAS bf16 only).  Launches `ctas` CTAs, each issuing
+ * iters x 4 back-to-back tcgen05.mma (128 x 256 x 32 int8 for kind 0, 128 x 256 x 16 fp16 for kind 1) on resident
+ * shared-memory tiles; *ops_out (host) receives the operation count of the launch; the caller times it with events. */
+int tb_mma_peak(int kind, int iters, int ctas, int* sink, double* ops_out, tb_stream_t stream);
 
 /* ---- one-shot NVLink all-reduce + residual add for decode-size messages ------------------------------------
  * replaces AllreducePlugin::enqueue -> ncclAllReduce (P/ncclPlugin/allreducePlugin.cpp:80-97) and the residual

@@ -140,11 +140,17 @@ def sq_gemm(a_i8, b_i8, scale_tokens, scale_channels, out_dtype=F16):
     int32 output: float->int32 round-to-nearest (NumericArrayConverter default)."""
     a = np.asarray(a_i8, dtype=np.int32)
     b = np.asarray(b_i8, dtype=np.int32)
-    acc = (a @ b.T).astype(np.int32)
+    return sq_gemm_epilogue((a @ b.T).astype(np.int32), scale_tokens, scale_channels, out_dtype)
+
+
+def sq_gemm_epilogue(acc_i32, scale_tokens, scale_channels, out_dtype=F16):
+    """The epilogue of ``sq_gemm`` on given exact int32 accumulators [M,N] (epilogue_per_row_per_col_scale.h:279-349);
+    lets a test feed accumulators computed elsewhere (exactly) for shapes where an integer matmul on the CPU is too slow."""
+    acc = np.asarray(acc_i32, dtype=np.int32)
     sr = np.asarray(scale_tokens, dtype=F32).reshape(-1)
     sc = np.asarray(scale_channels, dtype=F32).reshape(-1)
-    sr = np.broadcast_to(sr, (a.shape[0],)) if sr.size == 1 else sr
-    sc = np.broadcast_to(sc, (b.shape[0],)) if sc.size == 1 else sc
+    sr = np.broadcast_to(sr, (acc.shape[0],)) if sr.size == 1 else sr
+    sc = np.broadcast_to(sc, (acc.shape[1],)) if sc.size == 1 else sc
     s = (sc[None, :] * sr[:, None]).astype(F32)
     res = (acc.astype(F32) * s).astype(F32)
     if out_dtype == np.int32:

@@ -175,3 +175,86 @@ def test_weight_only_gemv_reference_kernel(ref, ops, bits):
         y_my = host(ops.weight_only_quant_matmul(d_x, dev(wp), d_s, 1 if bits == 8 else 2, use_gemv=use_gemv))
         np.testing.assert_allclose(y_my.astype(np.float32), y_ref, atol=tol)
         np.testing.assert_allclose(y_my.astype(np.float32), y_or, atol=2e-3 * np.abs(y_or).max() + 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's CUTLASS GEMMs (oracle/_ref/libref_cutlass.so: compute_90 PTX, JIT-compiled on this GPU) as GPU oracle
+# ------------------------------------------------------------------------------------------------
+REF_CUTLASS = os.path.join(ROOT, "oracle", "_ref", "libref_cutlass.so")
+
+
+@pytest.fixture(scope="module")
+def cutlass_ref():
+    if not os.path.exists(REF_CUTLASS):
+        pytest.skip("oracle/_ref/libref_cutlass.so not built")
+    return C.CDLL(REF_CUTLASS)
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 256, 512), (300, 384, 1024), (2048, 4096, 4096)])
+@pytest.mark.parametrize("per_token,per_channel", [(True, True), (False, False)])
+def test_sq_gemm_reference_cutlass_kernel(cutlass_ref, ops, M, N, K, per_token, per_channel):
+    """CutlassInt8GemmRunner's kernel (int8_gemm_template.h:56-172) == the oracle == this repo's tcgen05 GEMM, bit for bit
+    (test_smooth_quant_gemm.py:20-127 input distributions)."""
+    g = torch.Generator(device="cuda").manual_seed(31)
+    a = torch.randint(-128, 128, (M, K), device="cuda", dtype=torch.int8, generator=g)
+    b = torch.randint(-128, 128, (N, K), device="cuda", dtype=torch.int8, generator=g)
+    sr = (torch.randint(1, 10, (M if per_token else 1,), device="cuda", generator=g).float() * 1e-2).contiguous()
+    sc = (torch.randint(1, 10, (N if per_channel else 1,), device="cuda", generator=g).float() * 1e-2).contiguous()
+    ws = torch.zeros(16 << 20, dtype=torch.uint8, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ran = 0
+    mine = host(ops.gemm_tc(ops.KIND_A8W8, a, b, sc=sc.view(1, -1), sr=sr.view(-1, 1)))
+    for tactic in range(cutlass_ref.ref_int8_gemm_num_tactics()):
+        c = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+        rc = cutlass_ref.ref_int8_gemm_half(P(a), P(b), P(sc), P(sr), P(c), M, N, K, int(per_channel), int(per_token), tactic,
+                                            P(ws), C.c_size_t(ws.numel()), st)
+        if rc != 0:
+            continue
+        ran += 1
+        assert np.array_equal(host(c), mine), f"reference CUTLASS tactic {tactic} differs from the tcgen05 GEMM"
+    assert ran > 0, "no reference tactic ran"
+    if M <= 300:
+        assert np.array_equal(mine, R.sq_gemm(host(a), host(b), host(sr), host(sc), np.float16))
+
+
+@pytest.mark.parametrize("bits", [8, 4])
+@pytest.mark.parametrize("M", [8, 130])
+def test_weight_only_gemm_reference_cutlass_kernel(cutlass_ref, ops, bits, M):
+    """CutlassFpAIntBGemmRunner's kernel on the reference's own pre-processed weights (the path the reference takes for
+    batch > 1, fpA_intB_gemm_template.h:49-175) against the oracle and this repo's kernels on their own layout."""
+    if not os.path.exists(REF_HOST):
+        pytest.skip("oracle/_ref/libref_host.so not built")
+    hostlib = C.CDLL(REF_HOST)
+    rng = np.random.default_rng(0)
+    K, N = 4096, 1024
+    w = (rng.random((K, N), dtype=np.float32) * 2 - 1).astype(np.float16)
+    x = (rng.random((M, K), dtype=np.float32) * 0.2 - 0.1).astype(np.float16)
+    nb = K * N * bits // 8
+    proc = np.zeros(nb, np.int8); unproc = np.zeros(nb, np.int8); sc = np.zeros(N, np.uint16)
+    assert hostlib.ref_symmetric_quantize(w.ctypes.data_as(C.c_void_p), C.c_int64(K), C.c_int64(N), bits,
+                                          proc.ctypes.data_as(C.c_void_p), unproc.ctypes.data_as(C.c_void_p),
+                                          sc.ctypes.data_as(C.c_void_p)) == 0
+    scales = sc.view(np.float16)
+    q, _ = R.symmetric_quantize(w, bits)
+    y_or = R.weight_only_matmul(x, q, scales).astype(np.float32)
+    d_x, d_w, d_s = dev(x), dev(proc), dev(scales)
+    ws = torch.zeros(16 << 20, dtype=torch.uint8, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    tol = 1.5 * np.abs(y_or).max() / (1 << (bits - 1))   # the reference's own tolerance (_utils.py:62-89)
+    ran = 0
+    for tactic in range(cutlass_ref.ref_fpA_intB_gemm_num_tactics()):
+        y = torch.zeros((M, N), dtype=torch.float16, device="cuda")
+        rc = cutlass_ref.ref_fpA_intB_gemm_half(P(d_x), P(d_w), P(d_s), P(y), M, N, K, bits, tactic, P(ws),
+                                                C.c_size_t(ws.numel()), st)
+        if rc != 0:
+            continue
+        ran += 1
+        y_ref = host(y).astype(np.float32)
+        np.testing.assert_allclose(y_or, y_ref, atol=tol)
+    assert ran > 0, "no reference tactic ran"
+    from trtllm_llama_b200.quantization import pack_processed_int4
+    qt = np.ascontiguousarray(q.T)
+    wp = qt if bits == 8 else pack_processed_int4(torch.from_numpy(qt)).numpy()
+    y_my = host(ops.weight_only_quant_matmul(d_x, dev(wp), d_s, 1 if bits == 8 else 2, use_gemv=M <= 8)).astype(np.float32)
+    np.testing.assert_allclose(y_my, y_ref, atol=tol)
+    np.testing.assert_allclose(y_my, y_or, atol=2e-3 * np.abs(y_or).max() + 1e-3)

@@ -40,6 +40,7 @@ SIGNATURES = {
     "tb_mmha_counter_bytes": (sz, [i32, i32]),
     "tb_mmha_decode": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32, i32,
                              i32, vp]),
+    "tb_mmha_set_mode": (i32, [i32]),
     "tb_mmha_decode_dev": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32,
                                  i32, i32, vp]),
     "tb_context_attention_workspace_bytes": (sz, [i32, i32, i32]),
@@ -55,6 +56,7 @@ SIGNATURES = {
     "tb_fill_int": (i32, [vp, i32, i32, vp]),
     "tb_copy": (i32, [vp, vp, sz, vp]),
     "tb_gather_logits": (i32, [vp, vp, i32, i32, i32, vp]),
+    "tb_mma_peak": (i32, [i32, i32, i32, vp, C.POINTER(C.c_double), vp]),
 }
 
 

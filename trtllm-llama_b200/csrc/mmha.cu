@@ -471,7 +471,15 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
 
 using namespace tb;
 
+static int g_mma_mode = getenv("TB_MMHA_MMA") ? atoi(getenv("TB_MMHA_MMA")) : -1;
+
 extern "C" {
+
+int tb_mmha_set_mode(int mode) {
+  const int prev = g_mma_mode;
+  g_mma_mode = mode < -1 ? -1 : (mode > 1 ? 1 : mode);
+  return prev;
+}
 
 size_t tb_mmha_workspace_bytes(int batch, int num_heads, int max_splits) {
   return (size_t) batch * num_heads * max_splits * (kDh + 2) * sizeof(float) + 256;
@@ -522,7 +530,7 @@ int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* se
   p.past_len = past_len; p.max_input_len = max_input_len; p.S_max = max_seq_len; p.H = num_heads;
   p.rotary_dim = rotary_dim; p.inv_sqrt_dh = 1.f / (sqrtf((float) head_size) * q_scaling);
   // int8 caches with long contexts: tensor-core loops, two CTAs per SM, so no more splits than fit one wave
-  static const int mma_env = getenv("TB_MMHA_MMA") ? atoi(getenv("TB_MMHA_MMA")) : -1;   // A/B switch: 0 off, 1 always
+  const int mma_env = g_mma_mode;   // A/B switch (TB_MMHA_MMA / tb_mmha_set_mode): 0 off, 1 always, -1 automatic
   const bool use_mma = int8_kv && (mma_env == 1 || (mma_env != 0 && len_cap >= 512));
   if (use_mma) {
     const int fit = (2 * kNumSMs) / (batch * num_heads);

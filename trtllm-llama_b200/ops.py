@@ -175,7 +175,7 @@ def matmul_f16(x, w, residual=None, out_fp32=False, use_gemv=None):
 # ------------------------------------------------------------------------------------------------
 def mmha_decode(qkv, kv_cache, past_len, *, num_heads, head_size, max_input_len, seq_lens=None, input_lengths=None,
                 masked_tokens=None, kv_scale_orig_quant=None, kv_scale_quant_orig=None, q_scaling=1.0,
-                rotary_dim=None, nsplit=0, len_cap=None, max_splits=32):
+                rotary_dim=None, nsplit=0, len_cap=None, max_splits=32, max_input_len_dev=None):
     """GPTAttention plugin, generation phase (T/tensorrt_llm/functional.py:2695-2928 with
     past_key_value_length = [past_len, 0]).  kv_cache [B,2,H,S_max,Dh] is updated in place."""
     _chk_cuda(qkv, kv_cache, seq_lens, input_lengths, masked_tokens, kv_scale_orig_quant, kv_scale_quant_orig)
@@ -188,10 +188,11 @@ def mmha_decode(qkv, kv_cache, past_len, *, num_heads, head_size, max_input_len,
         nsplit = lib.tb_mmha_num_splits(B, num_heads, cap, max_splits)
     ws = _workspace(lib.tb_mmha_workspace_bytes(B, num_heads, max(nsplit, max_splits)), qkv.device)
     out = torch.empty((B, num_heads * head_size), dtype=torch.float16, device=qkv.device)
-    check(lib.tb_mmha_decode(_p(out), _p(qkv), _p(kv_cache), _p(seq_lens), _p(input_lengths), _p(masked_tokens),
-                             _p(kv_scale_orig_quant), _p(kv_scale_quant_orig), _p(ws), _p(_counters(qkv.device)), B, num_heads, head_size, S_max,
-                             int(past_len), int(max_input_len), int(cap), rot, float(q_scaling), int(int8_kv),
-                             nsplit, _stream()), "tb_mmha_decode")
+    # max_input_len_dev: one device int that overrides max_input_len (what the engine's replayed step graph passes)
+    check(lib.tb_mmha_decode_dev(_p(out), _p(qkv), _p(kv_cache), _p(seq_lens), _p(input_lengths), _p(masked_tokens),
+                                 _p(max_input_len_dev), _p(kv_scale_orig_quant), _p(kv_scale_quant_orig), _p(ws), None, B,
+                                 num_heads, head_size, S_max, int(past_len), int(max_input_len), int(cap), rot,
+                                 float(q_scaling), int(int8_kv), nsplit, _stream()), "tb_mmha_decode")
     return out
 
 
