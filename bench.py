@@ -49,7 +49,7 @@ WORKLOADS = {
     "sq": ("sq", True, 1, 128, 128, "LLaMA-7B SmoothQuant per-token/per-channel int8 + int8 KV, batch=1, 128-in/128-out"),
     "sq_b8": ("sq", True, 8, 128, 128, "LLaMA-7B SmoothQuant per-token/per-channel int8 + int8 KV, batch=8, 128-in/128-out"),
 }
-SIDE_N1 = ["sq", "sq_b8", "cfg3", "cfg3_int8kv", "cfg5", "cfg5_b8"]     # + cfg4_prefill, at N = 1
+SIDE_N1 = ["sq", "cfg3", "cfg3_int8kv", "cfg5", "cfg5_b8"]     # + cfg4_prefill, at N = 1
 SIDE_TP = ["cfg5", "cfg5_b8"]                                            # BASELINE configs[4], at N > 1
 BPW = {"fp16": 2.0, "w8": 1.0, "w4": 0.5, "sq": 1.0}
 DTYPE = {"fp16": "fp16", "w8": "fp16 x int8", "w4": "fp16 x int4", "sq": "int8"}
