@@ -142,6 +142,43 @@ int tb_copy(void* dst, const void* src, size_t bytes, tb_stream_t s); /* device-
 /* in [tp, rows, vocab_local] fp16 (all-gathered vocab-parallel lm_head) -> out [rows, tp*vocab_local] fp32 */
 int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int tp, tb_stream_t s);
 
+/* ---- whole decode step in one persistent kernel (1..tb_decode_step_max_batch() token rows) -----------------------
+ * replaces, per generated token, the plugin schedule of GenerationSession.decode's step
+ * (T/tensorrt_llm/runtime/generation.py:852-963): every layer's projections (Gemm / WeightOnlyQuantMatmul /
+ * SmoothQuantGemm at decode shapes), GPTAttention's generation phase, RmsnormQuantization / QuantizePerToken, the
+ * TensorRT-native glue, lm_head and the greedy DynamicDecodeOp — one cooperative launch of one CTA per SM whose
+ * producer warps stream the model's weights through shared memory across phase boundaries (csrc/decode_step.cu).
+ * kind as tb_gemv; weights in this library's layouts ([N,K] rows; fc_gate = gate rows then up rows); scales fp16
+ * (weight-only) or fp32 (SmoothQuant), NULL for fp16 weights.  All buffers are device pointers owned by the caller:
+ * h_a/h_b/qkv/att/act fp16 scratch of max_batch rows, logits fp32 [max_batch, vocab]; ids / seq_lens / step_pos /
+ * out_ids / next_ids / in_lens / max_in are the device-resident step state (as tb_advance_step / tb_mmha_decode_dev).
+ * create returns < 0 when the configuration is not supported (the caller keeps the per-operator path).          */
+typedef struct tb_decode_step tb_decode_step;
+typedef struct {
+  int32_t kind, layers, hidden, heads_local, inter_local, vocab_local, vocab, max_batch, max_seq_len, int8_kv, out_stride;
+  float rms_eps;
+  int32_t tp_size, tp_rank;
+} tb_decode_step_config;
+typedef struct {
+  const void *w_qkv, *w_dense, *w_fc_gate, *w_proj, *s_qkv, *s_dense, *s_fc_gate, *s_proj, *ln_in, *ln_post;
+  void* kv_cache;
+  const float *kv_orig_quant, *kv_quant_orig;
+} tb_decode_step_layer;
+typedef struct {
+  const void *emb, *ln_f, *lm_head;
+  void *h_a, *h_b, *qkv, *att, *act;
+  float* logits;
+  int32_t *ids, *seq_lens, *step_pos, *out_ids, *next_ids;
+  const int32_t *in_lens, *max_in;
+} tb_decode_step_buffers;
+int tb_decode_step_max_batch(void);
+int tb_decode_step_create(tb_decode_step** out, const tb_decode_step_config* cfg, const tb_decode_step_layer* layers,
+                          const tb_decode_step_buffers* buffers);
+void tb_decode_step_destroy(tb_decode_step* d);
+int tb_decode_step_launch(tb_decode_step* d, int batch, tb_stream_t stream);
+/* ring depth (4 KB stages), dynamic shared memory and grid of the launch for `batch` rows (diagnostics) */
+int tb_decode_step_info(const tb_decode_step* d, int batch, int* stages, size_t* smem_bytes, int* grid);
+
 /* ---- measurement support: tensor-pipe ceiling of this GPU at the clock it sustains (SURVEY 8d asks for a measured
  * tcgen05 kind::i8 peak; MEASURED_PEAKS.json has HBM and cuBLAS bf16 only).  Launches `ctas` CTAs, each issuing
  * iters x 4 back-to-back tcgen05.mma (128 x 256 x 32 int8 for kind 0, 128 x 256 x 16 fp16 for kind 1) on resident

@@ -4,7 +4,8 @@
  * registry, creates the operators, and runs the fixed layer schedule of
  * LQ/llama_model.py:78-119,159-287 by calling IPluginV2DynamicExt::enqueue on each, with the
  * TensorRT-native glue ops (RMSNorm, residual, SwiGLU, embedding, last-token gather, lm_head, argmax)
- * fused into plugin epilogues or run as small kernels.  The decode step is captured in a CUDA graph.
+ * fused into plugin epilogues or run as small kernels.  The decode step is captured in a CUDA graph, or — for
+ * 1..4 sequences — runs as one persistent kernel over the same buffers (tbrt_set_decode_mode).
  *
  * Replaces: the serialised TensorRT engine + IExecutionContext (T/tensorrt_llm/runtime/generation.py:61-100)
  * and the step loop of GenerationSession.decode (generation.py:782-997) for greedy, contiguous-KV, beam 1.
@@ -78,6 +79,12 @@ int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_l
 int tbrt_ar_handle(tbrt_engine* e, void* out64);
 int tbrt_ar_open(tbrt_engine* e, const void* handles);
 int tbrt_set_end_id(tbrt_engine* e, int end_id);
+/* Generation steps run as ONE persistent kernel (tb_decode_step_*) whenever the engine's configuration and the batch allow
+ * it (mode 1, default); mode 0 forces the per-operator plugin schedule (IPluginV2DynamicExt::enqueue per operator, CUDA
+ * graph) — same weights, caches and step state, so the two can be compared step by step.
+ * tbrt_fused_step_available: largest batch the fused step takes for this engine (0: not available). */
+int tbrt_set_decode_mode(tbrt_engine* e, int mode);
+int tbrt_fused_step_available(const tbrt_engine* e);
 /* generation steps (incl. the context phase) the last tbrt_generate actually ran */
 int tbrt_last_steps(const tbrt_engine* e);
 /* kernels launched by the last tbrt_context / tbrt_step / tbrt_generate call */

@@ -1,0 +1,123 @@
+"""The whole-step persistent decode kernel (csrc/decode_step.cu, tb_decode_step_*) against (a) the numpy oracle model and
+(b) the per-operator plugin schedule of the same engine (same weights, caches and device-resident step state), for every
+quantisation mode, both KV-cache types and 1..4 sequences with ragged prompts.
+
+Tolerances as tests/test_engine_gpu.py: logits within 1e-2 * max(1, |logits|max) (3e-2 for SmoothQuant) of the oracle;
+greedy ids identical wherever the oracle's top-2 margin exceeds that.  Against the plugin path the bound is the same (the
+two paths sum a row's products in different orders); SmoothQuant int8 GEMMs are exact, so there logits agree to 1 fp16
+ulp of the residual stream unless an activation's int8 code flips."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import ref_model as RM  # noqa: E402
+from tests.test_engine_gpu import _prompts, _session  # noqa: E402
+
+
+def _run(sess, ids, lens, new):
+    B, S = ids.shape
+    sess.setup(B, S, new)
+    logits = [sess.context(torch.from_numpy(ids), torch.from_numpy(lens)).cpu().numpy()]
+    launches = []
+    for _ in range(new - 1):
+        logits.append(sess.step().cpu().numpy())
+        launches.append(int(sess.last_launches))
+    return np.stack(logits, 1), sess.output_ids(new).cpu().numpy(), launches
+
+
+@pytest.mark.parametrize("mode", ["fp16", "w8", "w4", "sq"])
+@pytest.mark.parametrize("int8_kv", [False, True])
+@pytest.mark.parametrize("B", [1, 2, 3, 4])
+def test_fused_step_matches_oracle_and_plugin_schedule(mode, int8_kv, B):
+    cfg = RM.LlamaCfg.tiny(layers=3, hidden=256, inter=384, vocab=512)
+    w = RM.random_weights(cfg, seed=21, std=0.05)
+    S, new = 14, 7
+    lens = [S] + [max(1, S - 4 - 3 * i) for i in range(B - 1)]
+    rng = np.random.default_rng(22)
+    ids, lens = _prompts(rng, cfg, B, S, lens)
+    oracle = RM.OracleLlama(cfg, RM.quantize_model(w, mode), mode, int8_kv, kv_scale=4.0 / 127.0, max_seq_len=S + new)
+    ref_ids, ref_logits = oracle.generate(ids, lens, new, return_logits=True)
+
+    fused, _ = _session(cfg, w, mode, int8_kv, max_batch=4, max_in=S, max_out=new, fused=True)
+    assert fused.fused_step_max_batch >= 4, "the persistent step kernel rejected a configuration it is built for"
+    plug, _ = _session(cfg, w, mode, int8_kv, max_batch=4, max_in=S, max_out=new, fused=False)
+    f_logits, f_ids, f_launch = _run(fused, ids, lens, new)
+    p_logits, p_ids, p_launch = _run(plug, ids, lens, new)
+    assert set(f_launch) == {1} and min(p_launch) > 10        # one kernel per step vs the per-operator schedule
+
+    tol = (3e-2 if mode == "sq" else 1e-2) * max(1.0, float(np.abs(ref_logits).max()))
+    for name, got, got_ids in (("fused", f_logits, f_ids), ("plugin", p_logits, p_ids)):
+        for s in range(new):
+            np.testing.assert_allclose(got[:, s], ref_logits[:, s], atol=tol, err_msg=f"{name} step {s}")
+            top2 = np.sort(ref_logits[:, s], axis=-1)[:, -2:]
+            decided = (top2[:, 1] - top2[:, 0]) > 2 * tol
+            assert np.array_equal(got_ids[decided, s], ref_ids[decided, s]), f"{name}: greedy ids differ at step {s}"
+            if not np.array_equal(got_ids[:, s], ref_ids[:, s]):
+                assert s >= 1
+                break
+    # the two paths against each other, step by step while their ids agree
+    for s in range(new):
+        np.testing.assert_allclose(f_logits[:, s], p_logits[:, s], atol=tol, err_msg=f"fused vs plugin, step {s}")
+        if not np.array_equal(f_ids[:, s], p_ids[:, s]):
+            break
+    # KV cache rows appended by the fused step (layer 1), against the plugin path's
+    if np.array_equal(f_ids, p_ids):
+        a, b = fused.kv_cache(1).cpu().numpy()[:B], plug.kv_cache(1).cpu().numpy()[:B]
+        if int8_kv:
+            d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+            assert d.max() <= 1 and (d != 0).mean() < 2e-2
+        else:
+            np.testing.assert_allclose(a.astype(np.float32), b.astype(np.float32), atol=4e-3)
+
+
+def test_fused_step_generate_api_and_mode_switching():
+    """tbrt_generate through the fused step == stepwise; switching modes between requests keeps both paths consistent
+    (shared caches and step state); a batch above the fused limit falls back to the plugin schedule transparently."""
+    cfg = RM.LlamaCfg.tiny(layers=2, hidden=256, inter=384, vocab=512)
+    w = RM.random_weights(cfg, seed=23, std=0.05)
+    S, new = 10, 12
+    rng = np.random.default_rng(24)
+    sess, _ = _session(cfg, w, "w8", True, max_batch=6, max_in=S, max_out=new)
+    host = lambda a: torch.from_numpy(a).pin_memory()   # noqa: E731
+    for B, ln in ((2, [S, 6]), (6, [S, 3, 9, 1, 7, 10]), (1, [5])):
+        ids, lens = _prompts(rng, cfg, B, S, ln)
+        sess.setup(B, S, new)
+        sess.set_decode_mode(True)
+        a = sess.decode(host(ids), host(lens)).numpy().copy()
+        fused_launches = int(sess.last_launches)
+        a2 = sess.decode(host(ids), host(lens)).numpy().copy()
+        assert np.array_equal(a, a2), "fused step is not deterministic"
+        sess.set_decode_mode(False)
+        b = sess.decode(host(ids), host(lens)).numpy().copy()
+        plug_launches = int(sess.last_launches)
+        if B <= sess.fused_step_max_batch:
+            assert fused_launches < plug_launches
+        else:
+            assert fused_launches == plug_launches
+        # same weights, same arithmetic up to summation order: identical ids unless a near-tie (rare on this model)
+        agree = (a == b).mean()
+        assert agree > 0.9, f"fused and plugin paths disagree on {1 - agree:.0%} of the ids at B={B}"
+
+
+def test_fused_step_long_context_and_7b_row_sizes():
+    """Row lengths of LLaMA-7B (K = 4096 and 11008: rows split into 4 KB stages with a short tail stage), a vocabulary that
+    does not divide by the SM count, and a context long enough for several score / value iterations per thread."""
+    cfg = RM.LlamaCfg(hidden=4096, heads=32, inter=11008, layers=1, vocab=2048)
+    w = RM.random_weights(cfg, seed=7, std=0.02)
+    B, S, new = 2, 300, 3
+    rng = np.random.default_rng(9)
+    ids, lens = _prompts(rng, cfg, B, S, [S, 123])
+    for mode, int8_kv in (("fp16", True), ("w4", False), ("sq", True)):
+        fused, _ = _session(cfg, w, mode, int8_kv, max_batch=B, max_in=S, max_out=new, fused=True)
+        plug, _ = _session(cfg, w, mode, int8_kv, max_batch=B, max_in=S, max_out=new, fused=False)
+        f_logits, f_ids, f_launch = _run(fused, ids, lens, new)
+        p_logits, p_ids, _ = _run(plug, ids, lens, new)
+        assert set(f_launch) == {1}
+        tol = (3e-2 if mode == "sq" else 1e-2) * max(1.0, float(np.abs(p_logits).max()))
+        for s in range(new):
+            np.testing.assert_allclose(f_logits[:, s], p_logits[:, s], atol=tol, err_msg=f"{mode} step {s}")
+            if not np.array_equal(f_ids[:, s], p_ids[:, s]):
+                break
+        del fused, plug

@@ -26,7 +26,7 @@ def _to_torch(w):
     return out
 
 
-def _session(cfg, w, mode, int8_kv, max_batch, max_in, max_out, graph=True):
+def _session(cfg, w, mode, int8_kv, max_batch, max_in, max_out, graph=True, fused=None):
     from trtllm_llama_b200 import runtime as rt
     from trtllm_llama_b200.quantization import QuantMode
     qm = {"fp16": QuantMode(0), "w8": QuantMode.use_weight_only(False), "w4": QuantMode.use_weight_only(True),
@@ -37,7 +37,10 @@ def _session(cfg, w, mode, int8_kv, max_batch, max_in, max_out, graph=True):
                         inter_size=cfg.inter, rms_eps=cfg.eps, quant_mode=qm, max_batch_size=max_batch,
                         max_input_len=max_in, max_output_len=max_out)
     tensors = rt.build_engine_tensors(_to_torch(w), mc, kv_scale=4.0 / 127.0)
-    return rt.GenerationSession(mc, tensors, use_cuda_graph=graph), mc
+    sess = rt.GenerationSession(mc, tensors, use_cuda_graph=graph)
+    if fused is not None:      # None: the engine's default (one persistent kernel per step for <= 4 sequences)
+        sess.set_decode_mode(fused)
+    return sess, mc
 
 
 def _prompts(rng, cfg, B, S, lens):
@@ -155,8 +158,8 @@ def test_graph_replay_survives_a_change_of_prompt_length_and_batch():
     new = 8
     host = lambda a: torch.from_numpy(a).pin_memory()   # noqa: E731
     for mode, int8_kv in (("fp16", True), ("sq", False), ("w8", True)):
-        sg, _ = _session(cfg, w, mode, int8_kv, max_batch=4, max_in=16, max_out=new, graph=True)
-        se, _ = _session(cfg, w, mode, int8_kv, max_batch=4, max_in=16, max_out=new, graph=False)
+        sg, _ = _session(cfg, w, mode, int8_kv, max_batch=4, max_in=16, max_out=new, graph=True, fused=False)
+        se, _ = _session(cfg, w, mode, int8_kv, max_batch=4, max_in=16, max_out=new, graph=False, fused=False)
         rng = np.random.default_rng(12)
         for B, S, lens in ((2, 16, [16, 9]), (2, 11, [7, 11]), (4, 16, [16, 3, 12, 8]), (2, 16, [16, 9]), (2, 7, [7, 2])):
             ids, lens = _prompts(rng, cfg, B, S, lens)

@@ -56,6 +56,11 @@ SIGNATURES = {
     "tb_fill_int": (i32, [vp, i32, i32, vp]),
     "tb_copy": (i32, [vp, vp, sz, vp]),
     "tb_gather_logits": (i32, [vp, vp, i32, i32, i32, vp]),
+    "tb_decode_step_max_batch": (i32, []),
+    "tb_decode_step_create": (i32, [vp, vp, vp, vp]),
+    "tb_decode_step_destroy": (None, [vp]),
+    "tb_decode_step_launch": (i32, [vp, i32, vp]),
+    "tb_decode_step_info": (i32, [vp, i32, vp, vp, vp]),
     "tb_mma_peak": (i32, [i32, i32, i32, vp, C.POINTER(C.c_double), vp]),
 }
 
@@ -126,6 +131,8 @@ SIGNATURES.update({
     "tbrt_generate": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
     "tbrt_last_launches": (i64, [vp]),
     "tbrt_set_end_id": (i32, [vp, i32]),
+    "tbrt_set_decode_mode": (i32, [vp, i32]),
+    "tbrt_fused_step_available": (i32, [vp]),
     "tbrt_last_steps": (i32, [vp]),
     "tb_finished": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "tbrt_ar_handle": (i32, [vp, vp]),

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -130,6 +131,8 @@ struct tbrt_engine {
   std::map<int, int64_t> graph_nodes;
   std::map<int, int> eager_steps;
   cudaStream_t cap_stream = nullptr;
+  tb_decode_step* ds = nullptr; // whole-step persistent kernel (csrc/decode_step.cu); NULL when the configuration is not taken
+  int decode_mode = 1;          // 1: fused step kernel whenever available; 0: per-operator plugin schedule (CUDA graph)
   tb_ar* ar = nullptr;          // peer-memory all-reduce of the decode path (tensor parallel)
   bool ar_open = false;
   int ar_site = 0;              // call-site parity, reset per step (two calls per layer: even per step)
@@ -146,6 +149,7 @@ struct tbrt_engine {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (ar) tb_ar_destroy(ar);
+    if (ds) tb_decode_step_destroy(ds);
     for (void* p : allocs) cudaFree(p);
     if (h_flag) cudaFreeHost(h_flag);
   }
@@ -158,6 +162,8 @@ struct tbrt_engine {
   int layers_forward(int M, int S, bool context, cudaStream_t s);
   int head(int rows, const __half* src, cudaStream_t s);
   int step_body(cudaStream_t s);
+  void build_decode_step();
+  bool fused_step() const { return ds && decode_mode != 0 && B <= tb_decode_step_max_batch(); }
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -533,6 +539,28 @@ int tbrt_engine::step_body(cudaStream_t s) {
   return head(B, h, s);
 }
 
+// The whole decode step as one persistent kernel over the same weights, KV caches, activation arena and device-resident
+// step state the plugin schedule uses (either path can run any step).  Not an error when the configuration is not taken.
+void tbrt_engine::build_decode_step() {
+  static const bool off = getenv("TB_DECODE_STEP") && atoi(getenv("TB_DECODE_STEP")) == 0;
+  if (off || c.tp_size != 1) return;
+  tb_decode_step_config dc{};
+  dc.kind = c.mode; dc.layers = c.layers; dc.hidden = c.hidden; dc.heads_local = Hl; dc.inter_local = inter_l;
+  dc.vocab_local = vocab_l; dc.vocab = c.vocab; dc.max_batch = c.max_batch; dc.max_seq_len = S_max; dc.int8_kv = c.int8_kv;
+  dc.out_stride = c.max_output_len; dc.rms_eps = c.rms_eps; dc.tp_size = c.tp_size; dc.tp_rank = c.tp_rank;
+  std::vector<tb_decode_step_layer> dl(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    const LayerW& l = L[i];
+    dl[i] = tb_decode_step_layer{l.qkv.w, l.dense.w, l.fc_gate.w, l.proj.w, l.qkv.scale, l.dense.scale, l.fc_gate.scale,
+                                 l.proj.scale, l.ln_in, l.ln_post, kv[i], l.kv_oq, l.kv_qo};
+  }
+  tb_decode_step_buffers db{};
+  db.emb = emb; db.ln_f = ln_f; db.lm_head = lm_head; db.h_a = h; db.h_b = h2; db.qkv = qkv; db.att = att; db.act = act;
+  db.logits = logits; db.ids = d_ids; db.seq_lens = d_seq_lens; db.step_pos = d_step_pos; db.out_ids = d_out_ids;
+  db.next_ids = d_next; db.in_lens = d_in_lens; db.max_in = d_max_in;
+  if (tb_decode_step_create(&ds, &dc, dl.data(), &db) != 0) ds = nullptr;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -611,6 +639,7 @@ int tbrt_finalize(tbrt_engine* e) {
     return -1;
   RT_CUDA(cudaMemset(e->d_dummy_scale, 0, 4));
   if (c.tp_size > 1 && c.tp_size <= 8) RT_CALL(tb_ar_create(&e->ar, c.tp_rank, c.tp_size, (size_t) 8 * c.hidden * 2));
+  e->build_decode_step();
   RT_CUDA(cudaDeviceSynchronize());
   e->finalized = true;
   return 0;
@@ -620,6 +649,8 @@ size_t tbrt_device_bytes(const tbrt_engine* e) { return e->dev_bytes; }
 const float* tbrt_logits(const tbrt_engine* e) { return e->logits; }
 const int32_t* tbrt_output_ids(const tbrt_engine* e) { return e->d_out_ids; }
 int tbrt_set_end_id(tbrt_engine* e, int end_id) { e->end_id = end_id; return 0; }
+int tbrt_set_decode_mode(tbrt_engine* e, int mode) { e->decode_mode = mode ? 1 : 0; return 0; }
+int tbrt_fused_step_available(const tbrt_engine* e) { return e->ds ? tb_decode_step_max_batch() : 0; }
 int tbrt_last_steps(const tbrt_engine* e) { return e->last_steps; }
 void* tbrt_kv_cache(const tbrt_engine* e, int layer) { return (layer >= 0 && layer < (int) e->kv.size()) ? e->kv[layer] : nullptr; }
 int64_t tbrt_last_launches(const tbrt_engine* e) { return e->launches; }
@@ -660,6 +691,11 @@ int tbrt_step(tbrt_engine* e, tb_stream_t st) {
   if (e->S_in + e->steps_done + 1 >= e->S_max) return fail("KV cache is full");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
   e->steps_done += 1;
+  if (e->fused_step()) {
+    e->launches = 1;
+    RT_CALL(tb_decode_step_launch(e->ds, e->B, st));
+    return 0;
+  }
   if (!e->c.use_cuda_graph) { e->launches = 0; return e->step_body(s); }
   auto it = e->graphs.find(e->B);
   if (it == e->graphs.end()) {

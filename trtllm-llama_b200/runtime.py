@@ -184,6 +184,15 @@ class GenerationSession:
     def device_bytes(self):
         return lib.tbrt_device_bytes(self._e)
 
+    def set_decode_mode(self, fused: bool):
+        """True (default): generation steps run as one persistent kernel when the engine / batch allow it;
+        False: the per-operator plugin schedule (one IPluginV2DynamicExt.enqueue per operator, CUDA graph)."""
+        lib.tbrt_set_decode_mode(self._e, int(bool(fused)))
+
+    @property
+    def fused_step_max_batch(self):
+        return lib.tbrt_fused_step_available(self._e)
+
     @property
     def last_launches(self):
         return lib.tbrt_last_launches(self._e)
