@@ -142,6 +142,19 @@ int tb_copy(void* dst, const void* src, size_t bytes, tb_stream_t s); /* device-
 /* in [tp, rows, vocab_local] fp16 (all-gathered vocab-parallel lm_head) -> out [rows, tp*vocab_local] fp32 */
 int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int tp, tb_stream_t s);
 
+/* ---- sampling beyond greedy: temperature, top-k, top-p, top-k + top-p ---------------------------------
+ * replaces the sampling half of DynamicDecodeOp (T/cpp/tensorrt_llm/thop/dynamicDecodeOp.cpp:359-363):
+ * K/samplingPenaltyKernels.cu:77-93 (temperature), K/samplingTopKKernels.cu:118-319 (top_k > 0: the k largest logits,
+ * r = u * top_p * sum exp(l - l_max), walk in descending order), K/samplingTopPKernels.cu:882-1010 (top_k == 0:
+ * softmax, r = u * top_p, first token of the descending order whose inclusive cumulative probability reaches r).
+ * u in (0, 1] is word 0 of Philox4x32-10(counter = (step, 0, row, 0), key = seed) under curand_uniform's mapping;
+ * step is read from *step_dev when step_dev != NULL (CUDA-graph replay).  logits fp32 [rows, vocab_stride];
+ * finished (optional, [rows]): finished rows emit end_id; uniform_out (optional, [rows]) receives u.
+ * top_k <= 1024, 0 < top_p <= 1, vocab <= 51200.                                                               */
+int tb_sample(int* out_ids, const float* logits, int rows, int vocab, int vocab_stride, int top_k, float top_p,
+              float temperature, unsigned long long seed, const int* step_dev, int step, const int* finished,
+              int end_id, float* uniform_out, tb_stream_t stream);
+
 /* ---- whole decode step in one persistent kernel (1..tb_decode_step_max_batch() token rows) -----------------------
  * replaces, per generated token, the plugin schedule of GenerationSession.decode's step
  * (T/tensorrt_llm/runtime/generation.py:852-963): every layer's projections (Gemm / WeightOnlyQuantMatmul /

@@ -79,6 +79,11 @@ int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_l
 int tbrt_ar_handle(tbrt_engine* e, void* out64);
 int tbrt_ar_open(tbrt_engine* e, const void* handles);
 int tbrt_set_end_id(tbrt_engine* e, int end_id);
+/* SamplingConfig (T/tensorrt_llm/runtime/generation.py:119-138): top_k = 1 (default) is greedy arg-max; top_k > 1 samples
+ * among the k largest logits (top_p > 0 additionally restricts to that share of their mass); top_k = 0 with top_p > 0 is
+ * nucleus sampling over the vocabulary; temperature scales the logits first (tb_sample).  The random stream is keyed by
+ * (seed, generation step, batch row).  Beam search (num_beams > 1) is not built. */
+int tbrt_set_sampling(tbrt_engine* e, int top_k, float top_p, float temperature, unsigned long long seed);
 /* Generation steps run as ONE persistent kernel (tb_decode_step_*) whenever the engine's configuration and the batch allow
  * it (mode 1, default); mode 0 forces the per-operator plugin schedule (IPluginV2DynamicExt::enqueue per operator, CUDA
  * graph) — same weights, caches and step state, so the two can be compared step by step.

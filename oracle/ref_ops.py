@@ -405,3 +405,73 @@ def greedy_argmax(logits):
     """top_k=1 sampling == argmax with lowest index on ties (DynamicDecodeOp top-k=1;
     T/tensorrt_llm/runtime/generation.py:119-131 SamplingConfig defaults)."""
     return np.argmax(np.asarray(logits, F32), axis=-1).astype(np.int32)
+
+
+# --------------------------------------------------------------------------- #
+# f4: sampling (top-k / top-p), K/samplingTopKKernels.cu, K/samplingTopPKernels.cu, K/samplingPenaltyKernels.cu
+# --------------------------------------------------------------------------- #
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., the generator behind curand's Philox): counter 4 x u32, key 2 x u32 -> 4 x u32."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [int(x) & 0xFFFFFFFF for x in counter]
+    k = [int(x) & 0xFFFFFFFF for x in key]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+    return c
+
+
+def sampling_uniform(seed, step, row):
+    """The uniform in (0, 1] a sampling kernel draws for (seed, generation step, batch row): word 0 of
+    Philox4x32-10(counter = (step, 0, row, 0), key = seed) mapped as curand_uniform does (x * 2^-32 + 2^-33).
+    The reference draws from curand's XORWOW state initialised with curand_init(seed, 0, 0) for EVERY row
+    (samplingTopKKernels.cu:38-62: all rows share one stream); a counter-based generator keyed by (step, row) needs no
+    state buffer, survives CUDA-graph replay and gives every row its own stream — same distribution, different numbers."""
+    x = philox4x32_10((step, 0, row, 0), (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))[0]
+    return F32(F32(x) * F32(2.3283064365386963e-10) + F32(1.1641532182693481e-10))
+
+
+def sample_top_k_top_p(logits, top_k, top_p, temperature, uniforms):
+    """logits [B, V] fp32 -> ids [B] (and the per-row candidate tables, for tolerance-aware tests).
+
+    temperature: logits * (1 / (T + 1e-6))                                   (samplingPenaltyKernels.cu:77-93)
+    top_k > 0:   the k largest logits (lowest index wins ties), e_i = exp(l_i - l_max), r = u * top_p * sum(e);
+                 walk the candidates in descending order subtracting e_i, take the first with r <= 0 (or the last)
+                                                                              (samplingTopKKernels.cu:197-319)
+    top_k == 0:  probabilities softmax(l), sorted descending (stable), r = u * top_p; first token whose inclusive
+                 cumulative probability reaches r                             (samplingTopPKernels.cu:882-1010, :1160-1236)"""
+    logits = np.asarray(logits, dtype=F32)
+    B, V = logits.shape
+    inv_t = F32(1.0) / (F32(temperature) + F32(1e-6))
+    ids, tables = np.zeros(B, np.int32), []
+    for b in range(B):
+        l = (logits[b] * inv_t).astype(F32)
+        u = F32(uniforms[b])
+        if top_k > 0:
+            k = min(int(top_k), V)
+            order = np.lexsort((np.arange(V), -l.astype(np.float64)))[:k]      # descending value, ascending index
+            e = np.exp((l[order] - l[order[0]]).astype(F32)).astype(F32)
+            s = F32(0)
+            for x in e:
+                s = F32(s + x)
+            r = F32(F32(u * F32(top_p)) * s)
+            pick = k - 1
+            for i in range(k):
+                r = F32(r - e[i])
+                if r <= 0:
+                    pick = i
+                    break
+            ids[b] = order[pick]
+            tables.append((order, e, s))
+        else:
+            m = l.max()
+            e = np.exp((l - m).astype(F32)).astype(F32)
+            p = (e / e.sum(dtype=F32)).astype(F32)
+            order = np.lexsort((np.arange(V), -p.astype(np.float64)))
+            c = np.cumsum(p[order], dtype=F32)
+            r = F32(u * F32(top_p))
+            j = int(np.searchsorted(c, r, side="left"))
+            ids[b] = order[j] if j < V else order[0]      # never reached: the scan leaves the top token (:957)
+            tables.append((order, p, c))
+    return ids, tables

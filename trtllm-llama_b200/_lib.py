@@ -56,6 +56,7 @@ SIGNATURES = {
     "tb_fill_int": (i32, [vp, i32, i32, vp]),
     "tb_copy": (i32, [vp, vp, sz, vp]),
     "tb_gather_logits": (i32, [vp, vp, i32, i32, i32, vp]),
+    "tb_sample": (i32, [vp, vp, i32, i32, i32, i32, f32, f32, C.c_uint64, vp, i32, vp, i32, vp, vp]),
     "tb_decode_step_max_batch": (i32, []),
     "tb_decode_step_create": (i32, [vp, vp, vp, vp]),
     "tb_decode_step_destroy": (None, [vp]),
@@ -132,6 +133,7 @@ SIGNATURES.update({
     "tbrt_last_launches": (i64, [vp]),
     "tbrt_set_end_id": (i32, [vp, i32]),
     "tbrt_set_decode_mode": (i32, [vp, i32]),
+    "tbrt_set_sampling": (i32, [vp, i32, f32, f32, C.c_uint64]),
     "tbrt_fused_step_available": (i32, [vp]),
     "tbrt_last_steps": (i32, [vp]),
     "tb_finished": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -82,6 +82,16 @@ __host__ __device__ constexpr int epc_of(int kind) { return kind == kF16 ? 8 : (
 template <int KIND, int MB> struct XF { static constexpr int v = KIND == kA8W8 ? kXInt8 : (MB == 1 ? kXFloat : kXHalf); };
 __host__ __device__ constexpr int xbytes_of(int xf) { return xf == kXFloat ? 4 : (xf == kXHalf ? 2 : 1); }
 
+// Staged activations are stored chunk-interleaved: a "chunk" is the E activations that meet one 16-byte weight chunk
+// (E = 8 / 16 / 32 elements = E * XB bytes = NV 16-byte vectors).  Lane l of a warp works on chunk c = l + 32 u, so vector
+// j of 32 consecutive chunks is stored contiguously: vec(c, j) = ((c / 32) * NV + j) * 32 + (c % 32).  A warp's LDS.128
+// for one j then covers 512 contiguous bytes (conflict-free); the natural layout put consecutive lanes E * XB bytes
+// apart (2-, 4- and 8-way bank conflicts for fp16 / int8 / int4 weights against fp32 activations).
+__host__ __device__ constexpr int xrow_bytes(int K, int E, int XB) { return ((K / E + 31) / 32) * 32 * E * XB; }
+__device__ __forceinline__ uint32_t xvec_off(int c, int j, int NV) {
+  return (uint32_t) (((c >> 5) * NV + j) * 32 + (c & 31)) * 16u;
+}
+
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
 __device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
@@ -149,27 +159,60 @@ __device__ __forceinline__ Phase phase_of(const Params& p, int idx) {
   }
 }
 
-// ---- producer: every weight byte this CTA will need during the step, in order, regardless of phase barriers -------------
-__device__ __forceinline__ void producer(const Params& p, uint8_t* ring, uint64_t* full, uint64_t* empty) {
+// ---- producer warp: every weight byte this CTA will need during the step, in order, regardless of phase barriers -------
+// One thread needs ~200 cycles per copy (mbarrier wait on the slot, expect_tx, cp.async.bulk): at one 4 KB stage per
+// ~180 cycles needed per SM that serial chain capped the kernel at ~3 TB/s.  The ring therefore has S = 32 (or 16) slots
+// and producer lane l OWNS slot l: it issues the stages l, l + S, l + 2S, ... of the step's global stage sequence, so the
+// uses of one slot are issued in order by one thread (mbarrier parity waits are only sound for consecutive phases) while
+// up to 32 copies are in flight.  The lanes poll their slots with the non-blocking test_wait and the warp stays
+// converged: a lane whose slot is still being read simply skips the round.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__device__ __forceinline__ void producer(const Params& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane) {
   const uint64_t pol = policy_evict_first();     // weights are read once per step: keep K/V and activations in L2
-  const int S = p.stages;
-  int slot = 0;
-  uint32_t par = 0;
-  for (int idx = 0; idx <= 4 * p.n_layers; ++idx) {
-    const Phase f = phase_of(p, idx);
-    const int rows = f.o1 - f.o0;
-    for (int r = 0; r < f.R; ++r) {
-      const uint8_t* src = f.w + (size_t) (r * f.n_out + f.o0) * f.rowbytes;
-      for (int row = 0; row < rows; ++row) {
-        for (uint32_t off = 0; off < f.rowbytes; off += kSeg) {
-          const uint32_t bytes = min((uint32_t) kSeg, f.rowbytes - off);
-          mbar_wait(&empty[slot], par ^ 1);
-          mbar_expect_tx(&full[slot], bytes);
-          bulk_load_1d_hint(ring + (size_t) slot * kSeg, src + off, bytes, &full[slot], pol);
-          if (++slot == S) { slot = 0; par ^= 1; }
-        }
-        src += f.rowbytes;
-      }
+  const uint32_t S = (uint32_t) p.stages;
+  const int last = 4 * p.n_layers;
+  bool done = lane >= (int) S;
+  uint32_t gi = (uint32_t) lane, use = 0, gbase = 0;
+  int idx = 0;
+  Phase f = phase_of(p, 0);
+  uint32_t nst = (uint32_t) (f.R * (f.o1 - f.o0) * f.nseg);
+  const long long t0 = clock64();
+  for (;;) {
+    while (!done && gi >= gbase + nst) {          // my next stage lies in a later projection
+      gbase += nst;
+      if (++idx > last) { done = true; break; }
+      f = phase_of(p, idx);
+      nst = (uint32_t) (f.R * (f.o1 - f.o0) * f.nseg);
+    }
+    if (__all_sync(0xffffffffu, done)) break;
+    if (!done && mbar_test_wait(&empty[lane], (use & 1u) ^ 1u)) {
+      const int i = (int) (gi - gbase);
+      const int per_r = (f.o1 - f.o0) * f.nseg;
+      const int r = i >= per_r ? 1 : 0;
+      const int rem = i - r * per_r;
+      const int row = rem / f.nseg, seg = rem - row * f.nseg;
+      const uint32_t off = (uint32_t) seg * kSeg;
+      const uint32_t bytes = min((uint32_t) kSeg, f.rowbytes - off);
+      const uint8_t* src = f.w + (size_t) (r * f.n_out + f.o0 + row) * f.rowbytes + off;
+      mbar_expect_tx(&full[lane], bytes);
+      bulk_load_1d_hint(ring + (size_t) lane * kSeg, src, bytes, &full[lane], pol);
+      gi += S;
+      ++use;
+    }
+    if (clock64() - t0 > 20000000000ll) {         // a wedged pipeline must surface as a trapped kernel, never as a hang
+      if (lane == 0) printf("[trtllm_b200] decode_step producer timed out (block %d)\n", blockIdx.x);
+      __trap();
     }
   }
 }
@@ -189,11 +232,12 @@ __device__ __forceinline__ float cta_reduce(float v, float* red, bool is_max, in
 // ---- activation staging with the fused prologue (same arithmetic as gemv.cu / norm_quant.cu) ----------------------------
 // mode 0: copy; 1: RMSNorm; 2: RMSNorm + dynamic per-token int8; 3: dynamic per-token int8.  rows[m]: fp16 [K] in global
 // memory, written by other CTAs earlier in this launch (read through L2).
-template <int XFMT, int MB>
+template <int XFMT, int MB, int E>
 __device__ __forceinline__ void stage_x(const Params& p, const __half* const (&rows)[MB], int K, int mode, const __half* gamma,
                                         uint8_t* xs, float* srow, float* red, int ctid) {
   constexpr int XB = xbytes_of(XFMT);
-  const int xstride = K * XB;
+  constexpr int NV = E * XB / 16;                          // 16-byte vectors per chunk
+  const int xstride = xrow_bytes(K, E, XB);
   constexpr int IT = 3;                                   // K <= 3 * 512 * 8 = 12288 stays in registers
 #pragma unroll 1
   for (int m = 0; m < MB; ++m) {
@@ -266,7 +310,8 @@ __device__ __forceinline__ void stage_x(const Params& p, const __half* const (&r
           uint2 o;
           o.x = pack4_i8(f[0], f[1], f[2], f[3]);
           o.y = pack4_i8(f[4], f[5], f[6], f[7]);
-          *reinterpret_cast<uint2*>(xs + (size_t) m * xstride + i) = o;
+          const int c = i / E, e = i % E;                   // 8 int8 = half of the chunk's single vector
+          *reinterpret_cast<uint2*>(xs + (size_t) m * xstride + xvec_off(c, e / 16, NV) + (e % 16)) = o;
         }
       }
     } else if constexpr (XFMT == kXFloat) {
@@ -276,16 +321,17 @@ __device__ __forceinline__ void stage_x(const Params& p, const __half* const (&r
         if (i < K) {
           const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
           const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
-          float4* dst = reinterpret_cast<float4*>(xs + (size_t) m * xstride + (size_t) i * 4);
-          dst[0] = make_float4(a.x, a.y, b.x, b.y);
-          dst[1] = make_float4(c.x, c.y, d.x, d.y);
+          const int ch = i / E, j = (i % E) / 4;              // 8 floats = vectors j, j + 1 of chunk ch
+          uint8_t* row = xs + (size_t) m * xstride;
+          *reinterpret_cast<float4*>(row + xvec_off(ch, j, NV)) = make_float4(a.x, a.y, b.x, b.y);
+          *reinterpret_cast<float4*>(row + xvec_off(ch, j + 1, NV)) = make_float4(c.x, c.y, d.x, d.y);
         }
       }
     } else {
 #pragma unroll
       for (int it = 0; it < IT; ++it) {
         const int i = (it * kCT + ctid) * 8;
-        if (i < K) *reinterpret_cast<uint4*>(xs + (size_t) m * xstride + (size_t) i * 2) = raw[it];
+        if (i < K) *reinterpret_cast<uint4*>(xs + (size_t) m * xstride + xvec_off(i / E, (i % E) / 8, NV)) = raw[it];
       }
     }
   }
@@ -294,12 +340,13 @@ __device__ __forceinline__ void stage_x(const Params& p, const __half* const (&r
 
 // ---- one 16-byte weight chunk against the staged activations of MB rows ------------------------------------------------
 template <int KIND, int XFMT, int MB>
-__device__ __forceinline__ void chunk_dot(const uint4& wq, const uint8_t* xs, int k0, int xstride, float (&acc)[MB],
+__device__ __forceinline__ void chunk_dot(const uint4& wq, const uint8_t* xs, int c, int xstride, float (&acc)[MB],
                                           int (&iacc)[MB]) {
+  constexpr int NV = epc_of(KIND) * xbytes_of(XFMT) / 16;
   if constexpr (KIND == kA8W8) {
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
-      const uint4 xv = lds128(xs + (size_t) m * xstride + k0);
+      const uint4 xv = lds128(xs + (size_t) m * xstride + xvec_off(c, 0, NV));
       iacc[m] = __dp4a((int) wq.x, (int) xv.x, iacc[m]);
       iacc[m] = __dp4a((int) wq.y, (int) xv.y, iacc[m]);
       iacc[m] = __dp4a((int) wq.z, (int) xv.z, iacc[m]);
@@ -327,10 +374,10 @@ __device__ __forceinline__ void chunk_dot(const uint4& wq, const uint8_t* xs, in
     for (int m = 0; m < MB; ++m) {
       float a0 = 0.f, a1 = 0.f;
       if constexpr (XFMT == kXFloat) {
-        const float4* xp = reinterpret_cast<const float4*>(xs + (size_t) m * xstride + (size_t) k0 * 4);
+        const uint8_t* xp = xs + (size_t) m * xstride + xvec_off(c, 0, NV);
 #pragma unroll
         for (int q = 0; q < E / 4; ++q) {
-          const float4 xv = xp[q];
+          const float4 xv = *reinterpret_cast<const float4*>(xp + q * 512);
           const float2 wa = __half22float2(wh[2 * q]), wb = __half22float2(wh[2 * q + 1]);
           a0 = fmaf(wa.x, xv.x, a0);
           a1 = fmaf(wa.y, xv.y, a1);
@@ -338,10 +385,10 @@ __device__ __forceinline__ void chunk_dot(const uint4& wq, const uint8_t* xs, in
           a1 = fmaf(wb.y, xv.w, a1);
         }
       } else {
-        const uint4* xp = reinterpret_cast<const uint4*>(xs + (size_t) m * xstride + (size_t) k0 * 2);
+        const uint8_t* xp = xs + (size_t) m * xstride + xvec_off(c, 0, NV);
 #pragma unroll
         for (int q = 0; q < E / 8; ++q) {
-          const uint4 xv = xp[q];
+          const uint4 xv = lds128(xp + q * 512);
           const __half2* x2 = reinterpret_cast<const __half2*>(&xv);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -360,31 +407,37 @@ __device__ __forceinline__ void chunk_dot(const uint4& wq, const uint8_t* xs, in
 template <int KIND, int XFMT, int MB>
 __device__ __forceinline__ void run_phase(const Phase& f, uint32_t g, int S, const uint8_t* ring, uint64_t* full,
                                           uint64_t* empty, const uint8_t* xs, float* part, int cwarp, int lane) {
-  constexpr int E = epc_of(KIND);
   const int rows = f.o1 - f.o0;
   const int nst = f.R * rows * f.nseg;
-  const int xstride = f.K * xbytes_of(XFMT);
+  const int xstride = xrow_bytes(f.K, epc_of(KIND), xbytes_of(XFMT));
+  // stage i of this phase: ring slot (g + i) % S with use count (g + i) / S, row segment i % nseg — kept incrementally
+  uint32_t q = (g + (uint32_t) cwarp) / (uint32_t) S;
+  int slot = (int) (g + (uint32_t) cwarp - q * (uint32_t) S);
+  int seg = cwarp % f.nseg;
+  const int seg_step = kCW % f.nseg;
   for (int i = cwarp; i < nst; i += kCW) {
-    const uint32_t gi = g + (uint32_t) i;
-    const uint32_t q = gi / (uint32_t) S;
-    const int slot = (int) (gi - q * (uint32_t) S);
-    const int seg = i % f.nseg;
     const uint32_t off = (uint32_t) seg * kSeg;
     const int nchunks = (int) (min((uint32_t) kSeg, f.rowbytes - off) >> 4);
-    const int kbase = (int) (off >> 4) * E;
+    const int cbase = (int) (off >> 4);
     const uint8_t* st = ring + (size_t) slot * kSeg;
+    const uint32_t parity = q & 1u;
+    const int slot_now = slot;
+    slot += kCW;
+    while (slot >= S) { slot -= S; ++q; }
+    seg += seg_step;
+    if (seg >= f.nseg) seg -= f.nseg;
     float acc[MB];
     int iacc[MB];
 #pragma unroll
     for (int m = 0; m < MB; ++m) { acc[m] = 0.f; iacc[m] = 0; }
-    mbar_wait(&full[slot], q & 1u);
+    mbar_wait(&full[slot_now], parity);
 #pragma unroll 4
     for (int c = lane; c < nchunks; c += 32) {
       const uint4 wq = lds128(st + (size_t) c * 16);
-      chunk_dot<KIND, XFMT, MB>(wq, xs, kbase + c * E, xstride, acc, iacc);
+      chunk_dot<KIND, XFMT, MB>(wq, xs, cbase + c, xstride, acc, iacc);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);      // the slot is free as soon as every lane has read its chunks
+    if (lane == 0) mbar_arrive(&empty[slot_now]);      // the slot is free as soon as every lane has read its chunks
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
       if constexpr (KIND == kA8W8) {
@@ -650,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
   }
   __syncthreads();
   if (tid >= kCT) {
-    if (tid == kCT) producer(p, ring, full, empty);
+    producer(p, ring, full, empty, tid - kCT);
     return;
   }
 
@@ -679,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
     {
       const Phase f = phase_of(p, 4 * li);
       if (target) grid_wait(p.bar, target, ctid);
-      stage_x<XM, MB>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, L.ln_in, xs, srow, red, ctid);
+      stage_x<XM, MB, epc_of(KIND)>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, L.ln_in, xs, srow, red, ctid);
       run_phase<KIND, XM, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
       epilogue<KIND, MB>(p, f, 0, part, srow, none, p.qkv, 3 * p.hid_l, lgs, ctid);
       g += stages_of(f);
@@ -705,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
 #pragma unroll
       for (int m = 0; m < MB; ++m) arow[m] = m < p.B ? p.att + (size_t) m * p.hid_l : nullptr;
       grid_wait(p.bar, target, ctid);
-      stage_x<XM, MB>(p, arow, p.hid_l, KIND == kA8W8 ? 3 : 0, nullptr, xs, srow, red, ctid);
+      stage_x<XM, MB, epc_of(KIND)>(p, arow, p.hid_l, KIND == kA8W8 ? 3 : 0, nullptr, xs, srow, red, ctid);
       run_phase<KIND, XM, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
       epilogue<KIND, MB>(p, f, 0, part, srow, hrow, p.hB, p.hidden, lgs, ctid);
       g += stages_of(f);
@@ -718,7 +771,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
     {
       const Phase f = phase_of(p, 4 * li + 2);
       grid_wait(p.bar, target, ctid);
-      stage_x<XM, MB>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, L.ln_post, xs, srow, red, ctid);
+      stage_x<XM, MB, epc_of(KIND)>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, L.ln_post, xs, srow, red, ctid);
       run_phase<KIND, XM, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
       epilogue<KIND, MB>(p, f, 1, part, srow, none, p.act, p.inter_l, lgs, ctid);
       g += stages_of(f);
@@ -732,7 +785,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
 #pragma unroll
       for (int m = 0; m < MB; ++m) arow[m] = m < p.B ? p.act + (size_t) m * p.inter_l : nullptr;
       grid_wait(p.bar, target, ctid);
-      stage_x<XM, MB>(p, arow, p.inter_l, KIND == kA8W8 ? 3 : 0, nullptr, xs, srow, red, ctid);
+      stage_x<XM, MB, epc_of(KIND)>(p, arow, p.inter_l, KIND == kA8W8 ? 3 : 0, nullptr, xs, srow, red, ctid);
       run_phase<KIND, XM, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
       epilogue<KIND, MB>(p, f, 0, part, srow, hrow, p.hA, p.hidden, lgs, ctid);
       g += stages_of(f);
@@ -747,7 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
 #pragma unroll
     for (int m = 0; m < MB; ++m) hrow[m] = m < p.B ? p.hA + (size_t) m * p.hidden : nullptr;
     grid_wait(p.bar, target, ctid);
-    stage_x<XL, MB>(p, hrow, p.hidden, 1, p.ln_f, xs, srow, red, ctid);
+    stage_x<XL, MB, epc_of(kF16)>(p, hrow, p.hidden, 1, p.ln_f, xs, srow, red, ctid);
     run_phase<kF16, XL, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
     epilogue<kF16, MB>(p, f, 2, part, srow, none, nullptr, 0, lgs, ctid);
     cbar();
@@ -909,13 +962,15 @@ int tb_decode_step_create(tb_decode_step** out, const tb_decode_step_config* c, 
     }
     const int xf_model = c->kind == 3 ? ds::kXInt8 : (MB == 1 ? ds::kXFloat : ds::kXHalf);
     const int xf_lm = MB == 1 ? ds::kXFloat : ds::kXHalf;
-    size_t xs = (size_t) MB * kmax * ds::xbytes_of(xf_model);
-    xs = std::max(xs, (size_t) MB * c->hidden * ds::xbytes_of(xf_lm));
+    size_t xs = (size_t) MB * ds::xrow_bytes(kmax, epc, ds::xbytes_of(xf_model));
+    xs = std::max(xs, (size_t) MB * ds::xrow_bytes(c->hidden, 8, ds::xbytes_of(xf_lm)));
     xs = std::max(xs, attn);
     const uint32_t ring_off = (uint32_t) ((ds::kOffXs + xs + 1023) & ~(size_t) 1023);
+    // S must be a multiple of the consumer warps (a slot is then always read by the same warp, in order) and at most the
+    // 32 producer lanes (a slot is always filled by the same lane, in order): 32 or 16
     int stages = (int) (((size_t) smem_max - ring_off) / ds::kSeg);
-    if (stages > ds::kMaxStages) stages = ds::kMaxStages;
-    if (stages < 8) { delete d; return -6; }
+    stages = stages >= 32 ? 32 : (stages >= 16 ? 16 : 0);
+    if (stages == 0) { delete d; return -6; }
     d->stages[mi] = stages;
     d->ring_off[mi] = ring_off;
     d->smem[mi] = ring_off + (size_t) stages * ds::kSeg;

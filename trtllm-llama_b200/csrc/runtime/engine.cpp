@@ -133,6 +133,11 @@ struct tbrt_engine {
   cudaStream_t cap_stream = nullptr;
   tb_decode_step* ds = nullptr; // whole-step persistent kernel (csrc/decode_step.cu); NULL when the configuration is not taken
   int decode_mode = 1;          // 1: fused step kernel whenever available; 0: per-operator plugin schedule (CUDA graph)
+  // sampling (SamplingConfig, generation.py:119-138): top_k = 1 / top_p = 0 is greedy arg-max
+  int top_k = 1;
+  float top_p = 0.f, temperature = 1.f;
+  unsigned long long seed = 0;
+  bool sampling() const { return top_k != 1 && !(top_k == 0 && top_p <= 0.f); }
   tb_ar* ar = nullptr;          // peer-memory all-reduce of the decode path (tensor parallel)
   bool ar_open = false;
   int ar_site = 0;              // call-site parity, reset per step (two calls per layer: even per step)
@@ -163,7 +168,7 @@ struct tbrt_engine {
   int head(int rows, const __half* src, cudaStream_t s);
   int step_body(cudaStream_t s);
   void build_decode_step();
-  bool fused_step() const { return ds && decode_mode != 0 && B <= tb_decode_step_max_batch(); }
+  bool fused_step() const { return ds && decode_mode != 0 && !sampling() && B <= tb_decode_step_max_batch(); }
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -526,7 +531,14 @@ int tbrt_engine::head(int rows, const __half* src, cudaStream_t s) {
     RT_CALL(allgather->enqueue(id, od, in, out, workspace, s));
     RT_CALL(tb_gather_logits(logits, logits_h + (size_t) rows * vocab_l, rows, vocab_l, c.tp_size, s));
   }
-  RT_CALL(tb_argmax(d_next, logits, rows, c.vocab, c.vocab, s));
+  if (sampling()) {
+    // the generation step (column of output_ids being produced) keys the random stream: read on the device, so the
+    // captured step graph draws fresh numbers on every replay
+    RT_CALL(tb_sample(d_next, logits, rows, c.vocab, c.vocab, top_k, top_p > 0.f ? top_p : 1.f, temperature, seed, d_step_pos, 0,
+                      nullptr, end_id, nullptr, s));
+  } else {
+    RT_CALL(tb_argmax(d_next, logits, rows, c.vocab, c.vocab, s));
+  }
   RT_CALL(tb_advance_step(d_next, d_ids, d_out_ids, d_seq_lens, d_step_pos, rows, c.max_output_len, s));
   return 0;
 }
@@ -649,6 +661,18 @@ size_t tbrt_device_bytes(const tbrt_engine* e) { return e->dev_bytes; }
 const float* tbrt_logits(const tbrt_engine* e) { return e->logits; }
 const int32_t* tbrt_output_ids(const tbrt_engine* e) { return e->d_out_ids; }
 int tbrt_set_end_id(tbrt_engine* e, int end_id) { e->end_id = end_id; return 0; }
+int tbrt_set_sampling(tbrt_engine* e, int top_k, float top_p, float temperature, unsigned long long seed) {
+  if (top_k < 0 || top_k > 1024 || top_p < 0.f || top_p > 1.f || !(temperature >= 0.f)) return fail("bad sampling parameters");
+  const bool changed = e->top_k != top_k || e->top_p != top_p || e->temperature != temperature || e->seed != seed;
+  e->top_k = top_k; e->top_p = top_p; e->temperature = temperature; e->seed = seed;
+  if (changed) {                       // captured step graphs bake the sampling kernel and its arguments
+    for (auto& g : e->graphs) cudaGraphExecDestroy(g.second);
+    e->graphs.clear();
+    e->graph_nodes.clear();
+    e->eager_steps.clear();
+  }
+  return 0;
+}
 int tbrt_set_decode_mode(tbrt_engine* e, int mode) { e->decode_mode = mode ? 1 : 0; return 0; }
 int tbrt_fused_step_available(const tbrt_engine* e) { return e->ds ? tb_decode_step_max_batch() : 0; }
 int tbrt_last_steps(const tbrt_engine* e) { return e->last_steps; }

@@ -211,6 +211,20 @@ def context_attention(qkv, kv_cache, input_lengths, *, num_heads, head_size, kv_
     return out
 
 
+def sample(logits, top_k=0, top_p=1.0, temperature=1.0, seed=0, step=0, finished=None, end_id=2, return_uniform=False):
+    """DynamicDecodeOp's sampling for one step (T/cpp/tensorrt_llm/thop/dynamicDecodeOp.cpp:359-363): logits fp32 [B, V]
+    -> ids int32 [B].  ``step`` may be a device int32 tensor (graph-replayable counter)."""
+    _chk_cuda(logits, finished)
+    B, V = logits.shape
+    out = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    u = torch.empty((B,), dtype=torch.float32, device=logits.device) if return_uniform else None
+    step_dev = step if isinstance(step, torch.Tensor) else None
+    check(lib.tb_sample(_p(out), _p(logits), B, V, logits.stride(0), int(top_k), float(top_p), float(temperature), int(seed),
+                        _p(step_dev), 0 if step_dev is not None else int(step), _p(finished), int(end_id), _p(u), _stream()),
+          "tb_sample")
+    return (out, u) if return_uniform else out
+
+
 # ------------------------------------------------------------------------------------------------
 def embedding(ids, table):
     _chk_cuda(ids, table)

@@ -51,7 +51,9 @@ class ModelConfig:
 
 @dataclass
 class SamplingConfig:
-    """generation.py:119-138.  Only the greedy defaults (top_k = 1, num_beams = 1) are built."""
+    """generation.py:119-138.  top_k = 1 (default) is greedy; top_k > 1, top_p in (0, 1] and temperature select the
+    sampling kernel (tb_sample: top-k, top-p, top-k + top-p), seeded by ``random_seed``.  Beam search (num_beams > 1),
+    repetition / length penalties and min_length are not built and are rejected, not ignored."""
     end_id: int = 2
     pad_id: int = 2
     num_beams: int = 1
@@ -61,6 +63,7 @@ class SamplingConfig:
     length_penalty: float = 1.0
     repetition_penalty: float = 1.0
     min_length: int = 1
+    random_seed: int = 0
     output_log_probs: bool = field(init=False, default=False)
 
 
@@ -266,8 +269,12 @@ class GenerationSession:
         tensors (pinned for asynchronous copies); returns HOST output ids [B, max_new_tokens] — the host<->device
         copies are part of the call, as in the reference's run.py timing (LQ/run.py:117-198)."""
         sc = sampling_config or SamplingConfig()
-        if sc.num_beams != 1 or sc.top_k != 1:
-            raise NotImplementedError("only greedy decoding (top_k=1, num_beams=1) is built (SURVEY 8f-4)")
+        if sc.num_beams != 1:
+            raise NotImplementedError("beam search (num_beams > 1) is not built (SURVEY 8f-4)")
+        if sc.repetition_penalty != 1.0 or sc.length_penalty != 1.0 or sc.min_length > 1:
+            raise NotImplementedError("repetition_penalty / length_penalty / min_length are not built (SURVEY 8f-4)")
+        if lib.tbrt_set_sampling(self._e, int(sc.top_k), float(sc.top_p), float(sc.temperature), int(sc.random_seed)):
+            raise _err("tbrt_set_sampling")
         B, S = input_ids.shape
         n = max_new_tokens or self.max_new_tokens
         if input_ids.is_cuda or input_ids.dtype != torch.int32 or not input_ids.is_contiguous():
