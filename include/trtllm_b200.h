@@ -191,6 +191,10 @@ void tb_decode_step_destroy(tb_decode_step* d);
 int tb_decode_step_launch(tb_decode_step* d, int batch, tb_stream_t stream);
 /* ring depth (4 KB stages), dynamic shared memory and grid of the launch for `batch` rows (diagnostics) */
 int tb_decode_step_info(const tb_decode_step* d, int batch, int* stages, size_t* smem_bytes, int* grid);
+/* diagnostics: record %globaltimer stamps of every CTA's pipeline in the next launches (per projection: after the grid
+ * barrier, after activation staging, after the last weight stage, after the epilogue; per attention phase: after the
+ * barrier, after the items); out_host (grid x 2048 u64, may be NULL) receives what was recorded so far. */
+int tb_decode_step_trace(tb_decode_step* d, int enable, unsigned long long* out_host);
 
 /* ---- measurement support: tensor-pipe ceiling of this GPU at the clock it sustains (SURVEY 8d asks for a measured
  * tcgen05 kind::i8 peak; MEASURED_PEAKS.json has HBM and cuBLAS bf16 only).  Launches `ctas` CTAs, each issuing

@@ -90,6 +90,8 @@ int tbrt_set_sampling(tbrt_engine* e, int top_k, float top_p, float temperature,
  * tbrt_fused_step_available: largest batch the fused step takes for this engine (0: not available). */
 int tbrt_set_decode_mode(tbrt_engine* e, int mode);
 int tbrt_fused_step_available(const tbrt_engine* e);
+/* the engine's tb_decode_step (NULL when not available), for tb_decode_step_info / tb_decode_step_trace */
+void* tbrt_decode_step_handle(tbrt_engine* e);
 /* generation steps (incl. the context phase) the last tbrt_generate actually ran */
 int tbrt_last_steps(const tbrt_engine* e);
 /* kernels launched by the last tbrt_context / tbrt_step / tbrt_generate call */

@@ -62,6 +62,8 @@ SIGNATURES = {
     "tb_decode_step_destroy": (None, [vp]),
     "tb_decode_step_launch": (i32, [vp, i32, vp]),
     "tb_decode_step_info": (i32, [vp, i32, vp, vp, vp]),
+    "tb_decode_step_trace": (i32, [vp, i32, vp]),
+    "tbrt_decode_step_handle": (vp, [vp]),
     "tb_mma_peak": (i32, [i32, i32, i32, vp, C.POINTER(C.c_double), vp]),
 }
 

@@ -43,9 +43,10 @@ constexpr int kThreads = kCT + 32;    // + one producer warp
 constexpr int kSeg = 4096;            // bytes per ring stage
 constexpr int kDh = 128;
 constexpr int kMaxStages = 60;
-constexpr int kPartFloats = 2048;     // per-(row, segment) partial sums of one phase of one CTA
-constexpr int kLgFloats = 1024;       // this CTA's logits (argmax candidates)
+constexpr int kPartFloats = 512;      // x MB: per-(row, segment) partial sums of one phase of one CTA
+constexpr int kLgFloats = 256;        // x MB: this CTA's logits (argmax candidates)
 constexpr int kMaxRows = 4;
+constexpr int kTraceSlots = 2048;
 
 enum Kind { kF16 = 0, kW8 = 1, kW4 = 2, kA8W8 = 3 };
 enum XFormat { kXHalf = 0, kXFloat = 1, kXInt8 = 2 };
@@ -71,15 +72,22 @@ struct Params {
   int *ids, *seq_lens, *step_pos, *out_ids, *next;
   const int *in_lens, *max_in;
   unsigned long long* bar;
-  int stages;
+  int stages, prefetch;          // ring slots; L2 prefetch distance in stages (0: off)
+  int interleave;                // output channels dealt round-robin over the CTAs (1) or in contiguous blocks (0)
+  int debug;                     // diagnostics (TB_DS_DEBUG): bit 0 = grid barriers do not wait (timing of the pure weight stream; results are garbage)
+  unsigned long long* trace;     // optional [gridDim.x][kTraceSlots]: globaltimer stamps of the consumer pipeline (diagnostics)
   uint32_t xs_off, ring_off;
 };
 
 // smem layout (dynamic): [0,1024) mbarriers | [1024,1536) reduction scratch + per-token scales | part | lgs | xs | ring
-constexpr uint32_t kOffRed = 1024, kOffPart = 1536, kOffLg = kOffPart + kPartFloats * 4, kOffXs = kOffLg + kLgFloats * 4;
+constexpr uint32_t kOffRed = 1024, kOffPart = 1536;
+__host__ __device__ constexpr uint32_t off_lg(int MB) { return kOffPart + (uint32_t) kPartFloats * MB * 4; }
+__host__ __device__ constexpr uint32_t off_xs(int MB) { return off_lg(MB) + (uint32_t) kLgFloats * MB * 4; }
 
 __host__ __device__ constexpr int epc_of(int kind) { return kind == kF16 ? 8 : (kind == kW4 ? 32 : 16); }
-template <int KIND, int MB> struct XF { static constexpr int v = KIND == kA8W8 ? kXInt8 : (MB == 1 ? kXFloat : kXHalf); };
+// fp16 activations (int8 for W8A8).  An fp32 copy for one row saves the consumers a conversion per element but costs
+// 22 KB of shared memory = the difference between 32 and 48 ring slots, which matters more.
+template <int KIND, int MB> struct XF { static constexpr int v = KIND == kA8W8 ? kXInt8 : kXHalf; };
 __host__ __device__ constexpr int xbytes_of(int xf) { return xf == kXFloat ? 4 : (xf == kXHalf ? 2 : 1); }
 
 // Staged activations are stored chunk-interleaved: a "chunk" is the E activations that meet one 16-byte weight chunk
@@ -91,6 +99,16 @@ __host__ __device__ constexpr int xrow_bytes(int K, int E, int XB) { return ((K 
 __device__ __forceinline__ uint32_t xvec_off(int c, int j, int NV) {
   return (uint32_t) (((c >> 5) * NV + j) * 32 + (c & 31)) * 16u;
 }
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define DS_STAMP()                                                                                   \
+  do {                                                                                               \
+    if (p.trace && ctid == 0 && tr_n < kTraceSlots) p.trace[(size_t) blockIdx.x * kTraceSlots + tr_n++] = gtime(); \
+  } while (0)
 
 __device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
@@ -109,18 +127,22 @@ __device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gs
 }
 
 // ---- grid-wide barrier: a monotonically increasing arrival counter in L2 (reset to 0 by CTA 0 at the end of the launch)
+// The CTA's writes reach thread 0 through the CTA barrier; its gpu-scope fence + release then publishes them (the
+// cooperative-groups grid.sync pattern): 511 threads do not pay a membar each.
 __device__ __forceinline__ void grid_arrive(unsigned long long* bar, int ctid) {
-  __threadfence();
   cbar();
   if (ctid == 0) asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
 }
-__device__ __forceinline__ void grid_wait(const unsigned long long* bar, unsigned long long target, int ctid) {
-  if (ctid == 0) {
+__device__ __forceinline__ void grid_wait(const unsigned long long* bar, unsigned long long target, int ctid, int debug = 0) {
+  if (ctid == 0 && !(debug & 1)) {
     unsigned long long v;
     const long long t0 = clock64();
     for (;;) {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
-      if (v >= target) break;
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+      if (v >= target) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");      // one acquire for the whole wait, not one per poll
+        break;
+      }
       if (clock64() - t0 > 4000000000ll) {     // a lost CTA must surface as a trapped kernel, never as a hung GPU
         printf("[trtllm_b200] decode_step grid barrier timed out (block %d, %llu < %llu)\n", blockIdx.x, v, target);
         __trap();
@@ -134,28 +156,37 @@ __device__ __forceinline__ void grid_wait(const unsigned long long* bar, unsigne
 struct Phase {
   const uint8_t* w;
   const void* scale;
-  int K, n_out, R, kind, nseg, o0, o1;
+  int K, n_out, R, kind, nseg, o0, rows, ostride;   // this CTA's output channels: o0 + ostride * j, j < rows
   uint32_t rowbytes;
 };
 
-__device__ __forceinline__ Phase make_phase(const uint8_t* w, const void* scale, int kind, int K, int n_out, int R) {
+__device__ __forceinline__ Phase make_phase(const uint8_t* w, const void* scale, int kind, int K, int n_out, int R,
+                                            int interleave) {
   Phase f;
   f.w = w; f.scale = scale; f.kind = kind; f.K = K; f.n_out = n_out; f.R = R;
   f.rowbytes = (uint32_t) (K / epc_of(kind)) * 16u;
   f.nseg = (int) ((f.rowbytes + kSeg - 1) / kSeg);
-  f.o0 = (int) ((long long) n_out * blockIdx.x / gridDim.x);
-  f.o1 = (int) ((long long) n_out * (blockIdx.x + 1) / gridDim.x);
+  if (interleave) {
+    // channels dealt round-robin: at any instant the chip streams ONE window of ~G consecutive weight rows (DRAM pages stay
+    // open) instead of G far-apart streams
+    f.o0 = blockIdx.x; f.ostride = gridDim.x;
+    f.rows = (int) blockIdx.x < n_out ? (n_out - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x : 0;
+  } else {
+    f.o0 = (int) ((long long) n_out * blockIdx.x / gridDim.x);
+    f.ostride = 1;
+    f.rows = (int) ((long long) n_out * (blockIdx.x + 1) / gridDim.x) - f.o0;
+  }
   return f;
 }
 // idx = 4 * layer + {0 qkv, 1 dense, 2 gate|up, 3 down}; idx = 4 * n_layers: lm_head (always fp16, LQ/quant.py:58-59)
 __device__ __forceinline__ Phase phase_of(const Params& p, int idx) {
-  if (idx == 4 * p.n_layers) return make_phase(p.lm_head, nullptr, kF16, p.hidden, p.vocab_l, 1);
+  if (idx == 4 * p.n_layers) return make_phase(p.lm_head, nullptr, kF16, p.hidden, p.vocab_l, 1, p.interleave);
   const Layer& L = p.layers[idx >> 2];
   switch (idx & 3) {
-    case 0: return make_phase(L.w_qkv, L.s_qkv, p.kind, p.hidden, 3 * p.hid_l, 1);
-    case 1: return make_phase(L.w_dense, L.s_dense, p.kind, p.hid_l, p.hidden, 1);
-    case 2: return make_phase(L.w_fc, L.s_fc, p.kind, p.hidden, p.inter_l, 2);
-    default: return make_phase(L.w_proj, L.s_proj, p.kind, p.inter_l, p.hidden, 1);
+    case 0: return make_phase(L.w_qkv, L.s_qkv, p.kind, p.hidden, 3 * p.hid_l, 1, p.interleave);
+    case 1: return make_phase(L.w_dense, L.s_dense, p.kind, p.hid_l, p.hidden, 1, p.interleave);
+    case 2: return make_phase(L.w_fc, L.s_fc, p.kind, p.hidden, p.inter_l, 2, p.interleave);
+    default: return make_phase(L.w_proj, L.s_proj, p.kind, p.inter_l, p.hidden, 1, p.interleave);
   }
 }
 
@@ -178,39 +209,79 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+struct Cursor {                      // a lane's position in the step's global stage sequence
+  uint32_t gi, gbase, nst;
+  int idx;
+  bool done;
+  Phase f;
+};
+__device__ __forceinline__ void cursor_seek(const Params& p, Cursor& c) {
+  const int last = 4 * p.n_layers;
+  while (!c.done && c.gi >= c.gbase + c.nst) {          // the stage lies in a later projection
+    c.gbase += c.nst;
+    if (++c.idx > last) { c.done = true; break; }
+    c.f = phase_of(p, c.idx);
+    c.nst = (uint32_t) (c.f.R * c.f.rows * c.f.nseg);
+  }
+}
+__device__ __forceinline__ const uint8_t* cursor_src(const Cursor& c, uint32_t& bytes) {
+  const int i = (int) (c.gi - c.gbase);
+  const int per_r = c.f.rows * c.f.nseg;
+  const int r = i >= per_r ? 1 : 0;
+  const int rem = i - r * per_r;
+  const int row = rem / c.f.nseg, seg = rem - row * c.f.nseg;
+  const uint32_t off = (uint32_t) seg * kSeg;
+  bytes = min((uint32_t) kSeg, c.f.rowbytes - off);
+  return c.f.w + (size_t) (r * c.f.n_out + c.f.o0 + row * c.f.ostride) * c.f.rowbytes + off;
+}
+
 __device__ __forceinline__ void producer(const Params& p, uint8_t* ring, uint64_t* full, uint64_t* empty, int lane) {
   const uint64_t pol = policy_evict_first();     // weights are read once per step: keep K/V and activations in L2
   const uint32_t S = (uint32_t) p.stages;
-  const int last = 4 * p.n_layers;
-  bool done = lane >= (int) S;
-  uint32_t gi = (uint32_t) lane, use = 0, gbase = 0;
-  int idx = 0;
-  Phase f = phase_of(p, 0);
-  uint32_t nst = (uint32_t) (f.R * (f.o1 - f.o0) * f.nseg);
+  // slot cursors: c[k] walks the stages lane + 32 k, + S, + 2S, ... of the step's global stage sequence (slot lane + 32 k)
+  Cursor c[2];
+  uint32_t use[2] = {0, 0};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    c[k].gi = (uint32_t) (lane + 32 * k); c[k].gbase = 0; c[k].idx = 0; c[k].done = lane + 32 * k >= (int) S;
+    c[k].f = phase_of(p, 0);
+    c[k].nst = (uint32_t) (c[k].f.R * c[k].f.rows * c[k].f.nseg);
+  }
+  // Optional third cursor: cp.async.bulk.prefetch.L2 of the stages lane, lane + 32, ... (all lanes together: every stage
+  // once) up to p.prefetch stages ahead of what the ring has requested — L2 as the buffer behind the 192 KB ring, so that
+  // HBM keeps streaming while the consumers sit in a phase boundary (A/B switch TB_DS_PREFETCH; 0 = off).
+  Cursor pf = c[0];
+  pf.gi = (uint32_t) lane;
+  pf.done = false;
   const long long t0 = clock64();
   for (;;) {
-    while (!done && gi >= gbase + nst) {          // my next stage lies in a later projection
-      gbase += nst;
-      if (++idx > last) { done = true; break; }
-      f = phase_of(p, idx);
-      nst = (uint32_t) (f.R * (f.o1 - f.o0) * f.nseg);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) cursor_seek(p, c[k]);
+    if (__all_sync(0xffffffffu, c[0].done && c[1].done)) break;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int slot = lane + 32 * k;
+      if (!c[k].done && mbar_test_wait(&empty[slot], (use[k] & 1u) ^ 1u)) {
+        uint32_t bytes;
+        const uint8_t* src = cursor_src(c[k], bytes);
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_load_1d_hint(ring + (size_t) slot * kSeg, src, bytes, &full[slot], pol);
+        c[k].gi += S;
+        ++use[k];
+      }
     }
-    if (__all_sync(0xffffffffu, done)) break;
-    if (!done && mbar_test_wait(&empty[lane], (use & 1u) ^ 1u)) {
-      const int i = (int) (gi - gbase);
-      const int per_r = (f.o1 - f.o0) * f.nseg;
-      const int r = i >= per_r ? 1 : 0;
-      const int rem = i - r * per_r;
-      const int row = rem / f.nseg, seg = rem - row * f.nseg;
-      const uint32_t off = (uint32_t) seg * kSeg;
-      const uint32_t bytes = min((uint32_t) kSeg, f.rowbytes - off);
-      const uint8_t* src = f.w + (size_t) (r * f.n_out + f.o0 + row) * f.rowbytes + off;
-      mbar_expect_tx(&full[lane], bytes);
-      bulk_load_1d_hint(ring + (size_t) lane * kSeg, src, bytes, &full[lane], pol);
-      gi += S;
-      ++use;
+    const uint32_t head = __shfl_sync(0xffffffffu, c[0].gi, 0);      // lane 0's next stage ~ the ring's request frontier
+    if (p.prefetch > 0 && !pf.done && pf.gi < head + S + (uint32_t) p.prefetch) {
+      while (pf.gi < head + S) pf.gi += 32;                           // never behind the ring
+      cursor_seek(p, pf);
+      if (!pf.done) {
+        uint32_t bytes;
+        const uint8_t* src = cursor_src(pf, bytes);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        pf.gi += 32;
+      }
     }
-    if (clock64() - t0 > 20000000000ll) {         // a wedged pipeline must surface as a trapped kernel, never as a hang
+    if (clock64() - t0 > 8000000000ll) {          // a wedged pipeline must surface as a trapped kernel, never as a hang
       if (lane == 0) printf("[trtllm_b200] decode_step producer timed out (block %d)\n", blockIdx.x);
       __trap();
     }
@@ -232,9 +303,18 @@ __device__ __forceinline__ float cta_reduce(float v, float* red, bool is_max, in
 // ---- activation staging with the fused prologue (same arithmetic as gemv.cu / norm_quant.cu) ----------------------------
 // mode 0: copy; 1: RMSNorm; 2: RMSNorm + dynamic per-token int8; 3: dynamic per-token int8.  rows[m]: fp16 [K] in global
 // memory, written by other CTAs earlier in this launch (read through L2).
+// RMSNorm weights of the coming phase: independent of every activation, so they are requested BEFORE the grid barrier
+__device__ __forceinline__ void load_gamma(const __half* gamma, int K, uint4 (&g)[3], int ctid) {
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int i = (it * kCT + ctid) * 8;
+    g[it] = (gamma && i < K) ? *reinterpret_cast<const uint4*>(gamma + i) : make_uint4(0, 0, 0, 0);
+  }
+}
+
 template <int XFMT, int MB, int E>
-__device__ __forceinline__ void stage_x(const Params& p, const __half* const (&rows)[MB], int K, int mode, const __half* gamma,
-                                        uint8_t* xs, float* srow, float* red, int ctid) {
+__device__ __forceinline__ void stage_x(const Params& p, const __half* const (&rows)[MB], int K, int mode,
+                                        const uint4 (&gam)[3], uint8_t* xs, float* srow, float* red, int ctid) {
   constexpr int XB = xbytes_of(XFMT);
   constexpr int NV = E * XB / 16;                          // 16-byte vectors per chunk
   const int xstride = xrow_bytes(K, E, XB);
@@ -270,8 +350,7 @@ __device__ __forceinline__ void stage_x(const Params& p, const __half* const (&r
       for (int it = 0; it < IT; ++it) {
         const int i = (it * kCT + ctid) * 8;
         if (i < K) {
-          const uint4 g4 = *reinterpret_cast<const uint4*>(gamma + i);
-          const __half2* g = reinterpret_cast<const __half2*>(&g4);
+          const __half2* g = reinterpret_cast<const __half2*>(&gam[it]);
           __half2* h = reinterpret_cast<__half2*>(&raw[it]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -407,7 +486,7 @@ __device__ __forceinline__ void chunk_dot(const uint4& wq, const uint8_t* xs, in
 template <int KIND, int XFMT, int MB>
 __device__ __forceinline__ void run_phase(const Phase& f, uint32_t g, int S, const uint8_t* ring, uint64_t* full,
                                           uint64_t* empty, const uint8_t* xs, float* part, int cwarp, int lane) {
-  const int rows = f.o1 - f.o0;
+  const int rows = f.rows;
   const int nst = f.R * rows * f.nseg;
   const int xstride = xrow_bytes(f.K, epc_of(KIND), xbytes_of(XFMT));
   // stage i of this phase: ring slot (g + i) % S with use count (g + i) / S, row segment i % nseg — kept incrementally
@@ -456,27 +535,61 @@ __device__ __forceinline__ void run_phase(const Phase& f, uint32_t g, int S, con
 
 // ---- fused epilogue over this CTA's output channels -------------------------------------------------------------------
 // mode 0: y[m][n] = fp16(v) (+ residual);  1: SwiGLU (R = 2);  2: fp32 logits (+ copy in lgs for the argmax)
+// A thread owns at most kEpiItems (output channel, row) pairs; their per-channel scales and residual values are loaded
+// BEFORE the phase's stages are consumed (they depend on nothing the phase computes), so the tail of the phase — the part
+// every other CTA waits for at the grid barrier — is shared-memory sums, arithmetic and stores only.
+constexpr int kEpiItems = 2;
+struct EpiPre { float sc[kEpiItems][2]; float res[kEpiItems]; };
+
 template <int KIND, int MB>
-__device__ __forceinline__ void epilogue(const Params& p, const Phase& f, int mode, const float* part, const float* srow,
-                                         const __half* const (&resid)[MB], __half* y, int ldy, float* lgs, int ctid) {
-  const int rows = f.o1 - f.o0;
-  for (int t = ctid; t < rows * MB; t += kCT) {
+__device__ __forceinline__ void epilogue_prefetch(const Params& p, const Phase& f, const __half* const (&resid)[MB], EpiPre& e,
+                                                  int ctid) {
+  const int rows = f.rows;
+#pragma unroll
+  for (int k = 0; k < kEpiItems; ++k) {
+    const int t = ctid + k * kCT;
+    e.sc[k][0] = e.sc[k][1] = 1.f;
+    e.res[k] = 0.f;
+    if (t >= rows * MB) continue;
     const int row = t / MB, m = t % MB;
     if (m >= p.B) continue;
-    const int n = f.o0 + row;
+    const int n = f.o0 + row * f.ostride;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r < f.R) {
+        if constexpr (KIND == kA8W8) e.sc[k][r] = reinterpret_cast<const float*>(f.scale)[n + r * f.n_out];
+        else if constexpr (KIND == kW8 || KIND == kW4) e.sc[k][r] = __half2float(reinterpret_cast<const __half*>(f.scale)[n + r * f.n_out]);
+      }
+    }
+    if (resid[m]) e.res[k] = ldcg_h(resid[m] + n);
+  }
+}
+
+template <int KIND, int MB>
+__device__ __forceinline__ void epilogue(const Params& p, const Phase& f, int mode, const float* part, const float* srow,
+                                         const EpiPre& e, bool has_resid, __half* y, int ldy, float* lgs, int ctid) {
+  const int rows = f.rows;
+#pragma unroll
+  for (int k = 0; k < kEpiItems; ++k) {
+    const int t = ctid + k * kCT;
+    if (t >= rows * MB) continue;
+    const int row = t / MB, m = t % MB;
+    if (m >= p.B) continue;
+    const int n = f.o0 + row * f.ostride;
     float v[2] = {0.f, 0.f};
-    for (int r = 0; r < f.R; ++r) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r >= f.R) continue;
       const int base = ((r * rows + row) * f.nseg) * MB + m;
-      const int nr = n + r * f.n_out;
       if constexpr (KIND == kA8W8) {
         int s = 0;
         for (int sg = 0; sg < f.nseg; ++sg) s += reinterpret_cast<const int*>(part)[base + sg * MB];
         // reference grouping: accum * (scale_col * scale_row)  (epilogue_per_row_per_col_scale.h:325,341)
-        v[r] = (float) s * (reinterpret_cast<const float*>(f.scale)[nr] * srow[m]);
+        v[r] = (float) s * (e.sc[k][r] * srow[m]);
       } else {
         float s = 0.f;
         for (int sg = 0; sg < f.nseg; ++sg) s += part[base + sg * MB];
-        if constexpr (KIND == kW8 || KIND == kW4) s *= __half2float(reinterpret_cast<const __half*>(f.scale)[nr]);
+        if constexpr (KIND == kW8 || KIND == kW4) s *= e.sc[k][r];
         v[r] = s;
       }
     }
@@ -488,7 +601,7 @@ __device__ __forceinline__ void epilogue(const Params& p, const Phase& f, int mo
       y[(size_t) m * ldy + n] = __float2half_rn(__half2float(__float2half_rn(silu_f(gte))) * up);
     } else {
       __half oh = __float2half_rn(v[0]);
-      if (resid[m]) oh = __float2half_rn(__half2float(oh) + ldcg_h(resid[m] + n));
+      if (has_resid) oh = __float2half_rn(__half2float(oh) + e.res[k]);
       y[(size_t) m * ldy + n] = oh;
     }
   }
@@ -521,7 +634,8 @@ __device__ __forceinline__ void unpack16(const uint4& r, float* f) {
   }
 }
 template <bool INT8>
-__device__ __forceinline__ void attention_item(const Params& p, const Layer& L, int b, int h, float* scr, int ctid) {
+__device__ __forceinline__ void attention_item(const Params& p, const Layer& L, int b, int h, float* scr, int ctid,
+                                               float rope_c, float rope_s) {
   constexpr int LPK = INT8 ? 8 : 16, DPL = kDh / LPK, KPI = kCT / LPK, ELT = INT8 ? 1 : 2, UN = INT8 ? 4 : 8;
   float* q_s = scr;                                               // [128]
   __half* kcur_s = reinterpret_cast<__half*>(scr + kDh);          // [128]
@@ -534,7 +648,6 @@ __device__ __forceinline__ void attention_item(const Params& p, const Layer& L, 
   const int tlen = p.seq_lens[b];                                 // positions [0, tlen) are cached
   const int max_in = p.max_in[0];
   const int in_len = p.in_lens[b];
-  const int pos = tlen - (max_in - in_len);
   const int len = tlen;
   const float kv_dq = INT8 ? L.kv_qo[0] : 1.f;
   const size_t seq_stride = (size_t) 2 * H * p.S_max * kDh * ELT;
@@ -543,9 +656,7 @@ __device__ __forceinline__ void attention_item(const Params& p, const Layer& L, 
 
   const __half* qrow = p.qkv + (size_t) b * 3 * hidden + (size_t) h * kDh;
   if (ctid < kDh / 2) {
-    // inv_freq = t / pow(10000, 2j/rot)  (decoderMaskedMultiheadAttentionUtils.h:1511-1515)
-    const float ang = (float) pos / powf(10000.0f, (2 * ctid) / (float) kDh);
-    const float c = cosf(ang), s = sinf(ang);
+    const float c = rope_c, s = rope_s;
     const int i0 = ctid, i1 = ctid + kDh / 2;
     const float qa = ldcg_h(qrow + i0), qb = ldcg_h(qrow + i1);
     q_s[i0] = __half2float(__float2half_rn(c * qa - s * qb));
@@ -666,13 +777,21 @@ __device__ __forceinline__ void attention_item(const Params& p, const Layer& L, 
       for (int j = 0; j < DPL; ++j) acc[j] = fmaf(pv, vf[j], acc[j]);
     }
   }
+  // the 32 / LPK key groups of a warp hold partial outputs for the same dims: fold them with shuffles, one row per warp
 #pragma unroll
-  for (int j = 0; j < DPL; ++j) o_red[grp * kDh + gl * DPL + j] = acc[j] * kv_dq;
+  for (int j = 0; j < DPL; ++j) {
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (lane < LPK) {
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) o_red[warp * kDh + gl * DPL + j] = acc[j] * kv_dq;
+  }
   cbar();
   if (ctid < kDh) {
     float o = 0.f;
-#pragma unroll 8
-    for (int g2 = 0; g2 < KPI; ++g2) o += o_red[g2 * kDh + ctid];
+#pragma unroll
+    for (int g2 = 0; g2 < kCW; ++g2) o += o_red[g2 * kDh + ctid];
     o = fmaf(s_s[len], __half2float(vcur_s[ctid]), o);
     p.att[(size_t) b * hidden + h * kDh + ctid] = __float2half_rn(o);
   }
@@ -688,7 +807,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
   float* red = reinterpret_cast<float*>(smem + kOffRed);          // [32]
   float* srow = red + 64;                                         // [MB] per-token scales (W8A8)
   float* part = reinterpret_cast<float*>(smem + kOffPart);
-  float* lgs = reinterpret_cast<float*>(smem + kOffLg);
+  float* lgs = reinterpret_cast<float*>(smem + off_lg(MB));
   uint8_t* xs = smem + p.xs_off;
   uint8_t* ring = smem + p.ring_off;
   const int tid = threadIdx.x;
@@ -713,10 +832,14 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
   const unsigned long long G = gridDim.x;
   unsigned long long target = 0;
   uint32_t g = 0;                           // running stage counter (the producer counts the same sequence)
-  auto stages_of = [](const Phase& f) { return (uint32_t) (f.R * (f.o1 - f.o0) * f.nseg); };
+  auto stages_of = [](const Phase& f) { return (uint32_t) (f.R * f.rows * f.nseg); };
 
   const __half* none[MB];
   const __half* hrow[MB];
+  uint4 gam[3];
+  EpiPre epre;
+  int tr_n = 0;
+  DS_STAMP();
 #pragma unroll
   for (int m = 0; m < MB; ++m) none[m] = nullptr;
 
@@ -731,23 +854,45 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
     // ---- QKV projection (RMSNorm / RmsnormQuantization prologue) --------------------------------------------------------
     {
       const Phase f = phase_of(p, 4 * li);
-      if (target) grid_wait(p.bar, target, ctid);
-      stage_x<XM, MB, epc_of(KIND)>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, L.ln_in, xs, srow, red, ctid);
+      load_gamma(L.ln_in, p.hidden, gam, ctid);
+      epilogue_prefetch<KIND, MB>(p, f, none, epre, ctid);
+      if (target) grid_wait(p.bar, target, ctid, p.debug);
+      DS_STAMP();
+      stage_x<XM, MB, epc_of(KIND)>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, gam, xs, srow, red, ctid);
+      DS_STAMP();
       run_phase<KIND, XM, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
-      epilogue<KIND, MB>(p, f, 0, part, srow, none, p.qkv, 3 * p.hid_l, lgs, ctid);
+      DS_STAMP();
+      epilogue<KIND, MB>(p, f, 0, part, srow, epre, false, p.qkv, 3 * p.hid_l, lgs, ctid);
+      DS_STAMP();
       g += stages_of(f);
       grid_arrive(p.bar, ctid);
       target += G;
     }
     // ---- attention ----------------------------------------------------------------------------------------------------
     {
-      grid_wait(p.bar, target, ctid);
+      // the rotary angle of this CTA's first (sequence, head) depends on the position only: computed (powf, sincos)
+      // while waiting for the QKV projection
+      float rope_c = 1.f, rope_s = 0.f;
+      auto rope_of = [&](int b) {
+        if (ctid < kDh / 2) {
+          // inv_freq = t / pow(10000, 2j/rot)  (decoderMaskedMultiheadAttentionUtils.h:1511-1515)
+          const int pos = p.seq_lens[b] - (p.max_in[0] - p.in_lens[b]);
+          const float ang = (float) pos / powf(10000.0f, (2 * ctid) / (float) kDh);
+          rope_c = cosf(ang);
+          rope_s = sinf(ang);
+        }
+      };
+      if ((int) blockIdx.x < p.B * p.Hl) rope_of(blockIdx.x / p.Hl);
+      grid_wait(p.bar, target, ctid, p.debug);
+      DS_STAMP();
       float* scr = reinterpret_cast<float*>(xs);
       for (int it = blockIdx.x; it < p.B * p.Hl; it += gridDim.x) {
         const int b = it / p.Hl, h = it % p.Hl;
-        if (p.int8_kv) attention_item<true>(p, L, b, h, scr, ctid);
-        else attention_item<false>(p, L, b, h, scr, ctid);
+        if (it != (int) blockIdx.x) rope_of(b);
+        if (p.int8_kv) attention_item<true>(p, L, b, h, scr, ctid, rope_c, rope_s);
+        else attention_item<false>(p, L, b, h, scr, ctid, rope_c, rope_s);
       }
+      DS_STAMP();
       grid_arrive(p.bar, ctid);
       target += G;
     }
@@ -757,10 +902,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
       const __half* arow[MB];
 #pragma unroll
       for (int m = 0; m < MB; ++m) arow[m] = m < p.B ? p.att + (size_t) m * p.hid_l : nullptr;
-      grid_wait(p.bar, target, ctid);
-      stage_x<XM, MB, epc_of(KIND)>(p, arow, p.hid_l, KIND == kA8W8 ? 3 : 0, nullptr, xs, srow, red, ctid);
+      load_gamma(nullptr, 0, gam, ctid);
+      epilogue_prefetch<KIND, MB>(p, f, hrow, epre, ctid);       // residual = the stream entering the layer (older than QKV)
+      grid_wait(p.bar, target, ctid, p.debug);
+      DS_STAMP();
+      stage_x<XM, MB, epc_of(KIND)>(p, arow, p.hid_l, KIND == kA8W8 ? 3 : 0, gam, xs, srow, red, ctid);
+      DS_STAMP();
       run_phase<KIND, XM, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
-      epilogue<KIND, MB>(p, f, 0, part, srow, hrow, p.hB, p.hidden, lgs, ctid);
+      DS_STAMP();
+      epilogue<KIND, MB>(p, f, 0, part, srow, epre, true, p.hB, p.hidden, lgs, ctid);
+      DS_STAMP();
       g += stages_of(f);
       grid_arrive(p.bar, ctid);
       target += G;
@@ -770,10 +921,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
     // ---- gate | up + SwiGLU (RMSNorm prologue) --------------------------------------------------------------------------
     {
       const Phase f = phase_of(p, 4 * li + 2);
-      grid_wait(p.bar, target, ctid);
-      stage_x<XM, MB, epc_of(KIND)>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, L.ln_post, xs, srow, red, ctid);
+      load_gamma(L.ln_post, p.hidden, gam, ctid);
+      epilogue_prefetch<KIND, MB>(p, f, none, epre, ctid);
+      grid_wait(p.bar, target, ctid, p.debug);
+      DS_STAMP();
+      stage_x<XM, MB, epc_of(KIND)>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, gam, xs, srow, red, ctid);
+      DS_STAMP();
       run_phase<KIND, XM, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
-      epilogue<KIND, MB>(p, f, 1, part, srow, none, p.act, p.inter_l, lgs, ctid);
+      DS_STAMP();
+      epilogue<KIND, MB>(p, f, 1, part, srow, epre, false, p.act, p.inter_l, lgs, ctid);
+      DS_STAMP();
       g += stages_of(f);
       grid_arrive(p.bar, ctid);
       target += G;
@@ -784,10 +941,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
       const __half* arow[MB];
 #pragma unroll
       for (int m = 0; m < MB; ++m) arow[m] = m < p.B ? p.act + (size_t) m * p.inter_l : nullptr;
-      grid_wait(p.bar, target, ctid);
-      stage_x<XM, MB, epc_of(KIND)>(p, arow, p.inter_l, KIND == kA8W8 ? 3 : 0, nullptr, xs, srow, red, ctid);
+      grid_wait(p.bar, target, ctid, p.debug);
+      // residual = hB, written by the dense phase of THIS layer two barriers ago: loaded after this barrier, but still
+      // before the stages (its latency hides behind the weight stream)
+      DS_STAMP();
+      stage_x<XM, MB, epc_of(KIND)>(p, arow, p.inter_l, KIND == kA8W8 ? 3 : 0, gam, xs, srow, red, ctid);
+      epilogue_prefetch<KIND, MB>(p, f, hrow, epre, ctid);
+      DS_STAMP();
       run_phase<KIND, XM, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
-      epilogue<KIND, MB>(p, f, 0, part, srow, hrow, p.hA, p.hidden, lgs, ctid);
+      DS_STAMP();
+      epilogue<KIND, MB>(p, f, 0, part, srow, epre, true, p.hA, p.hidden, lgs, ctid);
+      DS_STAMP();
       g += stages_of(f);
       grid_arrive(p.bar, ctid);
       target += G;
@@ -799,12 +963,14 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
     const Phase f = phase_of(p, 4 * p.n_layers);
 #pragma unroll
     for (int m = 0; m < MB; ++m) hrow[m] = m < p.B ? p.hA + (size_t) m * p.hidden : nullptr;
-    grid_wait(p.bar, target, ctid);
-    stage_x<XL, MB, epc_of(kF16)>(p, hrow, p.hidden, 1, p.ln_f, xs, srow, red, ctid);
+    load_gamma(p.ln_f, p.hidden, gam, ctid);
+    epilogue_prefetch<kF16, MB>(p, f, none, epre, ctid);
+    grid_wait(p.bar, target, ctid, p.debug);
+    stage_x<XL, MB, epc_of(kF16)>(p, hrow, p.hidden, 1, gam, xs, srow, red, ctid);
     run_phase<kF16, XL, MB>(f, g, S, ring, full, empty, xs, part, cwarp, lane);
-    epilogue<kF16, MB>(p, f, 2, part, srow, none, nullptr, 0, lgs, ctid);
+    epilogue<kF16, MB>(p, f, 2, part, srow, epre, false, nullptr, 0, lgs, ctid);
     cbar();
-    const int rows = f.o1 - f.o0;
+    const int rows = f.rows;
     float* rv = red;
     int* ri = reinterpret_cast<int*>(red + kCW);
     for (int m = 0; m < p.B; ++m) {
@@ -812,7 +978,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
       int bi = 0x7fffffff;
       for (int r = ctid; r < rows; r += kCT) {
         const float v = lgs[r * MB + m];
-        if (v > bv || (v == bv && f.o0 + r < bi)) { bv = v; bi = f.o0 + r; }
+        const int n = f.o0 + r * f.ostride;
+        if (v > bv || (v == bv && n < bi)) { bv = v; bi = n; }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -836,7 +1003,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
 
   // ---- greedy token (lowest index wins ties, as tb_argmax) + device-side step bookkeeping, by CTA 0 ----------------------
   if (blockIdx.x != 0) return;
-  grid_wait(p.bar, target, ctid);
+  grid_wait(p.bar, target, ctid, p.debug);
   const int pos = p.step_pos[0];
   if (ctid < p.B) {
     const int m = ctid;
@@ -870,6 +1037,7 @@ struct tb_decode_step {
   float* d_cand_v = nullptr;
   int* d_cand_i = nullptr;
   unsigned long long* d_bar = nullptr;
+  unsigned long long* d_trace = nullptr;
   int grid = 0, max_batch = 0, smem_max = 0;
   size_t smem[3] = {0, 0, 0};       // per MB in {1, 2, 4}
   int stages[3] = {0, 0, 0};
@@ -884,7 +1052,13 @@ int launch_t(tb_decode_step* d, int B, cudaStream_t stream) {
   ds::Params p = d->p;
   p.B = B;
   p.stages = d->stages[mi];
-  p.xs_off = ds::kOffXs;
+  static const int pf_env = getenv("TB_DS_PREFETCH") ? atoi(getenv("TB_DS_PREFETCH")) : 0;   // A/B switch (stages)
+  p.prefetch = pf_env;
+  static const int il_env = getenv("TB_DS_INTERLEAVE") ? atoi(getenv("TB_DS_INTERLEAVE")) : 1;   // A/B switch
+  p.interleave = il_env;
+  static const int dbg_env = getenv("TB_DS_DEBUG") ? atoi(getenv("TB_DS_DEBUG")) : 0;
+  p.debug = dbg_env;
+  p.xs_off = ds::off_xs(MB);
   p.ring_off = d->ring_off[mi];
   auto kern = ds::decode_step_kernel<KIND, MB>;
   static bool attr_done = false;      // per template instantiation
@@ -956,20 +1130,25 @@ int tb_decode_step_create(tb_decode_step** out, const tb_decode_step_config* c, 
   max_nst = std::max(max_nst, nst(0, c->hidden, c->vocab_local, 1));
   for (int mi = 0; mi < 3; ++mi) {
     const int MB = 1 << mi;
-    if (max_nst * MB > (size_t) ds::kPartFloats || (size_t) ((c->vocab_local + sms - 1) / sms) * MB > (size_t) ds::kLgFloats) {
+    int widest = std::max(std::max(3 * c->heads_local * ds::kDh, c->hidden), std::max(c->inter_local, c->vocab_local));
+    if ((size_t) ((widest + sms - 1) / sms) * MB > (size_t) ds::kEpiItems * ds::kCT) {   // outputs per thread in the epilogue
       delete d;
       return -5;
     }
-    const int xf_model = c->kind == 3 ? ds::kXInt8 : (MB == 1 ? ds::kXFloat : ds::kXHalf);
-    const int xf_lm = MB == 1 ? ds::kXFloat : ds::kXHalf;
+    if (max_nst > (size_t) ds::kPartFloats || (size_t) ((c->vocab_local + sms - 1) / sms) > (size_t) ds::kLgFloats) {
+      delete d;
+      return -5;
+    }
+    const int xf_model = c->kind == 3 ? ds::kXInt8 : ds::kXHalf;
+    const int xf_lm = ds::kXHalf;
     size_t xs = (size_t) MB * ds::xrow_bytes(kmax, epc, ds::xbytes_of(xf_model));
     xs = std::max(xs, (size_t) MB * ds::xrow_bytes(c->hidden, 8, ds::xbytes_of(xf_lm)));
     xs = std::max(xs, attn);
-    const uint32_t ring_off = (uint32_t) ((ds::kOffXs + xs + 1023) & ~(size_t) 1023);
-    // S must be a multiple of the consumer warps (a slot is then always read by the same warp, in order) and at most the
-    // 32 producer lanes (a slot is always filled by the same lane, in order): 32 or 16
+    const uint32_t ring_off = (uint32_t) ((ds::off_xs(MB) + xs + 1023) & ~(size_t) 1023);
+    // S must be a multiple of the consumer warps (a slot is then always read by the same warp, in order); every slot is
+    // filled by one fixed producer lane, in order (48 slots: lanes 0..15 own two): 48, 32 or 16
     int stages = (int) (((size_t) smem_max - ring_off) / ds::kSeg);
-    stages = stages >= 32 ? 32 : (stages >= 16 ? 16 : 0);
+    stages = stages >= 48 ? 48 : (stages >= 32 ? 32 : (stages >= 16 ? 16 : 0));
     if (stages == 0) { delete d; return -6; }
     d->stages[mi] = stages;
     d->ring_off[mi] = ring_off;
@@ -1018,6 +1197,7 @@ void tb_decode_step_destroy(tb_decode_step* d) {
   if (d->d_cand_v) cudaFree(d->d_cand_v);
   if (d->d_cand_i) cudaFree(d->d_cand_i);
   if (d->d_bar) cudaFree(d->d_bar);
+  if (d->d_trace) cudaFree(d->d_trace);
   delete d;
 }
 
@@ -1029,6 +1209,24 @@ int tb_decode_step_launch(tb_decode_step* d, int batch, cudaStream_t stream) {
     case 2: return launch_m<ds::kW4>(d, batch, stream);
     default: return launch_m<ds::kA8W8>(d, batch, stream);
   }
+}
+
+/* diagnostics: the next launches record globaltimer stamps of every CTA's consumer pipeline (per projection: after the grid
+ * barrier, after activation staging, after the last stage, after the epilogue; per attention phase: after the barrier,
+ * after the items); out (host, grid x 2048 u64) receives them.  enable = 0 stops recording. */
+int tb_decode_step_trace(tb_decode_step* d, int enable, unsigned long long* out_host) {
+  if (!d) return -1;
+  const size_t bytes = (size_t) d->grid * ds::kTraceSlots * sizeof(unsigned long long);
+  if (enable && !d->d_trace) {
+    TB_CHECK_CUDA(cudaMalloc(&d->d_trace, bytes));
+    TB_CHECK_CUDA(cudaMemset(d->d_trace, 0, bytes));
+  }
+  if (out_host && d->d_trace) {
+    TB_CHECK_CUDA(cudaDeviceSynchronize());
+    TB_CHECK_CUDA(cudaMemcpy(out_host, d->d_trace, bytes, cudaMemcpyDeviceToHost));
+  }
+  d->p.trace = enable ? d->d_trace : nullptr;
+  return 0;
 }
 
 int tb_decode_step_info(const tb_decode_step* d, int batch, int* stages, size_t* smem_bytes, int* grid) {

@@ -674,6 +674,7 @@ int tbrt_set_sampling(tbrt_engine* e, int top_k, float top_p, float temperature,
   return 0;
 }
 int tbrt_set_decode_mode(tbrt_engine* e, int mode) { e->decode_mode = mode ? 1 : 0; return 0; }
+void* tbrt_decode_step_handle(tbrt_engine* e) { return e->ds; }
 int tbrt_fused_step_available(const tbrt_engine* e) { return e->ds ? tb_decode_step_max_batch() : 0; }
 int tbrt_last_steps(const tbrt_engine* e) { return e->last_steps; }
 void* tbrt_kv_cache(const tbrt_engine* e, int layer) { return (layer >= 0 && layer < (int) e->kv.size()) ? e->kv[layer] : nullptr; }
