@@ -183,7 +183,13 @@ typedef struct {
   float* logits;
   int32_t *ids, *seq_lens, *step_pos, *out_ids, *next_ids;
   const int32_t *in_lens, *max_in;
+  /* tensor parallel (cfg.tp_size > 1): rank r's peer-mapped scratch of tb_decode_step_tp_bytes() bytes, zero-initialised,
+   * as mapped into this process (tp_peers[tp_rank] is the local one) — e.g. tb_ar_extra().  The gathered fp32 logits
+   * [max_batch, vocab] of a tensor-parallel step are at tb_decode_step_tp_logits(). */
+  void* tp_peers[8];
 } tb_decode_step_buffers;
+size_t tb_decode_step_tp_bytes(const tb_decode_step_config* cfg);
+const float* tb_decode_step_tp_logits(const tb_decode_step* d);
 int tb_decode_step_max_batch(void);
 int tb_decode_step_create(tb_decode_step** out, const tb_decode_step_config* cfg, const tb_decode_step_layer* layers,
                           const tb_decode_step_buffers* buffers);
@@ -210,6 +216,12 @@ int tb_mma_peak(int kind, int iters, int ctas, int* sink, double* ops_out, tb_st
  * (rank-ordered fp32 sum: bit-identical on all ranks).                                                        */
 typedef struct tb_ar tb_ar;
 int tb_ar_create(tb_ar** out, int rank, int world, size_t max_bytes);
+/* same, with `extra_bytes` of additional zero-initialised peer-mapped memory behind the all-reduce buffers (the fused decode
+ * step keeps its cross-GPU flags, partial sums, arg-max candidates and gathered logits there); tb_ar_extra(a, r) is rank
+ * r's copy of that area as mapped into this process (valid for r != own rank after tb_ar_open_peers). */
+int tb_ar_create_ex(tb_ar** out, int rank, int world, size_t max_bytes, size_t extra_bytes);
+void* tb_ar_extra(tb_ar* a, int r);
+size_t tb_ar_extra_bytes(tb_ar* a);
 void tb_ar_destroy(tb_ar* a);
 int tb_ar_ipc_handle(tb_ar* a, void* out64);
 int tb_ar_open_peers(tb_ar* a, const void* handles);

@@ -1,5 +1,7 @@
-"""Run under torchrun with N ranks (one per GPU): the tensor-parallel engine (NCCL AllReduce / AllGather plugins) must
-reproduce the CPU oracle's logits and greedy ids.  Driven by tests/test_tp_gpu.py when >= 2 GPUs are visible."""
+"""Run under torchrun with N ranks (one per GPU): the tensor-parallel engine must reproduce the CPU oracle's logits and
+greedy ids on BOTH decode paths — the fused step kernel (partial sums / flags / arg-max candidates exchanged through peer
+memory inside the one persistent kernel) and the per-operator plugin schedule (one-shot NVLink all-reduce kernel or the
+NCCL AllReduce / AllGather plugins).  Driven by tests/test_tp_gpu.py when >= 2 GPUs are visible."""
 import ctypes as C
 import os
 import sys
@@ -48,11 +50,25 @@ def main():
     if os.environ.get("TB_TP_NCCL_ONLY") != "1":
         sess.enable_peer_allreduce()      # fused NVLink all-reduce + residual on the decode path
     sess.setup(B, S, new)
-    logits = [sess.context(torch.from_numpy(ids), torch.from_numpy(lens)).cpu().numpy()]
-    for _ in range(new - 1):
-        logits.append(sess.step().cpu().numpy())
-    got = np.stack(logits, 1)
-    got_ids = sess.output_ids(new).cpu().numpy()
+    runs = {}
+    for path, fused in (("fused", True), ("plugins", False)):
+        sess.set_decode_mode(fused)
+        logits = [sess.context(torch.from_numpy(ids), torch.from_numpy(lens)).cpu().numpy()]
+        launches = []
+        for _ in range(new - 1):
+            logits.append(sess.step().cpu().numpy())
+            launches.append(int(sess.last_launches))
+        runs[path] = (np.stack(logits, 1), sess.output_ids(new).cpu().numpy(), launches)
+        dist.barrier()
+    if os.environ.get("TB_TP_NCCL_ONLY") != "1" and B <= sess.fused_step_max_batch:
+        assert set(runs["fused"][2]) == {1}, f"the fused step did not run under tensor parallelism: {runs['fused'][2]}"
+    assert min(runs["plugins"][2]) > 10
+    # every rank must hold the same ids (the arg-max candidates of all vocabulary shards reach every rank)
+    for path in runs:
+        t = torch.from_numpy(runs[path][1]).cuda()
+        ref_t = t.clone()
+        dist.broadcast(ref_t, 0)
+        assert torch.equal(t, ref_t), f"{path}: rank {rank} generated different ids than rank 0"
     if rank == 0:
         # the reference quantises each rank's shard separately (LQ/weight_quant.py:264-271); the oracle must do the same:
         # per-output-channel scales of column-parallel weights are shard-independent, row-parallel ones are not
@@ -74,14 +90,18 @@ def main():
         ref_ids, ref = RM.OracleLlama(cfg, ow, "fp16", int8_kv, kv_scale=4.0 / 127.0, max_seq_len=S + new).generate(
             ids, lens, new, return_logits=True)
         tol = 2e-2 * max(1.0, float(np.abs(ref).max()))
-        for s in range(new):
-            np.testing.assert_allclose(got[:, s], ref[:, s], atol=tol, err_msg=f"step {s}")
-            top2 = np.sort(ref[:, s], -1)[:, -2:]
-            dec = (top2[:, 1] - top2[:, 0]) > 2 * tol
-            assert np.array_equal(got_ids[dec, s], ref_ids[dec, s])
-            if not np.array_equal(got_ids[:, s], ref_ids[:, s]):
-                break
-        print(f"TP{world} {mode} OK maxdiff {np.abs(got - ref).max():.4f} tol {tol:.4f}")
+        for path, (got, got_ids, _) in runs.items():
+            for s in range(new):
+                np.testing.assert_allclose(got[:, s], ref[:, s], atol=tol, err_msg=f"{path} step {s}")
+                top2 = np.sort(ref[:, s], -1)[:, -2:]
+                dec = (top2[:, 1] - top2[:, 0]) > 2 * tol
+                assert np.array_equal(got_ids[dec, s], ref_ids[dec, s]), f"{path} step {s}"
+                if not np.array_equal(got_ids[:, s], ref_ids[:, s]):
+                    break
+        # both paths round at the same points (fp16 partial -> fp32 rank-ordered sum -> fp16 -> + residual)
+        same = np.array_equal(runs["fused"][1], runs["plugins"][1])
+        print(f"TP{world} {mode} OK maxdiff fused {np.abs(runs['fused'][0] - ref).max():.4f} plugins "
+              f"{np.abs(runs['plugins'][0] - ref).max():.4f} tol {tol:.4f} ids_equal_between_paths {same}")
     dist.barrier()
     dist.destroy_process_group()
 

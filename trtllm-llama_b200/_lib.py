@@ -142,6 +142,11 @@ SIGNATURES.update({
     "tbrt_ar_handle": (i32, [vp, vp]),
     "tbrt_ar_open": (i32, [vp, vp]),
     "tb_ar_create": (i32, [_P(vp), i32, i32, sz]),
+    "tb_ar_create_ex": (i32, [_P(vp), i32, i32, sz, sz]),
+    "tb_ar_extra": (vp, [vp, i32]),
+    "tb_ar_extra_bytes": (sz, [vp]),
+    "tb_decode_step_tp_bytes": (sz, [vp]),
+    "tb_decode_step_tp_logits": (vp, [vp]),
     "tb_ar_destroy": (None, [vp]),
     "tb_ar_ipc_handle": (i32, [vp, vp]),
     "tb_ar_open_peers": (i32, [vp, vp]),

@@ -125,22 +125,26 @@ using namespace tb;
 
 struct tb_ar {
   int rank = 0, world = 1;
-  size_t max_bytes = 0;
-  uint8_t* local = nullptr;                 // [2 sets][max_bytes] data, then [2][8] flags, [2] epochs, [2] arrive
+  size_t max_bytes = 0, extra_bytes = 0;
+  uint8_t* local = nullptr;                 // [2 sets][max_bytes] data, then [2][8] flags, [2] epochs, [2] arrive, then `extra`
   uint8_t* peer[kArMaxWorld] = {nullptr};   // mapped bases (peer[rank] == local)
   bool opened = false;
 };
 
-static size_t ar_total_bytes(size_t max_bytes) { return 2 * max_bytes + 1024; }
+static size_t ar_total_bytes(size_t max_bytes, size_t extra = 0) { return 2 * max_bytes + 1024 + extra; }
 
 extern "C" {
 
 int tb_ar_create(tb_ar** out, int rank, int world, size_t max_bytes) {
+  return tb_ar_create_ex(out, rank, world, max_bytes, 0);
+}
+int tb_ar_create_ex(tb_ar** out, int rank, int world, size_t max_bytes, size_t extra_bytes) {
   if (!out || world < 2 || world > kArMaxWorld || rank < 0 || rank >= world) return -1;
   auto* a = new tb_ar();
   a->rank = rank; a->world = world; a->max_bytes = (max_bytes + 255) & ~(size_t) 255;
-  TB_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&a->local), ar_total_bytes(a->max_bytes)));
-  TB_CHECK_CUDA(cudaMemset(a->local, 0, ar_total_bytes(a->max_bytes)));
+  a->extra_bytes = (extra_bytes + 255) & ~(size_t) 255;
+  TB_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&a->local), ar_total_bytes(a->max_bytes, a->extra_bytes)));
+  TB_CHECK_CUDA(cudaMemset(a->local, 0, ar_total_bytes(a->max_bytes, a->extra_bytes)));
   TB_CHECK_CUDA(cudaDeviceSynchronize());
   a->peer[rank] = a->local;
   *out = a;
@@ -173,6 +177,13 @@ int tb_ar_open_peers(tb_ar* a, const void* handles /* world x 64 bytes, rank ord
   a->opened = true;
   return 0;
 }
+/* rank r's `extra` area as mapped into this process (r == own rank: the local one); NULL before tb_ar_open_peers */
+void* tb_ar_extra(tb_ar* a, int r) {
+  if (!a || r < 0 || r >= a->world || !a->peer[r] || a->extra_bytes == 0) return nullptr;
+  if (r != a->rank && !a->opened) return nullptr;
+  return a->peer[r] + 2 * a->max_bytes + 1024;
+}
+size_t tb_ar_extra_bytes(tb_ar* a) { return a ? a->extra_bytes : 0; }
 /* local buffer a row-parallel projection should write its partial result to, for call-site parity `set` */
 void* tb_ar_buffer(tb_ar* a, int set) { return a->local + (size_t) (set & 1) * a->max_bytes; }
 

@@ -132,6 +132,7 @@ struct tbrt_engine {
   std::map<int, int> eager_steps;
   cudaStream_t cap_stream = nullptr;
   tb_decode_step* ds = nullptr; // whole-step persistent kernel (csrc/decode_step.cu); NULL when the configuration is not taken
+  bool last_step_fused = false;
   int decode_mode = 1;          // 1: fused step kernel whenever available; 0: per-operator plugin schedule (CUDA graph)
   // sampling (SamplingConfig, generation.py:119-138): top_k = 1 / top_p = 0 is greedy arg-max
   int top_k = 1;
@@ -555,7 +556,8 @@ int tbrt_engine::step_body(cudaStream_t s) {
 // step state the plugin schedule uses (either path can run any step).  Not an error when the configuration is not taken.
 void tbrt_engine::build_decode_step() {
   static const bool off = getenv("TB_DECODE_STEP") && atoi(getenv("TB_DECODE_STEP")) == 0;
-  if (off || c.tp_size != 1) return;
+  if (off || ds) return;
+  if (c.tp_size > 1 && !(ar && ar_open && tb_ar_extra_bytes(ar) > 0)) return;   // needs the peers' scratch mapped
   tb_decode_step_config dc{};
   dc.kind = c.mode; dc.layers = c.layers; dc.hidden = c.hidden; dc.heads_local = Hl; dc.inter_local = inter_l;
   dc.vocab_local = vocab_l; dc.vocab = c.vocab; dc.max_batch = c.max_batch; dc.max_seq_len = S_max; dc.int8_kv = c.int8_kv;
@@ -570,6 +572,7 @@ void tbrt_engine::build_decode_step() {
   db.emb = emb; db.ln_f = ln_f; db.lm_head = lm_head; db.h_a = h; db.h_b = h2; db.qkv = qkv; db.att = att; db.act = act;
   db.logits = logits; db.ids = d_ids; db.seq_lens = d_seq_lens; db.step_pos = d_step_pos; db.out_ids = d_out_ids;
   db.next_ids = d_next; db.in_lens = d_in_lens; db.max_in = d_max_in;
+  for (int r = 0; r < 8; ++r) db.tp_peers[r] = (c.tp_size > 1 && r < c.tp_size) ? tb_ar_extra(ar, r) : nullptr;
   if (tb_decode_step_create(&ds, &dc, dl.data(), &db) != 0) ds = nullptr;
 }
 
@@ -650,7 +653,11 @@ int tbrt_finalize(tbrt_engine* e) {
       e->alloc(e->d_prompt, Mmax * 4) || e->alloc(e->d_dummy_scale, 4))
     return -1;
   RT_CUDA(cudaMemset(e->d_dummy_scale, 0, 4));
-  if (c.tp_size > 1 && c.tp_size <= 8) RT_CALL(tb_ar_create(&e->ar, c.tp_rank, c.tp_size, (size_t) 8 * c.hidden * 2));
+  if (c.tp_size > 1 && c.tp_size <= 8) {
+    tb_decode_step_config dc{};
+    dc.hidden = c.hidden; dc.vocab = c.vocab; dc.tp_size = c.tp_size;
+    RT_CALL(tb_ar_create_ex(&e->ar, c.tp_rank, c.tp_size, (size_t) 8 * c.hidden * 2, tb_decode_step_tp_bytes(&dc)));
+  }
   e->build_decode_step();
   RT_CUDA(cudaDeviceSynchronize());
   e->finalized = true;
@@ -658,7 +665,11 @@ int tbrt_finalize(tbrt_engine* e) {
 }
 
 size_t tbrt_device_bytes(const tbrt_engine* e) { return e->dev_bytes; }
-const float* tbrt_logits(const tbrt_engine* e) { return e->logits; }
+const float* tbrt_logits(const tbrt_engine* e) {
+  // a tensor-parallel fused step gathers the vocabulary shards into its peer-mapped scratch
+  if (e->last_step_fused && e->c.tp_size > 1) return tb_decode_step_tp_logits(e->ds);
+  return e->logits;
+}
 const int32_t* tbrt_output_ids(const tbrt_engine* e) { return e->d_out_ids; }
 int tbrt_set_end_id(tbrt_engine* e, int end_id) { e->end_id = end_id; return 0; }
 int tbrt_set_sampling(tbrt_engine* e, int top_k, float top_p, float temperature, unsigned long long seed) {
@@ -688,6 +699,7 @@ int tbrt_ar_open(tbrt_engine* e, const void* handles) {
   if (!e->ar) return fail("no peer all-reduce context (tp_size == 1 or engine not finalized)");
   RT_CALL(tb_ar_open_peers(e->ar, handles));
   e->ar_open = true;
+  e->build_decode_step();       // tensor parallel: the fused step pushes partial sums / flags into the peers' scratch
   return 0;
 }
 
@@ -695,7 +707,7 @@ int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_length
   if (!e->finalized) return fail("engine not finalized");
   if (batch < 1 || batch > e->c.max_batch || seq < 1 || seq > e->c.max_input_len) return fail("batch / seq outside the engine limits");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
-  e->B = batch; e->S_in = seq; e->steps_done = 0; e->launches = 0; e->ar_site = 0;
+  e->B = batch; e->S_in = seq; e->steps_done = 0; e->launches = 0; e->ar_site = 0; e->last_step_fused = false;
   const int M = batch * seq;
   // step state: the first generated token lands in column 0; every sequence of the padded batch sits at
   // position seq afterwards (sequence_length = max_input_len + step, generation.py:686-687)
@@ -716,6 +728,7 @@ int tbrt_step(tbrt_engine* e, tb_stream_t st) {
   if (e->S_in + e->steps_done + 1 >= e->S_max) return fail("KV cache is full");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
   e->steps_done += 1;
+  e->last_step_fused = e->fused_step();
   if (e->fused_step()) {
     e->launches = 1;
     RT_CALL(tb_decode_step_launch(e->ds, e->B, st));
