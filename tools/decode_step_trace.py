@@ -25,7 +25,7 @@ def main():
     import bench
     cx = bench.Ctx(args)
     mode, int8_kv, B, in_len, out_len, _ = bench.WORKLOADS[args.workload]
-    sess, tensors = bench.build_session(cx, mode, int8_kv, B, in_len, out_len, 1, 0)
+    sess, tensors = bench.build_session(cx, mode, int8_kv, B, in_len, out_len, cx.world, cx.rank)
     lib = cx.lib
     ids = torch.randint(3, 32000, (B, in_len), dtype=torch.int32).cuda()
     lens = torch.full((B,), in_len, dtype=torch.int32).cuda()
@@ -45,6 +45,9 @@ def main():
     torch.cuda.synchronize()
     out = np.zeros((G, SL), np.uint64)
     assert lib.tb_decode_step_trace(h, 0, out.ctypes.data_as(C.c_void_p)) == 0
+    if cx.rank != 0:
+        cx.barrier()
+        return
     L = 32
     t = out.astype(np.int64)
     t0 = t[:, 0].min()
@@ -89,6 +92,8 @@ def main():
         b = 1 + li * per
         lag.append(t[:, b + 3].max() - np.median(t[:, b + 3]))
     print(f"straggler lag at the qkv epilogue (slowest - median CTA): mean {np.mean(lag) / 1e3:.2f} us")
+    if cx.world > 1:
+        cx.barrier()
 
 
 if __name__ == "__main__":

@@ -132,7 +132,7 @@ __device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gs
 // ---- tensor-parallel scratch, identical on every rank (offsets into the peer-mapped area) --------------------------------
 //   flags   u32[8]                              flags[r] = number of cross-GPU barriers rank r has completed (monotonic)
 //   xepoch  u32                                 cross-GPU barriers completed before this launch (local bookkeeping)
-//   partial [2 sets][world][kMaxRows][hidden]   fp16 partial sums of a row-parallel projection, pushed by every rank
+//   partial [2 sets][world][kMaxRows][hidden]   4-byte granules {fp16 partial sum, 16-bit exchange tag}, pushed by every rank
 //   cand    [world][grid][kMaxRows] {f32, i32}  arg-max candidates of every rank's vocabulary shard
 //   logits  [kMaxRows][vocab] f32               all-gathered logits
 struct TpLayout {
@@ -143,7 +143,7 @@ __host__ __device__ inline TpLayout tp_layout(int hidden, int vocab, int grid) {
   l.flags = 0;
   l.xepoch = 128;
   l.partial = 256;
-  l.cand = l.partial + (size_t) 2 * 8 * kMaxRows * hidden * 2;
+  l.cand = l.partial + (size_t) 2 * 8 * kMaxRows * hidden * 4;
   l.logits = (l.cand + (size_t) 8 * grid * kMaxRows * 8 + 255) & ~(size_t) 255;
   l.total = l.logits + (size_t) kMaxRows * vocab * 4;
   return l;
@@ -168,9 +168,9 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
 // published `xe`.  The local counter keeps the same accounting as grid_arrive (one arrival per CTA per barrier).
 __device__ __forceinline__ void xgrid_arrive(const Params& p, unsigned long long* bar, unsigned long long target_after,
                                              uint32_t xe, int ctid) {
-  __threadfence_system();
   cbar();
   if (ctid == 0) {
+    __threadfence_system();      // the CTA's remote stores (ordered before this thread by the CTA barrier), system-wide
     unsigned long long old;
     asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], 1;" : "=l"(old) : "l"(bar) : "memory");
     if (old + 1 == target_after) {
@@ -185,7 +185,13 @@ __device__ __forceinline__ void xgrid_wait(const Params& p, uint32_t xe, int cti
     const TpLayout l = tp_layout(p.hidden, p.vocab, gridDim.x);
     const uint32_t* f = reinterpret_cast<const uint32_t*>(p.peer[p.rank] + l.flags) + ctid;
     const long long t0 = clock64();
-    while ((int32_t) (ld_acquire_sys_u32(f) - xe) < 0) {
+    for (;;) {
+      uint32_t v;
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int32_t) (v - xe) >= 0) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        break;
+      }
       if (clock64() - t0 > 40000000000ll) {      // a peer died or never launched: trap instead of hanging the GPU
         printf("[trtllm_b200] decode_step cross-GPU barrier timed out (rank %d waiting for %d, block %d)\n", p.rank, ctid,
                blockIdx.x);
@@ -385,16 +391,20 @@ __device__ __forceinline__ void load_gamma(const __half* gamma, int K, uint4 (&g
 // Tensor parallel: the row is not in memory yet — it is residual + sum over ranks of the fp16 partials every rank pushed
 // into this rank's scratch (rank order, fp32; rounding points as allreduce.cu: fp16(sum), then fp16(sum + residual)).
 // CTA 0 also stores the reduced row (the new residual stream) for the epilogues that add it later.
+// No barrier guards the partials: every 4-byte granule carries the 16-bit tag of its exchange next to the fp16 value (the
+// NCCL "LL" idea: data and flag in one atomic store), so the reader simply polls the granules it needs until all of them
+// show the tag — one NVLink hop after the producer's store, no fence, no flag round trip.
 struct ReduceSrc {
-  const uint8_t* partial;     // [world][kMaxRows][hidden] fp16 of the current set (local scratch), or NULL: plain rows
+  const uint8_t* partial;     // [world][kMaxRows][hidden] granules of the current set (local scratch), or NULL: plain rows
   __half* store;              // [kMaxRows][hidden] (hA or hB)
   int world, hidden;
+  uint32_t tag;               // 16-bit tag of the exchange
 };
 
 template <int XFMT, int MB, int E>
 __device__ __forceinline__ void stage_x(const Params& p, const __half* const (&rows)[MB], int K, int mode,
                                         const uint4 (&gam)[3], uint8_t* xs, float* srow, float* red, int ctid,
-                                        const ReduceSrc rs = ReduceSrc{nullptr, nullptr, 1, 0}) {
+                                        const ReduceSrc rs = ReduceSrc{nullptr, nullptr, 1, 0, 0}) {
   constexpr int XB = xbytes_of(XFMT);
   constexpr int NV = E * XB / 16;                          // 16-byte vectors per chunk
   const int xstride = xrow_bytes(K, E, XB);
@@ -423,14 +433,24 @@ __device__ __forceinline__ void stage_x(const Params& p, const __half* const (&r
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] = 0.f;
           for (int r = 0; r < rs.world; ++r) {
-            const uint4 v = ld_volatile_v4(rs.partial + ((size_t) (r * kMaxRows + m) * rs.hidden + i) * 2);
-            const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = __half22float2(h[j]);
-              acc[2 * j] += f.x;
-              acc[2 * j + 1] += f.y;
+            const uint8_t* src = rs.partial + ((size_t) (r * kMaxRows + m) * rs.hidden + i) * 4;
+            uint4 a, b;
+            const long long t0 = clock64();
+            for (;;) {
+              a = ld_volatile_v4(src);
+              b = ld_volatile_v4(src + 16);
+              const uint32_t t = rs.tag;
+              if ((a.x >> 16) == t && (a.y >> 16) == t && (a.z >> 16) == t && (a.w >> 16) == t && (b.x >> 16) == t &&
+                  (b.y >> 16) == t && (b.z >> 16) == t && (b.w >> 16) == t)
+                break;
+              if (clock64() - t0 > 40000000000ll) {      // a peer died or never launched: trap instead of hanging the GPU
+                printf("[trtllm_b200] decode_step partial-sum exchange timed out (waiting for rank %d, block %d)\n", r, blockIdx.x);
+                __trap();
+              }
             }
+            const uint32_t g8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += __half2float(__ushort_as_half((unsigned short) (g8[j] & 0xffffu)));
           }
           __half2* h = reinterpret_cast<__half2*>(&raw[it]);
 #pragma unroll
@@ -716,10 +736,10 @@ __device__ __forceinline__ void epilogue(const Params& p, const Phase& f, int mo
       lgs[row * MB + m] = v[0];
     } else if (mode == 3) {
       // row-parallel projection under tensor parallelism: this rank's fp16 partial, pushed into every rank's scratch
-      const __half oh = __float2half_rn(v[0]);
+      const uint32_t gran = (uint32_t) __half_as_ushort(__float2half_rn(v[0])) | ((uint32_t) (ldy >> 1) << 16);   // ldy = tag << 1 | set
       const TpLayout l = tp_layout(p.hidden, p.vocab, gridDim.x);
-      const size_t off = l.partial + ((size_t) ((ldy /* set */ * 8 + p.rank) * kMaxRows + m) * p.hidden + n) * 2;
-      for (int r = 0; r < p.tp; ++r) *reinterpret_cast<__half*>(p.peer[r] + off) = oh;
+      const size_t off = l.partial + ((size_t) (((ldy & 1) * 8 + p.rank) * kMaxRows + m) * p.hidden + n) * 4;
+      for (int r = 0; r < p.tp; ++r) *reinterpret_cast<volatile uint32_t*>(p.peer[r] + off) = gran;
     } else if (mode == 1) {
       const float gte = __half2float(__float2half_rn(v[0])), up = __half2float(__float2half_rn(v[1]));
       y[(size_t) m * ldy + n] = __float2half_rn(__half2float(__float2half_rn(silu_f(gte))) * up);
@@ -971,24 +991,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
   const TpLayout tl = tp_layout(p.hidden, p.vocab, gridDim.x);
   const uint32_t xbase = tp ? *reinterpret_cast<const volatile uint32_t*>(p.peer[p.rank] + tl.xepoch) : 0u;
   uint32_t xk = 0;
-  bool xpending = false;                    // the barrier in front of the next phase is a cross-GPU one
+  bool xpending = false;                    // the barrier in front of the next phase is the cross-GPU one (end of step)
+  bool llpending = false;                   // the next phase's input arrives as tagged partial sums: no barrier at all
   auto wait_phase = [&]() {
-    if (xpending) xgrid_wait(p, xbase + xk, ctid);
-    else if (target) grid_wait(p.bar, target, ctid, p.debug);
+    if (xpending) xgrid_wait(p, xbase + 1, ctid);
+    else if (!llpending && target) grid_wait(p.bar, target, ctid, p.debug);
     xpending = false;
+    llpending = false;
   };
-  // after a phase whose outputs went to the peers: set index of the partial buffers = parity of the barrier count
   auto arrive_cross = [&]() {
-    ++xk;
     target += G;
-    xgrid_arrive(p, p.bar, target, xbase + xk, ctid);
+    xgrid_arrive(p, p.bar, target, xbase + 1, ctid);
     xpending = true;
   };
-  auto partial_set = [&]() { return (int) ((xbase + xk) & 1u); };          // set the NEXT cross barrier publishes
-  auto reduce_src = [&](int set, __half* store) {
-    return ReduceSrc{p.peer[p.rank] + tl.partial + (size_t) set * 8 * kMaxRows * p.hidden * 2, store, p.tp, p.hidden};
+  // exchanges of row-parallel partial sums: numbered xbase * (2 L) + xk (same on every rank); set = parity, tag = low 16 bits
+  const uint32_t ex_base = xbase * (uint32_t) (2 * p.n_layers) + 1u;
+  auto ex_tag = [&](uint32_t k) { return (ex_base + k) & 0xffffu; };
+  auto ex_set = [&](uint32_t k) { return (int) ((ex_base + k) & 1u); };
+  auto reduce_src = [&](uint32_t k, __half* store) {
+    return ReduceSrc{p.peer[p.rank] + tl.partial + (size_t) ex_set(k) * 8 * kMaxRows * p.hidden * 4, store, p.tp, p.hidden,
+                     ex_tag(k)};
   };
-  int last_set = 0;
+  uint32_t last_ex = 0;                     // the most recent exchange this CTA published
 
 #pragma unroll 1
   for (int li = 0; li < p.n_layers; ++li) {
@@ -1011,7 +1035,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
 #pragma unroll
         for (int m = 0; m < MB; ++m) rrow[m] = m < p.B ? p.hB + (size_t) m * p.hidden : nullptr;
         stage_x<XM, MB, epc_of(KIND)>(p, rrow, p.hidden, KIND == kA8W8 ? 2 : 1, gam, xs, srow, red, ctid,
-                                      reduce_src(last_set, p.hA));
+                                      reduce_src(last_ex, p.hA));
       } else {
         stage_x<XM, MB, epc_of(KIND)>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, gam, xs, srow, red, ctid);
       }
@@ -1069,10 +1093,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
       g += stages_of(f);
       if (tp) {
         // row-parallel: fp16 partial to every rank; the residual add happens where the all-reduce is consumed
-        last_set = partial_set() ^ 1;
-        epilogue<KIND, MB>(p, f, 3, part, srow, epre, false, nullptr, last_set, lgs, ctid);
+        last_ex = xk++;
+        epilogue<KIND, MB>(p, f, 3, part, srow, epre, false, nullptr, (int) (ex_tag(last_ex) << 1) | ex_set(last_ex), lgs, ctid);
         DS_STAMP();
-        arrive_cross();
+        llpending = true;
       } else {
         epilogue<KIND, MB>(p, f, 0, part, srow, epre, true, p.hB, p.hidden, lgs, ctid);
         DS_STAMP();
@@ -1096,7 +1120,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
         for (int m = 0; m < MB; ++m)
           rrow[m] = m < p.B ? (li == 0 ? p.emb + (size_t) p.ids[m] * p.hidden : p.hA + (size_t) m * p.hidden) : nullptr;
         stage_x<XM, MB, epc_of(KIND)>(p, rrow, p.hidden, KIND == kA8W8 ? 2 : 1, gam, xs, srow, red, ctid,
-                                      reduce_src(last_set, p.hB));
+                                      reduce_src(last_ex, p.hB));
       } else {
         stage_x<XM, MB, epc_of(KIND)>(p, hrow, p.hidden, KIND == kA8W8 ? 2 : 1, gam, xs, srow, red, ctid);
       }
@@ -1126,10 +1150,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
       DS_STAMP();
       g += stages_of(f);
       if (tp) {
-        last_set = partial_set() ^ 1;
-        epilogue<KIND, MB>(p, f, 3, part, srow, epre, false, nullptr, last_set, lgs, ctid);
+        last_ex = xk++;
+        epilogue<KIND, MB>(p, f, 3, part, srow, epre, false, nullptr, (int) (ex_tag(last_ex) << 1) | ex_set(last_ex), lgs, ctid);
         DS_STAMP();
-        arrive_cross();
+        llpending = true;
       } else {
         epilogue<KIND, MB>(p, f, 0, part, srow, epre, true, p.hA, p.hidden, lgs, ctid);
         DS_STAMP();
@@ -1151,7 +1175,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
       const __half* rrow[MB];
 #pragma unroll
       for (int m = 0; m < MB; ++m) rrow[m] = m < p.B ? p.hB + (size_t) m * p.hidden : nullptr;
-      stage_x<XL, MB, epc_of(kF16)>(p, rrow, p.hidden, 1, gam, xs, srow, red, ctid, reduce_src(last_set, p.hA));
+      stage_x<XL, MB, epc_of(kF16)>(p, rrow, p.hidden, 1, gam, xs, srow, red, ctid, reduce_src(last_ex, p.hA));
     } else {
       stage_x<XL, MB, epc_of(kF16)>(p, hrow, p.hidden, 1, gam, xs, srow, red, ctid);
     }
@@ -1232,7 +1256,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Params p
   if (ctid == 0) {
     p.step_pos[0] = pos + 1;
     *p.bar = 0ull;                 // every CTA has arrived at the last barrier and none reads the counter again
-    if (tp) *reinterpret_cast<volatile uint32_t*>(p.peer[p.rank] + tl.xepoch) = xbase + xk;
+    if (tp) *reinterpret_cast<volatile uint32_t*>(p.peer[p.rank] + tl.xepoch) = xbase + 1;   // launches completed
   }
 }
 
