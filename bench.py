@@ -340,6 +340,29 @@ def run_decode_workload(cx, name, steps, warmup, with_e2e=True, with_roofline=Tr
     torch.cuda.synchronize()
     step_ms = d0.elapsed_time(d1) / n_dec
     step_launches = int(sess.last_launches)
+    # ---- the other decode path on the same engine (fused persistent step kernel vs per-operator plugin schedule) -------
+    ab = None
+    if B <= sess.fused_step_max_batch:
+        fused_default = step_launches == 1
+        sess.set_decode_mode(not fused_default)
+        lib.tbrt_context(sess._e, dev_ids.data_ptr(), dev_lens.data_ptr(), B, in_len, st())
+        for _ in range(3):
+            lib.tbrt_step(sess._e, st())
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_dec):
+            lib.tbrt_step(sess._e, st())
+        a1.record()
+        torch.cuda.synchronize()
+        other_ms = a0.elapsed_time(a1) / n_dec
+        other_launches = int(sess.last_launches)
+        sess.set_decode_mode(None)
+        other_ms = cx.max_over_ranks([other_ms])[0]
+        ab = {"default_path": "fused persistent step kernel" if fused_default else "per-operator plugin schedule (CUDA graph)",
+              "fused_step_ms": round(step_ms if fused_default else other_ms, 4),
+              "plugin_schedule_ms": round(other_ms if fused_default else step_ms, 4),
+              "fused_kernels": 1, "plugin_kernels": other_launches if fused_default else step_launches}
     # ---- e2e: public API with pinned host buffers ----------------------------------------------------------
     e2e_ms, launches = 0.0, 0
     if with_e2e:
@@ -376,6 +399,8 @@ def run_decode_workload(cx, name, steps, warmup, with_e2e=True, with_roofline=Tr
                                "frac_of_hbm_peak": round(step_bytes / (step_ms * 1e-3) / 1e9 / cx.hbm, 4),
                                "hbm_floor_ms": round(hbm_ms, 4)},
                "roofline": roof, "clocks": clk, "gpu_launches": launches * (steps if with_e2e else 1)}
+        if ab:
+            res["decode_paths"] = ab
         if with_e2e:
             res["e2e"] = {"value": round(B * out_len * steps / (e2e_ms * 1e-3), 2), "unit": "tokens/s",
                           "h2d_bytes_per_step": int(B * in_len * 4 + B * 4), "d2h_bytes_per_step": int(B * out_len * 4)}
@@ -642,6 +667,8 @@ def main():
                        "step_definition": "one request = context phase + out_len-1 generation steps (CUDA-graph replays)"},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "decode_step": head["decode_step"],
             "context_ms": head["context_ms"], "roofline": head["roofline"], "clocks": head["clocks"]}
+    if "decode_paths" in head:
+        line["decode_paths"] = head["decode_paths"]
     if "limits" in head:
         line["limits"] = head["limits"]
     if parity is not None:

@@ -84,9 +84,10 @@ int tbrt_set_end_id(tbrt_engine* e, int end_id);
  * nucleus sampling over the vocabulary; temperature scales the logits first (tb_sample).  The random stream is keyed by
  * (seed, generation step, batch row).  Beam search (num_beams > 1) is not built. */
 int tbrt_set_sampling(tbrt_engine* e, int top_k, float top_p, float temperature, unsigned long long seed);
-/* Generation steps run as ONE persistent kernel (tb_decode_step_*) whenever the engine's configuration and the batch allow
- * it (mode 1, default); mode 0 forces the per-operator plugin schedule (IPluginV2DynamicExt::enqueue per operator, CUDA
- * graph) — same weights, caches and step state, so the two can be compared step by step.
+/* Generation steps can run as ONE persistent kernel (tb_decode_step_*) whenever the engine's configuration and the batch
+ * allow it (mode 1); mode 0 forces the per-operator plugin schedule (IPluginV2DynamicExt::enqueue per operator, CUDA
+ * graph) — same weights, caches and step state, so the two can be compared step by step.  Mode -1 (default) picks the
+ * path that measured faster on B200: the persistent kernel under tensor parallelism, the plugin schedule on one GPU.
  * tbrt_fused_step_available: largest batch the fused step takes for this engine (0: not available). */
 int tbrt_set_decode_mode(tbrt_engine* e, int mode);
 int tbrt_fused_step_available(const tbrt_engine* e);

@@ -1290,7 +1290,7 @@ int launch_t(tb_decode_step* d, int B, cudaStream_t stream) {
   static const int pf_env = getenv("TB_DS_PREFETCH") ? atoi(getenv("TB_DS_PREFETCH")) : 0;   // A/B switch (stages)
   p.prefetch = pf_env;
   static const int il_env = getenv("TB_DS_INTERLEAVE") ? atoi(getenv("TB_DS_INTERLEAVE")) : 1;   // A/B switch
-  p.interleave = il_env;
+  p.interleave = d->p.tp > 1 ? 0 : il_env;   // tensor parallel: contiguous channels per CTA -> coalesced stores to the peers
   static const int dbg_env = getenv("TB_DS_DEBUG") ? atoi(getenv("TB_DS_DEBUG")) : 0;
   p.debug = dbg_env;
   p.xs_off = ds::off_xs(MB);

@@ -187,10 +187,11 @@ class GenerationSession:
     def device_bytes(self):
         return lib.tbrt_device_bytes(self._e)
 
-    def set_decode_mode(self, fused: bool):
-        """True (default): generation steps run as one persistent kernel when the engine / batch allow it;
-        False: the per-operator plugin schedule (one IPluginV2DynamicExt.enqueue per operator, CUDA graph)."""
-        lib.tbrt_set_decode_mode(self._e, int(bool(fused)))
+    def set_decode_mode(self, fused):
+        """True: generation steps run as one persistent kernel when the engine / batch allow it; False: the per-operator
+        plugin schedule (one IPluginV2DynamicExt.enqueue per operator, CUDA graph); None (default): whichever measured
+        faster on B200 (the persistent kernel under tensor parallelism, the plugin schedule on one GPU)."""
+        lib.tbrt_set_decode_mode(self._e, -1 if fused is None else int(bool(fused)))
 
     @property
     def fused_step_max_batch(self):
