@@ -49,11 +49,12 @@ def parse_arguments():
     p.add_argument('--int8_kv_cache', default=False, action="store_true")
     p.add_argument('--random_seed', type=int, default=None)
     p.add_argument('--paged_kv_cache', action="store_true", default=False)
+    p.add_argument('--tokens_per_block', type=int, default=64, help='paged KV cache block size (a power of two >= 16)')
     args = p.parse_args()
     if args.dtype != 'float16':
         p.error("only --dtype float16 is built on this path")
-    if args.n_kv_head not in (None, args.n_head) or args.paged_kv_cache or args.remove_input_padding or args.max_beam_width != 1:
-        p.error("multi-query attention, paged KV cache, packed input and beam search are out of scope (DESIGN.md)")
+    if args.n_kv_head not in (None, args.n_head) or args.remove_input_padding or args.max_beam_width != 1:
+        p.error("multi-query attention, packed input and beam search are out of scope (DESIGN.md)")
     if args.use_smooth_quant and not (args.per_token and args.per_channel):
         p.error("SmoothQuant is built for --per_token --per_channel")
     return args
@@ -69,7 +70,8 @@ def main():
     qm = B.quant_mode_from_args(args)
     mc = ModelConfig(vocab_size=args.vocab_size, num_layers=args.n_layer, num_heads=args.n_head, hidden_size=args.n_embd,
                      inter_size=args.inter_size, quant_mode=qm, max_batch_size=args.max_batch_size,
-                     max_input_len=args.max_input_len, max_output_len=args.max_output_len, tp_size=args.world_size)
+                     max_input_len=args.max_input_len, max_output_len=args.max_output_len, tp_size=args.world_size,
+                     paged_kv_cache=args.paged_kv_cache, tokens_per_block=args.tokens_per_block)
     dev = "cuda" if torch.cuda.is_available() else "cpu"       # quantisation is build-time work; a GPU only makes it fast
     weights = (B.load_from_ft_llama(args.model_dir, mc, dev) if args.model_dir
                else B.random_llama_weights(mc, seed=args.random_seed or 0, device=dev))
@@ -85,7 +87,8 @@ def main():
                                  "weight_only_quant_matmul_plugin": "float16" if args.use_weight_only else False,
                                  "rmsnorm_quantization_plugin": "float16" if args.use_smooth_quant else False,
                                  "nccl_plugin": "float16" if args.world_size > 1 else False,
-                                 "remove_input_padding": False, "paged_kv_cache": False})
+                                 "remove_input_padding": False, "paged_kv_cache": bool(args.paged_kv_cache),
+                                 "tokens_per_block": args.tokens_per_block})
     print(f"Total time of building all {args.world_size} engines: {time.strftime('%H:%M:%S', time.gmtime(time.time() - tik))}")
 
 

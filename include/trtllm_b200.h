@@ -108,6 +108,20 @@ int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* se
                        const float* kv_scale_quant_orig, void* workspace, int* counters, int batch, int num_heads,
                        int head_size, int max_seq_len, int past_len, int max_input_len, int len_cap, int rotary_dim,
                        float q_scaling, int int8_kv, int nsplit, tb_stream_t stream);
+/* Paged KV cache (GPTAttention field paged_kv_cache; K/kvCacheUtils.h:34-112 KVBlockArray, beam width 1): instead of one
+ * buffer, block_pointers [B, 2, max_blocks_per_seq] (int64 device addresses; K table then V table per sequence, as
+ * T/tensorrt_llm/runtime/kv_cache_manager.py:163-184 builds it) name blocks of tokens_per_block positions laid out
+ * [H, tokens_per_block, Dh]; position t of head h is row h * tokens_per_block + t % tokens_per_block of block
+ * t / tokens_per_block.  tokens_per_block: a power of two >= 16.  Everything else as tb_mmha_decode_dev. */
+int tb_mmha_decode_paged(void* out, const void* qkv, const int64_t* block_pointers, int tokens_per_block,
+                         int max_blocks_per_seq, const int* seq_lens, const int* input_lengths, const int* masked_tokens,
+                         const int* max_input_len_dev, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
+                         int batch, int num_heads, int head_size, int past_len, int max_input_len, int len_cap,
+                         int rotary_dim, float q_scaling, int int8_kv, int nsplit, tb_stream_t stream);
+int tb_context_attention_paged(void* out, void* qkv, const int64_t* block_pointers, int tokens_per_block,
+                               int max_blocks_per_seq, const int* input_lengths, const float* kv_scale_orig_quant,
+                               void* workspace, int batch, int seq_len, int num_heads, int head_size, int rotary_dim,
+                               float q_scaling, int int8_kv, tb_stream_t stream);
 /* context phase: replaces GPTAttentionPluginCommon::enqueueContext (gptAttentionCommon.cpp:361-620).
  * qkv [B,S,3*H*Dh] fp16 is rotated in place (q,k), out [B,S,H*Dh].
  * workspace: non-NULL (tb_context_attention_workspace_bytes(), a nominal 256 bytes since V is consumed in place as an

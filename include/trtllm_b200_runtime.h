@@ -34,6 +34,7 @@ typedef struct {
   int32_t max_batch, max_input_len, max_output_len; /* builder limits (LQ/build.py:73-75) */
   int32_t tp_size, tp_rank;   /* Mapping(world_size, rank) (T/tensorrt_llm/mapping.py) */
   int32_t use_cuda_graph;
+  int32_t paged_kv_tokens_per_block; /* --paged_kv_cache (LQ/build.py:190-196): 0 = contiguous cache; else a power of two >= 16 */
 } tbrt_config;
 
 tbrt_engine* tbrt_create(const tbrt_config* cfg);
@@ -79,6 +80,13 @@ int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_l
 int tbrt_ar_handle(tbrt_engine* e, void* out64);
 int tbrt_ar_open(tbrt_engine* e, const void* handles);
 int tbrt_set_end_id(tbrt_engine* e, int end_id);
+/* Paged KV cache (cfg.paged_kv_tokens_per_block > 0): every layer owns a pool of max_batch * tbrt_kv_max_blocks_per_seq()
+ * blocks [2][blocks][H/tp][tokens_per_block][Dh]; the host assigns pool blocks to sequences (KVCacheManager of
+ * T/tensorrt_llm/runtime/kv_cache_manager.py) and hands the table over before the context phase and whenever a sequence
+ * grows into a new block: block_ids host int32 [batch, blocks_per_seq], -1 = not allocated.  The engine turns it into the
+ * per-layer pointer tables the GPTAttention plugin reads (block_pointers input). */
+int tbrt_kv_max_blocks_per_seq(const tbrt_engine* e);
+int tbrt_set_kv_blocks(tbrt_engine* e, const int32_t* host_block_ids, int batch, int blocks_per_seq, tb_stream_t s);
 /* SamplingConfig (T/tensorrt_llm/runtime/generation.py:119-138): top_k = 1 (default) is greedy arg-max; top_k > 1 samples
  * among the k largest logits (top_p > 0 additionally restricts to that share of their mass); top_k = 0 with top_p > 0 is
  * nucleus sampling over the vocabulary; temperature scales the logits first (tb_sample).  The random stream is keyed by

@@ -43,6 +43,9 @@ SIGNATURES = {
     "tb_mmha_set_mode": (i32, [i32]),
     "tb_mmha_decode_dev": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32,
                                  i32, i32, vp]),
+    "tb_mmha_decode_paged": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, i32,
+                                   i32, vp]),
+    "tb_context_attention_paged": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, vp]),
     "tb_context_attention_workspace_bytes": (sz, [i32, i32, i32]),
     "tb_context_attention": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, i32, vp]),
     "tb_embedding": (i32, [vp, vp, vp, i32, i32, i32, vp]),
@@ -73,7 +76,8 @@ class TbrtConfig(C.Structure):
     """== tbrt_config (include/trtllm_b200_runtime.h)"""
     _fields_ = [("hidden", i32), ("heads", i32), ("inter", i32), ("layers", i32), ("vocab", i32), ("head_size", i32),
                 ("rms_eps", f32), ("mode", i32), ("int8_kv", i32), ("max_batch", i32), ("max_input_len", i32),
-                ("max_output_len", i32), ("tp_size", i32), ("tp_rank", i32), ("use_cuda_graph", i32)]
+                ("max_output_len", i32), ("tp_size", i32), ("tp_rank", i32), ("use_cuda_graph", i32),
+                ("paged_kv_tokens_per_block", i32)]
 
 
 class TbpField(C.Structure):
@@ -135,6 +139,8 @@ SIGNATURES.update({
     "tbrt_last_launches": (i64, [vp]),
     "tbrt_set_end_id": (i32, [vp, i32]),
     "tbrt_set_decode_mode": (i32, [vp, i32]),
+    "tbrt_kv_max_blocks_per_seq": (i32, [vp]),
+    "tbrt_set_kv_blocks": (i32, [vp, vp, i32, i32, vp]),
     "tbrt_set_sampling": (i32, [vp, i32, f32, f32, C.c_uint64]),
     "tbrt_fused_step_available": (i32, [vp]),
     "tbrt_last_steps": (i32, [vp]),

@@ -86,8 +86,10 @@ def save_config(path, *, precision, world_size, mc: ModelConfig, plugin_config: 
 
 def model_config_from_json(path, rank=0) -> ModelConfig:
     with open(path) as f:
-        c = json.load(f)["builder_config"]
-    return ModelConfig(vocab_size=c["vocab_size"], num_layers=c["num_layers"], num_heads=c["num_heads"],
+        full = json.load(f)
+    c, pc = full["builder_config"], full.get("plugin_config", {})
+    return ModelConfig(paged_kv_cache=bool(pc.get("paged_kv_cache", False)), tokens_per_block=int(pc.get("tokens_per_block", 64)),
+                       vocab_size=c["vocab_size"], num_layers=c["num_layers"], num_heads=c["num_heads"],
                        hidden_size=c["hidden_size"], inter_size=c["inter_size"], rms_eps=c.get("rms_eps", 1e-6),
                        quant_mode=QuantMode(c.get("quant_mode", 0)), max_batch_size=c["max_batch_size"],
                        max_input_len=c["max_input_len"], max_output_len=c["max_output_len"],

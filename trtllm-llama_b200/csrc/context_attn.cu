@@ -31,7 +31,8 @@ constexpr int kD = 128;
 constexpr int kPrepThreads = 256;
 __global__ void __launch_bounds__(kPrepThreads) ctx_prep_kernel(__half* qkv, void* kv_cache, const int* input_lengths,
                                                                 const float* kv_scale_orig_quant, int S, int H, int S_max,
-                                                                int rotary_dim, int int8_kv) {
+                                                                int rotary_dim, int int8_kv, const long long* block_ptrs,
+                                                                int tpb_log2, int max_blocks) {
   __shared__ float cs[kD / 2], sn_s[kD / 2];
   const int tok = blockIdx.x;
   const int b = tok / S, s = tok % S;
@@ -81,8 +82,15 @@ __global__ void __launch_bounds__(kPrepThreads) ctx_prep_kernel(__half* qkv, voi
       vlo = *reinterpret_cast<const uint4*>(row + 2 * hidden + g8 * 8);
       vhi = *reinterpret_cast<const uint4*>(row + 2 * hidden + 64 + g8 * 8);
     }
-    uint8_t* kc = reinterpret_cast<uint8_t*>(kv_cache) + ((size_t) b * 2 * H + h) * S_max * kD * elt + (size_t) s * kD * elt;
-    uint8_t* vc = kc + (size_t) H * S_max * kD * elt;
+    uint8_t *kc, *vc;
+    if (block_ptrs) {   // paged cache (K/kvCacheUtils.h:34-112): block s >> log2(tpb), row h * tpb + (s & (tpb - 1))
+      const size_t row = ((size_t) (h << tpb_log2) + (s & ((1 << tpb_log2) - 1))) * kD * elt;
+      kc = reinterpret_cast<uint8_t*>(block_ptrs[(size_t) b * 2 * max_blocks + (s >> tpb_log2)]) + row;
+      vc = reinterpret_cast<uint8_t*>(block_ptrs[(size_t) b * 2 * max_blocks + max_blocks + (s >> tpb_log2)]) + row;
+    } else {
+      kc = reinterpret_cast<uint8_t*>(kv_cache) + ((size_t) b * 2 * H + h) * S_max * kD * elt + (size_t) s * kD * elt;
+      vc = kc + (size_t) H * S_max * kD * elt;
+    }
     if (int8_kv) {
       auto q8 = [&](const uint4& x) {
         const __half* hx = reinterpret_cast<const __half*>(&x);
@@ -298,17 +306,43 @@ extern "C" size_t tb_context_attention_workspace_bytes(int batch, int seq_len, i
   return flash_ctx_tc_workspace_bytes(batch, seq_len, num_heads);
 }
 
+static int context_attention_impl(void* out, void* qkv, void* kv_cache, const long long* block_ptrs, int tokens_per_block,
+                                  int max_blocks, const int* input_lengths, const float* kv_scale_orig_quant,
+                                  void* workspace, int batch, int seq_len, int num_heads, int head_size, int max_seq_len,
+                                  int rotary_dim, float q_scaling, int int8_kv, cudaStream_t stream);
+
 extern "C" int tb_context_attention(void* out, void* qkv, void* kv_cache, const int* input_lengths,
                                     const float* kv_scale_orig_quant, void* workspace, int batch, int seq_len,
                                     int num_heads, int head_size, int max_seq_len, int rotary_dim, float q_scaling,
                                     int int8_kv, cudaStream_t stream) {
+  return context_attention_impl(out, qkv, kv_cache, nullptr, 0, 0, input_lengths, kv_scale_orig_quant, workspace, batch, seq_len,
+                                num_heads, head_size, max_seq_len, rotary_dim, q_scaling, int8_kv, stream);
+}
+
+extern "C" int tb_context_attention_paged(void* out, void* qkv, const int64_t* block_pointers, int tokens_per_block,
+                                          int max_blocks_per_seq, const int* input_lengths, const float* kv_scale_orig_quant,
+                                          void* workspace, int batch, int seq_len, int num_heads, int head_size,
+                                          int rotary_dim, float q_scaling, int int8_kv, cudaStream_t stream) {
+  if (!block_pointers || tokens_per_block < 16 || (tokens_per_block & (tokens_per_block - 1)) || max_blocks_per_seq < 1) return -1;
+  return context_attention_impl(out, qkv, nullptr, reinterpret_cast<const long long*>(block_pointers), tokens_per_block,
+                                max_blocks_per_seq, input_lengths, kv_scale_orig_quant, workspace, batch, seq_len, num_heads,
+                                head_size, tokens_per_block * max_blocks_per_seq, rotary_dim, q_scaling, int8_kv, stream);
+}
+
+static int context_attention_impl(void* out, void* qkv, void* kv_cache, const long long* block_ptrs, int tokens_per_block,
+                                  int max_blocks, const int* input_lengths, const float* kv_scale_orig_quant,
+                                  void* workspace, int batch, int seq_len, int num_heads, int head_size, int max_seq_len,
+                                  int rotary_dim, float q_scaling, int int8_kv, cudaStream_t stream) {
   if (head_size != kD) return -1;
   if (rotary_dim != 0 && rotary_dim != kD) return -1;
   if (seq_len > max_seq_len || batch <= 0 || seq_len <= 0) return -2;
   if (int8_kv && !kv_scale_orig_quant) return -1;
+  int tpb_log2 = 0;
+  while (block_ptrs && (1 << tpb_log2) < tokens_per_block) ++tpb_log2;
   ctx_prep_kernel<<<dim3(batch * seq_len), kPrepThreads, 0, stream>>>((__half*) qkv, kv_cache, input_lengths,
                                                                       kv_scale_orig_quant, seq_len, num_heads,
-                                                                      max_seq_len, rotary_dim, int8_kv);
+                                                                      max_seq_len, rotary_dim, int8_kv, block_ptrs, tpb_log2,
+                                                                      max_blocks);
   const float qk_scale_tc = 1.f / (sqrtf((float) head_size) * q_scaling);
   if (workspace)   // tcgen05 path (context_attn_tc.cu); without a workspace the warp-MMA kernel below runs
     return launch_flash_ctx_tc(out, qkv, workspace, input_lengths, batch, seq_len, num_heads, qk_scale_tc, stream);

@@ -35,6 +35,10 @@ struct MmhaParams {
   const int* input_lengths;  // [B] real prompt lengths (device); nullptr -> no padding
   const int* masked_tokens;  // [B, S_max] optional
   const int* max_in_dev;     // optional device int: overrides max_input_len (one captured graph serves any prompt length)
+  // paged KV cache (K/kvCacheUtils.h:34-112 KVBlockArray): block_ptrs [B, 2, max_blocks] device pointers (beam width 1) to
+  // blocks laid out [H, tokens_per_block, Dh]; NULL: contiguous kv_cache [B, 2, H, S_max, Dh]
+  const long long* block_ptrs;
+  int tpb_log2, max_blocks;
   const float* kv_scale_orig_quant;
   const float* kv_scale_quant_orig;
   float* partial;            // [B*H*nsplit*(Dh+2)] fp32 workspace
@@ -97,7 +101,7 @@ __device__ __forceinline__ uint32_t mmha_pack_h2(float a, float b) { return mmha
 // column 0 of B.  P.V: A = V^T with lane g owning dims [16g, 16g + 16) (row g of MMA m = dim 16g + m, row g + 8 = dim
 // 16g + 8 + m), so a lane loads 16 contiguous bytes of 4 keys; key pairs are interleaved with PRMT before the
 // expansion; the fp16 probabilities sit in column 0 of B.
-template <bool INT8, bool MMA = false>
+template <bool INT8, bool MMA = false, bool PAGED = false>
 __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_decode_kernel(MmhaParams p) {
   static_assert(!MMA || INT8, "the tensor-core loops are for int8 caches");
   using TR = KvTraits<INT8>;
@@ -134,12 +138,29 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
   const size_t seq_stride = (size_t) 2 * H * p.S_max * kDh * ELT;
   uint8_t* kbase = reinterpret_cast<uint8_t*>(p.kv_cache) + (size_t) b * seq_stride + (size_t) h * p.S_max * kDh * ELT;
   uint8_t* vbase = kbase + (size_t) H * p.S_max * kDh * ELT;
+  // row of cached position t of this (sequence, head): contiguous cache, or KVBlockArray addressing — block t >> log2(tpb)
+  // of the sequence's K (V) table, row (h * tpb + (t & (tpb - 1))) of the block (kvCacheUtils.h:58-112 getKVLocalIdx)
+  const long long* ktab = PAGED ? p.block_ptrs + (size_t) b * 2 * p.max_blocks : nullptr;
+  auto krow = [&](int t) -> uint8_t* {
+    if constexpr (PAGED)
+      return reinterpret_cast<uint8_t*>(ktab[t >> p.tpb_log2]) +
+             ((size_t) (h << p.tpb_log2) + (t & ((1 << p.tpb_log2) - 1))) * kDh * ELT;
+    else
+      return kbase + (size_t) t * kDh * ELT;
+  };
+  auto vrow = [&](int t) -> uint8_t* {
+    if constexpr (PAGED)
+      return reinterpret_cast<uint8_t*>(ktab[p.max_blocks + (t >> p.tpb_log2)]) +
+             ((size_t) (h << p.tpb_log2) + (t & ((1 << p.tpb_log2) - 1))) * kDh * ELT;
+    else
+      return vbase + (size_t) t * kDh * ELT;
+  };
 
   // Long fp16 contexts: pull this CTA's K and V ranges into L2 up front.  The load loops keep 32 KB per CTA in flight,
   // short of what HBM needs at 2048-token contexts, and the V range is not touched until the Q.K^T pass and the softmax
   // are done (cfg3, fp16 KV: 1260 -> 1295 tokens/s).  The int8 variant is issue-bound on the dequantisation (3
   // instructions per element), not on memory: the same prefetch costs it 2 %, so it is compiled out there.
-  if constexpr (!INT8) {
+  if constexpr (!INT8 && !PAGED) {
     if (len >= 256) {
       const uint32_t range = (uint32_t) len * kDh * ELT, piece = 16384;
       const uint32_t npiece = (range + piece - 1) / piece;
@@ -192,11 +213,11 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
                       __half2float(vcur_s[d0 + 2]) * qs, __half2float(vcur_s[d0 + 3]) * qs);
       vq.y = pack4_i8(__half2float(vcur_s[d0 + 4]) * qs, __half2float(vcur_s[d0 + 5]) * qs,
                       __half2float(vcur_s[d0 + 6]) * qs, __half2float(vcur_s[d0 + 7]) * qs);
-      *reinterpret_cast<uint2*>(kbase + (size_t) tlen * kDh + d0) = kq;
-      *reinterpret_cast<uint2*>(vbase + (size_t) tlen * kDh + d0) = vq;
+      *reinterpret_cast<uint2*>(krow(tlen) + d0) = kq;
+      *reinterpret_cast<uint2*>(vrow(tlen) + d0) = vq;
     } else {
-      *reinterpret_cast<uint4*>(kbase + ((size_t) tlen * kDh + d0) * 2) = *reinterpret_cast<uint4*>(&kcur_s[d0]);
-      *reinterpret_cast<uint4*>(vbase + ((size_t) tlen * kDh + d0) * 2) = *reinterpret_cast<uint4*>(&vcur_s[d0]);
+      *reinterpret_cast<uint4*>(krow(tlen) + d0 * 2) = *reinterpret_cast<uint4*>(&kcur_s[d0]);
+      *reinterpret_cast<uint4*>(vrow(tlen) + d0 * 2) = *reinterpret_cast<uint4*>(&vcur_s[d0]);
     }
   }
 
@@ -229,8 +250,9 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
       for (int u = 0; u < 2; ++u) {
         const int k0 = (kb + u * (kMmhaThreads / 32)) * 16;
         const bool okl = k0 + g < len, okh = k0 + g + 8 < len;
-        const uint8_t* rl = kbase + (size_t) (l0 + k0 + g) * kDh + t * 16;
-        const uint8_t* rh = rl + 8 * kDh;
+        // keys g and g + 8 of the 16-key block (a block of the paged cache holds a multiple of 16 positions)
+        const uint8_t* rl = krow(l0 + k0 + g) + t * 16;
+        const uint8_t* rh = PAGED ? krow(l0 + k0 + g + 8) + t * 16 : rl + 8 * kDh;
 #pragma unroll
         for (int st = 0; st < 2; ++st) {
           lo[u][st] = okl ? ldg_nc_v4(rl + 64 * st) : make_uint4(0, 0, 0, 0);
@@ -277,7 +299,7 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
     for (int u = 0; u < UN; ++u) {
       const int ii = i + u * KPI;
       raw[u] = make_uint4(0, 0, 0, 0);
-      if (ii < len) raw[u] = ldg_nc_v4(kbase + ((size_t) (l0 + ii) * kDh + gl * DPL) * ELT);
+      if (ii < len) raw[u] = ldg_nc_v4(krow(l0 + ii) + (size_t) gl * DPL * ELT);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -352,7 +374,7 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
       for (int i = 0; i < 4; ++i) {
         const int ii = kb * 16 + 2 * t + (i & 1) + 8 * (i >> 1);
         const bool ok = kb < nblk && ii < len;
-        r[i] = ok ? ldg_nc_v4(vbase + (size_t) (l0 + ii) * kDh + g * 16) : make_uint4(0, 0, 0, 0);
+        r[i] = ok ? ldg_nc_v4(vrow(l0 + ii) + g * 16) : make_uint4(0, 0, 0, 0);
         pk[i] = ok ? s_s[ii] : 0.f;
       }
     };
@@ -407,7 +429,7 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
     for (int u = 0; u < UN; ++u) {
       const int ii = i + u * KPI;
       raw[u] = make_uint4(0, 0, 0, 0);
-      if (ii < len) raw[u] = ldg_nc_v4(vbase + ((size_t) (l0 + ii) * kDh + gl * DPL) * ELT);
+      if (ii < len) raw[u] = ldg_nc_v4(vrow(l0 + ii) + (size_t) gl * DPL * ELT);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -509,11 +531,53 @@ int tb_mmha_decode(void* out, const void* qkv, void* kv_cache, const int* seq_le
                             max_input_len, len_cap, rotary_dim, q_scaling, int8_kv, nsplit, stream);
 }
 
+static int mmha_launch(void* out, const void* qkv, void* kv_cache, const long long* block_ptrs, int tokens_per_block,
+                       int max_blocks, const int* seq_lens, const int* input_lengths, const int* masked_tokens,
+                       const int* max_input_len_dev, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
+                       void* workspace, int* counters, int batch, int num_heads, int head_size, int max_seq_len,
+                       int past_len, int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv,
+                       int nsplit, cudaStream_t stream);
+
 int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
                        const int* masked_tokens, const int* max_input_len_dev, const float* kv_scale_orig_quant,
                        const float* kv_scale_quant_orig, void* workspace, int* counters, int batch, int num_heads,
                        int head_size, int max_seq_len, int past_len, int max_input_len, int len_cap, int rotary_dim,
                        float q_scaling, int int8_kv, int nsplit, cudaStream_t stream) {
+  return mmha_launch(out, qkv, kv_cache, nullptr, 0, 0, seq_lens, input_lengths, masked_tokens, max_input_len_dev,
+                     kv_scale_orig_quant, kv_scale_quant_orig, workspace, counters, batch, num_heads, head_size, max_seq_len,
+                     past_len, max_input_len, len_cap, rotary_dim, q_scaling, int8_kv, nsplit, stream);
+}
+
+int tb_mmha_decode_paged(void* out, const void* qkv, const int64_t* block_pointers, int tokens_per_block,
+                         int max_blocks_per_seq, const int* seq_lens, const int* input_lengths, const int* masked_tokens,
+                         const int* max_input_len_dev, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
+                         int batch, int num_heads, int head_size, int past_len, int max_input_len, int len_cap,
+                         int rotary_dim, float q_scaling, int int8_kv, int nsplit, cudaStream_t stream) {
+  if (!block_pointers || tokens_per_block < 16 || (tokens_per_block & (tokens_per_block - 1)) || max_blocks_per_seq < 1) return -1;
+  const int max_seq_len = tokens_per_block * max_blocks_per_seq;
+  return mmha_launch(out, qkv, nullptr, reinterpret_cast<const long long*>(block_pointers), tokens_per_block,
+                     max_blocks_per_seq, seq_lens, input_lengths, masked_tokens, max_input_len_dev, kv_scale_orig_quant,
+                     kv_scale_quant_orig, nullptr, nullptr, batch, num_heads, head_size, max_seq_len, past_len,
+                     max_input_len, len_cap, rotary_dim, q_scaling, int8_kv, nsplit, stream);
+}
+}   // extern "C"
+
+template <bool INT8, bool MMA>
+static int mmha_launch_t(const cudaLaunchConfig_t& cfg, const MmhaParams& p, size_t smem, bool paged) {
+  if (paged) {
+    if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<INT8, MMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<INT8, MMA, true>, p);
+  }
+  if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<INT8, MMA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<INT8, MMA, false>, p);
+}
+
+static int mmha_launch(void* out, const void* qkv, void* kv_cache, const long long* block_ptrs, int tokens_per_block,
+                       int max_blocks, const int* seq_lens, const int* input_lengths, const int* masked_tokens,
+                       const int* max_input_len_dev, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
+                       void* workspace, int* counters, int batch, int num_heads, int head_size, int max_seq_len,
+                       int past_len, int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv,
+                       int nsplit, cudaStream_t stream) {
   if (head_size != kDh) return -1;                 // LLaMA-7B head size; other sizes are not built
   if (rotary_dim != 0 && rotary_dim != kDh) return -1;
   if (past_len + 1 > max_seq_len || len_cap + 1 > max_seq_len + 1) return -2;
@@ -529,6 +593,10 @@ int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* se
   p.partial = reinterpret_cast<float*>(workspace);
   p.past_len = past_len; p.max_input_len = max_input_len; p.S_max = max_seq_len; p.H = num_heads;
   p.rotary_dim = rotary_dim; p.inv_sqrt_dh = 1.f / (sqrtf((float) head_size) * q_scaling);
+  p.block_ptrs = block_ptrs; p.max_blocks = max_blocks;
+  p.tpb_log2 = 0;
+  while (block_ptrs && (1 << p.tpb_log2) < tokens_per_block) ++p.tpb_log2;
+  const bool paged = block_ptrs != nullptr;
   // int8 caches with long contexts: tensor-core loops, two CTAs per SM, so no more splits than fit one wave
   const int mma_env = g_mma_mode;   // A/B switch (TB_MMHA_MMA / tb_mmha_set_mode): 0 off, 1 always, -1 automatic
   const bool use_mma = int8_kv && (mma_env == 1 || (mma_env != 0 && len_cap >= 512));
@@ -554,15 +622,7 @@ int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* se
   attr[0].val.clusterDim.z = nsplit;
   cfg.attrs = attr;
   cfg.numAttrs = nsplit > 1 ? 1 : 0;
-  if (use_mma) {
-    if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<true, true>, p);
-  }
-  if (int8_kv) {
-    if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<true>, p);
-  }
-  if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<false>, p);
-}
+  if (use_mma) return mmha_launch_t<true, true>(cfg, p, smem, paged);
+  if (int8_kv) return mmha_launch_t<true, false>(cfg, p, smem, paged);
+  return mmha_launch_t<false, false>(cfg, p, smem, paged);
 }

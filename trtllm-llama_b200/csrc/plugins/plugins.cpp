@@ -28,6 +28,8 @@ bool linear(const PluginTensorDesc& d, DataType t) { return d.type == t && d.for
 // inputs  0 qkv [B,S,3*H*Dh]  1 past_key_value [B,2,H,S_max,Dh]  2 sequence_length [B]  3 past_key_value_length [2] (HOST:
 //         {past_len, is_context})  4 masked_tokens [B,S_max]  5 input_lengths [B]  6 max_input_length [max_in] (shape only)
 //         7 cache_indirection [B,beam,S_max]  (8 kv_orig_quant_scale [1], 9 kv_quant_orig_scale [1] iff int8 KV)
+//         (next: block_pointers [B,beam,2,2*max_blocks] int32 view of int64 addresses iff paged_kv_cache — then input 1 is
+//          the block pool [blocks,2,H,tokens_per_block,Dh]; P/gptAttentionPlugin/gptAttentionPlugin.cpp:204-235)
 // outputs 0 context [B,S,H*Dh]   1 present_key_value (same buffer as input 1: updated in place)
 // =====================================================================================================
 class GPTAttentionPlugin : public BasePlugin {
@@ -102,6 +104,7 @@ class GPTAttentionPlugin : public BasePlugin {
   bool supportsFormatCombination(int32_t pos, const PluginTensorDesc* io, int32_t nb_in, int32_t) noexcept override {
     if (pos >= 2 && pos <= 7) return linear(io[pos], DataType::kINT32);
     if (int8_kv_ && (pos == 8 || pos == 9)) return linear(io[pos], DataType::kFLOAT);
+    if (paged_kv_ && pos == (int8_kv_ ? 10 : 8)) return linear(io[pos], DataType::kINT32);
     if (int8_kv_ && (pos == 1 || pos == nb_in + 1)) return linear(io[pos], DataType::kINT8);
     return linear(io[pos], (DataType) type_);
   }
@@ -116,8 +119,18 @@ class GPTAttentionPlugin : public BasePlugin {
                   void* workspace, cudaStream_t stream) noexcept override {
     return guarded("GPTAttention::enqueue", [&]() -> int {
       const int B = id[0].dims.d[0], S = id[0].dims.d[1];
-      const int S_max = id[1].dims.d[3];
       const int max_in = id[6].dims.d[0];
+      // paged cache: input 1 is the pool [blocks,2,H,tokens_per_block,Dh]; the per-sequence block tables come as an
+      // int32 view of int64 device addresses [B, beam = 1, 2, 2 * max_blocks] (T/tensorrt_llm/runtime/kv_cache_manager.py:286)
+      const int bp_idx = int8_kv_ ? 10 : 8;
+      const int tpb = paged_kv_ ? id[1].dims.d[3] : 0;
+      const int max_blocks = paged_kv_ ? id[bp_idx].dims.d[id[bp_idx].dims.nbDims - 1] / 2 : 0;
+      const int64_t* block_ptrs = paged_kv_ ? static_cast<const int64_t*>(in[bp_idx]) : nullptr;
+      if (paged_kv_) {
+        TBP_REQUIRE(block_ptrs != nullptr && max_blocks > 0, "paged_kv_cache needs the block_pointers input");
+        TBP_REQUIRE(id[bp_idx].dims.nbDims < 2 || id[bp_idx].dims.d[1] == 1, "beam width 1 only");
+      }
+      const int S_max = paged_kv_ ? tpb * max_blocks : id[1].dims.d[3];
       const int* host_len = static_cast<const int*>(in[3]);          // HOST tensor {past_len, is_context}
       TBP_REQUIRE(host_len != nullptr, "past_key_value_length must be a host tensor");
       const int past_len = host_len[0];
@@ -126,6 +139,10 @@ class GPTAttentionPlugin : public BasePlugin {
       const float* s_qo = int8_kv_ ? static_cast<const float*>(in[9]) : nullptr;
       void* cache = out[1] ? out[1] : const_cast<void*>(in[1]);      // in-place: runtime binds one buffer to both
       if (is_context) {
+        if (paged_kv_)
+          return tb_context_attention_paged(out[0], const_cast<void*>(in[0]), block_ptrs, tpb, max_blocks,
+                                            static_cast<const int*>(in[5]), s_oq, workspace, B, S, num_heads_, head_size_,
+                                            rotary_dim_, q_scaling_, int8_kv_, stream);
         return tb_context_attention(out[0], const_cast<void*>(in[0]), cache, static_cast<const int*>(in[5]), s_oq, workspace,
                                     B, S, num_heads_, head_size_, S_max, rotary_dim_, q_scaling_, int8_kv_, stream);
       }
@@ -138,6 +155,11 @@ class GPTAttentionPlugin : public BasePlugin {
       // its shape), so no per-request value is baked into a captured launch.  Split partials live in distributed
       // shared memory: the kernel needs no counters.
       const int* max_in_dev = device_lengths_ ? static_cast<const int*>(in[6]) : nullptr;
+      if (paged_kv_)
+        return tb_mmha_decode_paged(out[0], in[0], block_ptrs, tpb, max_blocks, static_cast<const int*>(in[2]),
+                                    static_cast<const int*>(in[5]), static_cast<const int*>(in[4]), max_in_dev, s_oq, s_qo, B,
+                                    num_heads_, head_size_, device_lengths_ ? 0 : past_len, max_in, cap, rotary_dim_,
+                                    q_scaling_, int8_kv_, nsplit, stream);
       return tb_mmha_decode_dev(out[0], in[0], cache, static_cast<const int*>(in[2]), static_cast<const int*>(in[5]),
                                 static_cast<const int*>(in[4]), max_in_dev, s_oq, s_qo, workspace, nullptr, B, num_heads_,
                                 head_size_, S_max, device_lengths_ ? 0 : past_len, max_in, cap, rotary_dim_, q_scaling_,
@@ -152,8 +174,8 @@ class GPTAttentionPlugin : public BasePlugin {
     TBP_REQUIRE(rotary_dim_ == 0 || rotary_dim_ == head_size_, "rotary_embedding_dim must be 0 or head_size");
     TBP_REQUIRE(rotary_dim_ == 0 || neox_, "only neox-style rotary embedding is built");
     TBP_REQUIRE(is_half(type_), "only type_id = half is built");
-    TBP_REQUIRE(!multi_query_ && !fp8_kv_ && !paged_kv_ && !ifb_ && !remove_padding_,
-                "multi-query / fp8 KV / paged KV / in-flight batching / packed input are out of scope (SURVEY 8f)");
+    TBP_REQUIRE(!multi_query_ && !fp8_kv_ && !ifb_ && !remove_padding_,
+                "multi-query / fp8 KV / in-flight batching / packed input are out of scope (SURVEY 8f)");
     TBP_REQUIRE(unidirectional_ == 1, "causal attention only");
   }
   int32_t num_heads_ = 0, head_size_ = 0, unidirectional_ = 1, rotary_dim_ = 0, context_fmha_ = 0, mask_type_ = 1;

@@ -103,6 +103,10 @@ struct tbrt_engine {
 
   // plugins (one instance per distinct configuration, shared by all layers)
   PluginPtr lin, lin_res, lin_swiglu, lm, attn, normq, qpt, allreduce, allgather;
+  // paged KV cache: per-layer pools live in kv[]; one device table [layers][max_batch][2][max_blocks] of block addresses
+  int tpb = 0, max_blocks = 0, pool_blocks = 0;
+  long long* d_block_tables = nullptr;
+  std::vector<long long> h_block_tables;
   // decode-shape (M <= 4) variants with the norm / quantiser fused into the projection's prologue ([ext] fields)
   PluginPtr lin_n, lin_n_swiglu, lin_q_res, lm_n, normq_res;
 
@@ -294,7 +298,7 @@ int tbrt_engine::build_plugins() {
     fl.add<int32_t>("fp8_kv_cache", PluginFieldType::kINT32, 0);
     fl.add<int8_t>("remove_input_padding", PluginFieldType::kINT8, 0);
     fl.add<int32_t>("mask_type", PluginFieldType::kINT32, 1);
-    fl.add<int32_t>("paged_kv_cache", PluginFieldType::kINT32, 0);
+    fl.add<int32_t>("paged_kv_cache", PluginFieldType::kINT32, c.paged_kv_tokens_per_block > 0 ? 1 : 0);
     fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
     fl.add<int32_t>("in_flight_batching", PluginFieldType::kINT32, 0);
     fl.add<int32_t>("device_lengths", PluginFieldType::kINT32, 1);
@@ -406,8 +410,8 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     else RT_CALL(linear(lin.get(), l.qkv, lin_in, xs, qkv, nullptr, M, DataType::kHALF, s));
     {
       const DataType kvt = c.int8_kv ? DataType::kINT8 : DataType::kHALF;
-      PluginTensorDesc id[10] = {desc({Bq, context ? S : 1, 3 * hid_l}, DataType::kHALF),
-                                 desc({Bq, 2, Hl, S_max, c.head_size}, kvt),
+      PluginTensorDesc id[11] = {desc({Bq, context ? S : 1, 3 * hid_l}, DataType::kHALF),
+                                 tpb ? desc({pool_blocks, 2, Hl, tpb, c.head_size}, kvt) : desc({Bq, 2, Hl, S_max, c.head_size}, kvt),
                                  desc({Bq}, DataType::kINT32), desc({2}, DataType::kINT32),
                                  desc({Bq, S_max}, DataType::kINT32), desc({Bq}, DataType::kINT32),
                                  desc({S_in}, DataType::kINT32), desc({Bq, 1, S_max}, DataType::kINT32),
@@ -415,8 +419,13 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       PluginTensorDesc od[2] = {desc({Bq, context ? S : 1, hid_l}, DataType::kHALF), id[1]};
       // masked_tokens = NULL: derived from input_lengths / max_input_length on the device ([ext])
       // input 6: max_input_length as one device int (device_lengths [ext]) — a replayed step graph must not bake S_in
-      const void* in[10] = {qkv, kv[li], d_seq_lens, host_len, nullptr, d_in_lens, context ? nullptr : d_max_in, nullptr,
-                            l.kv_oq, l.kv_qo};
+      const void* in[11] = {qkv, kv[li], d_seq_lens, host_len, nullptr, d_in_lens, context ? nullptr : d_max_in, nullptr,
+                            l.kv_oq, l.kv_qo, nullptr};
+      if (tpb) {   // block_pointers [B, 1, 2, 2 * max_blocks] (int32 view of int64) right after the optional KV scales
+        const int bp = c.int8_kv ? 10 : 8;
+        id[bp] = desc({Bq, 1, 2, 2 * max_blocks}, DataType::kINT32);
+        in[bp] = d_block_tables + (size_t) li * c.max_batch * 2 * max_blocks;
+      }
       void* out[2] = {att, kv[li]};
       launches += context ? 2 : 1;
       RT_CALL(attn->enqueue(id, od, in, out, workspace, s));
@@ -562,7 +571,7 @@ int tbrt_engine::step_body(cudaStream_t s) {
 // step state the plugin schedule uses (either path can run any step).  Not an error when the configuration is not taken.
 void tbrt_engine::build_decode_step() {
   static const bool off = getenv("TB_DECODE_STEP") && atoi(getenv("TB_DECODE_STEP")) == 0;
-  if (off || ds) return;
+  if (off || ds || tpb) return;     // the fused step reads a contiguous cache
   if (c.tp_size > 1 && !(ar && ar_open && tb_ar_extra_bytes(ar) > 0)) return;   // needs the peers' scratch mapped
   tb_decode_step_config dc{};
   dc.kind = c.mode; dc.layers = c.layers; dc.hidden = c.hidden; dc.heads_local = Hl; dc.inter_local = inter_l;
@@ -627,7 +636,18 @@ int tbrt_finalize(tbrt_engine* e) {
   if (e->alloc(e->logits, (size_t) c.max_batch * c.vocab * 4)) return -1;
   if (c.tp_size > 1 && e->alloc(e->logits_h, (size_t) c.max_batch * e->vocab_l * 2 * (1 + c.tp_size))) return -1;
   e->kv.resize(c.layers);
-  const size_t kv_bytes = (size_t) c.max_batch * 2 * e->Hl * e->S_max * c.head_size * (c.int8_kv ? 1 : 2);
+  if (c.paged_kv_tokens_per_block > 0) {
+    const int t = c.paged_kv_tokens_per_block;
+    if (t < 16 || (t & (t - 1))) return fail("paged_kv_tokens_per_block must be a power of two >= 16");
+    e->tpb = t;
+    e->max_blocks = (e->S_max + t - 1) / t;
+    e->pool_blocks = c.max_batch * e->max_blocks;
+    e->h_block_tables.assign((size_t) c.layers * c.max_batch * 2 * e->max_blocks, 0);
+    if (e->alloc(e->d_block_tables, e->h_block_tables.size() * sizeof(long long))) return -1;
+    RT_CUDA(cudaMemset(e->d_block_tables, 0, e->h_block_tables.size() * sizeof(long long)));
+  }
+  const size_t kv_bytes = e->tpb ? (size_t) 2 * e->pool_blocks * e->Hl * e->tpb * c.head_size * (c.int8_kv ? 1 : 2)
+                                 : (size_t) c.max_batch * 2 * e->Hl * e->S_max * c.head_size * (c.int8_kv ? 1 : 2);
   for (int i = 0; i < c.layers; ++i) {
     if (e->alloc(e->kv[i], kv_bytes)) return -1;
     RT_CUDA(cudaMemset(e->kv[i], 0, kv_bytes));
@@ -678,6 +698,32 @@ const float* tbrt_logits(const tbrt_engine* e) {
 }
 const int32_t* tbrt_output_ids(const tbrt_engine* e) { return e->d_out_ids; }
 int tbrt_set_end_id(tbrt_engine* e, int end_id) { e->end_id = end_id; return 0; }
+int tbrt_kv_max_blocks_per_seq(const tbrt_engine* e) { return e->max_blocks; }
+int tbrt_set_kv_blocks(tbrt_engine* e, const int32_t* ids, int batch, int blocks_per_seq, tb_stream_t st) {
+  if (!e->tpb) return fail("the engine was not built with a paged KV cache");
+  if (!ids || batch < 1 || batch > e->c.max_batch || blocks_per_seq < 1 || blocks_per_seq > e->max_blocks)
+    return fail("tbrt_set_kv_blocks: bad table shape");
+  const size_t elt = e->c.int8_kv ? 1 : 2;
+  const size_t block_bytes = (size_t) e->Hl * e->tpb * e->c.head_size * elt;
+  const size_t per_layer = (size_t) e->c.max_batch * 2 * e->max_blocks;
+  for (int li = 0; li < e->c.layers; ++li) {
+    // pool layout [2][blocks][H][tokens_per_block][Dh]: K blocks, then V blocks (kv_cache_manager.py:84-93)
+    const long long base = reinterpret_cast<long long>(e->kv[li]);
+    long long* t = e->h_block_tables.data() + (size_t) li * per_layer;
+    for (int b = 0; b < batch; ++b)
+      for (int j = 0; j < e->max_blocks; ++j) {
+        const int id = j < blocks_per_seq ? ids[(size_t) b * blocks_per_seq + j] : -1;
+        if (id >= e->pool_blocks) return fail("tbrt_set_kv_blocks: block id outside the pool");
+        t[((size_t) b * 2 + 0) * e->max_blocks + j] = id < 0 ? 0 : base + (long long) ((size_t) id * block_bytes);
+        t[((size_t) b * 2 + 1) * e->max_blocks + j] = id < 0 ? 0 : base + (long long) (((size_t) e->pool_blocks + id) * block_bytes);
+      }
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
+  RT_CUDA(cudaMemcpyAsync(e->d_block_tables, e->h_block_tables.data(), e->h_block_tables.size() * sizeof(long long),
+                          cudaMemcpyHostToDevice, s));
+  RT_CUDA(cudaStreamSynchronize(s));      // the staging vector is reused by the next call
+  return 0;
+}
 int tbrt_set_sampling(tbrt_engine* e, int top_k, float top_p, float temperature, unsigned long long seed) {
   if (top_k < 0 || top_k > 1024 || top_p < 0.f || top_p > 1.f || !(temperature >= 0.f)) return fail("bad sampling parameters");
   const bool changed = e->top_k != top_k || e->top_p != top_p || e->temperature != temperature || e->seed != seed;

@@ -29,6 +29,7 @@ class ModelConfig:
     multi_query_mode: bool = False
     remove_input_padding: bool = False
     paged_kv_cache: bool = False
+    tokens_per_block: int = 64          # paged KV cache block size (LQ/build.py --tokens_per_block; a power of two >= 16)
     rms_eps: float = 1e-6
     quant_mode: QuantMode = QuantMode(0)
     max_batch_size: int = 8
@@ -161,7 +162,8 @@ class GenerationSession:
                        vocab=mc.vocab_size, head_size=mc.hidden_size // mc.num_heads, rms_eps=mc.rms_eps, mode=mc.mode,
                        int8_kv=int(mc.quant_mode.has_int8_kv_cache()), max_batch=mc.max_batch_size,
                        max_input_len=mc.max_input_len, max_output_len=mc.max_output_len, tp_size=mc.tp_size,
-                       tp_rank=mc.tp_rank, use_cuda_graph=int(use_cuda_graph))
+                       tp_rank=mc.tp_rank, use_cuda_graph=int(use_cuda_graph),
+                       paged_kv_tokens_per_block=int(mc.tokens_per_block) if mc.paged_kv_cache else 0)
         self._e = lib.tbrt_create(C.byref(c))
         if not self._e:
             raise _err("tbrt_create")
@@ -174,6 +176,11 @@ class GenerationSession:
         if lib.tbrt_finalize(self._e):
             raise _err("tbrt_finalize")
         self.batch_size = self.max_input_len = self.max_new_tokens = 0
+        self.kv_cache_manager = None
+        if mc.paged_kv_cache:
+            per_seq = lib.tbrt_kv_max_blocks_per_seq(self._e)
+            self.kv_cache_manager = KVCacheManager(blocks=mc.max_batch_size * per_seq, tokens_per_block=mc.tokens_per_block,
+                                                   max_blocks_per_seq=per_seq)
 
     def __del__(self):
         e, self._e = getattr(self, "_e", None), None
@@ -229,8 +236,20 @@ class GenerationSession:
         return torch.cuda.current_stream().cuda_stream
 
     # granular entry points (tests compare logits step by step)
+    def _upload_kv_blocks(self, batch):
+        table = self.kv_cache_manager.get_block_table(batch)
+        if lib.tbrt_set_kv_blocks(self._e, table.data_ptr(), table.shape[0], table.shape[1], self._stream()):
+            raise _err("tbrt_set_kv_blocks")
+
     def context(self, input_ids: torch.Tensor, input_lengths: torch.Tensor):
         B, S = input_ids.shape
+        if self.kv_cache_manager is not None:
+            # generation.py:609-640: every sequence of the padded batch gets blocks for max_input_length + 1 positions
+            m = self.kv_cache_manager
+            m.reset()
+            for b in range(B):
+                m.add_sequence(GenerationSequence(seq_idx=b, batch_idx=b), S)
+            self._upload_kv_blocks(B)
         ids = input_ids.to(device="cuda", dtype=torch.int32).contiguous()
         lens = input_lengths.to(device="cuda", dtype=torch.int32).contiguous()
         if lib.tbrt_context(self._e, ids.data_ptr(), lens.data_ptr(), B, S, self._stream()):
@@ -239,6 +258,10 @@ class GenerationSession:
         return self.logits()
 
     def step(self):
+        if self.kv_cache_manager is not None:
+            # generation.py:944-949: advance the manager; a sequence entering a new block gets one from the free list
+            if self.kv_cache_manager.step([False] * self._B):
+                self._upload_kv_blocks(self._B)
         if lib.tbrt_step(self._e, self._stream()):
             raise _err("tbrt_step")
         return self.logits()
@@ -287,11 +310,113 @@ class GenerationSession:
         # whether every sequence has produced end_id, stops early, and pads finished sequences with end_id
         end_id = sampling_config.end_id if (sampling_config is not None and sampling_config.end_id is not None) else -1
         lib.tbrt_set_end_id(self._e, int(end_id))
+        if self.kv_cache_manager is not None:
+            # paged KV cache: the block tables change while the request runs, so the step loop is driven from the host as
+            # in the reference (generation.py:852-997); the stop criterion is applied to the finished ids
+            self.context(input_ids, lens)
+            for _ in range(n - 1):
+                self.step()
+            ids = self.output_ids(n).cpu()
+            if end_id >= 0:
+                pad_finished(ids, end_id)
+            out.copy_(ids)
+            self.last_steps = n
+            return out
         if lib.tbrt_generate(self._e, input_ids.data_ptr(), lens.data_ptr(), B, S, n, out.data_ptr(), self._stream()):
             raise _err("tbrt_generate")
         self._B = B
         self.last_steps = lib.tbrt_last_steps(self._e)
         return out
+
+
+@dataclass(eq=False)
+class GenerationSequence:
+    """T/tensorrt_llm/runtime/kv_cache_manager.py:31-52"""
+    seq_idx: int
+    batch_idx: int
+
+    def get_batch_idx(self) -> int:
+        return self.batch_idx
+
+    def get_seq_idx(self) -> int:
+        return self.seq_idx
+
+    def __eq__(self, other):
+        return isinstance(other, GenerationSequence) and (self.seq_idx, self.batch_idx) == (other.seq_idx, other.batch_idx)
+
+    def __hash__(self):
+        return self.seq_idx
+
+
+class KVCacheManager:
+    """Block bookkeeping of the paged KV cache — T/tensorrt_llm/runtime/kv_cache_manager.py:57-292 (BlocksManager +
+    KVCacheManager) for beam width 1.  The pools live in the engine (one per layer, same block ids in every layer); this
+    class only decides WHICH pool block holds which 2^k positions of which sequence:
+
+      add_sequence(seq, context_len)   ceil((context_len + 1) / tokens_per_block) blocks (:262-277)
+      step(finished)                   one more block for every unfinished sequence whose length is about to cross a block
+                                       boundary, finished sequences return their blocks (:225-260); returns True when the
+                                       table changed
+      get_block_table(batch)           int32 [batch, max_blocks_per_seq], -1 = not allocated  (the engine turns ids into the
+                                       [B, 1, 2, max_blocks] pointer array of get_pointer_arrays, :279-292)
+
+    The free list is dealt in a seeded shuffled order so that a sequence's blocks are scattered over the pool and
+    interleaved with other sequences' — the layout a long-running server converges to, and what the tests need to show
+    that the kernels really follow the table."""
+
+    def __init__(self, blocks: int, tokens_per_block: int, max_blocks_per_seq: int, seed: int = 0):
+        if tokens_per_block < 16 or tokens_per_block & (tokens_per_block - 1):
+            raise ValueError("tokens_per_block must be a power of two >= 16")
+        self.blocks, self.tokens_per_block, self.max_blocks_per_seq, self.seed = blocks, tokens_per_block, max_blocks_per_seq, seed
+        self.reset()
+
+    def reset(self):
+        g = torch.Generator().manual_seed(self.seed)
+        self.free_blocks = torch.randperm(self.blocks, generator=g).tolist()
+        self.allocated = {}          # GenerationSequence -> [block ids]
+        self.sequences, self.lens = [], []
+
+    def has_free_block(self) -> bool:
+        return len(self.free_blocks) > 0
+
+    def _allocate(self, seq):
+        if not self.has_free_block():
+            raise RuntimeError("Can't allocate new block for KV cache")
+        if len(self.allocated[seq]) >= self.max_blocks_per_seq:
+            raise RuntimeError("sequence exceeds max_blocks_per_seq")
+        self.allocated[seq].append(self.free_blocks.pop(0))
+
+    def add_sequence(self, sequence: GenerationSequence, context_len: int):
+        self.sequences.append(sequence)
+        self.lens.append(context_len)
+        self.allocated[sequence] = []
+        for _ in range(-(-(context_len + 1) // self.tokens_per_block)):     # one more token for the 1st generation step
+            self._allocate(sequence)
+
+    def step(self, finished) -> bool:
+        changed = False
+        for seq in self.sequences:
+            b = seq.get_batch_idx()
+            if not finished[b] and self.lens[b] % self.tokens_per_block == self.tokens_per_block - 1:
+                self._allocate(seq)
+                changed = True
+            self.lens[b] += 1
+        for b, f in enumerate(finished):
+            if f:
+                self.free_blocks.extend(self.allocated.pop(self.sequences[b]))
+                changed = True
+        keep = [(s, l) for s, l, f in zip(self.sequences, self.lens, finished) if not f]
+        self.sequences, self.lens = [s for s, _ in keep], [l for _, l in keep]
+        for i, s in enumerate(self.sequences):
+            s.batch_idx = i
+        return changed
+
+    def get_block_table(self, batch: int) -> torch.Tensor:
+        t = torch.full((batch, self.max_blocks_per_seq), -1, dtype=torch.int32)
+        for seq, ids in self.allocated.items():
+            if seq.get_batch_idx() < batch:
+                t[seq.get_batch_idx(), :len(ids)] = torch.tensor(ids, dtype=torch.int32)
+        return t
 
 
 def pad_finished(output_ids: torch.Tensor, end_id: int) -> torch.Tensor:
