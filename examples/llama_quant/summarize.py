@@ -17,9 +17,28 @@ def main(args):
     import torch
     from trtllm_llama_b200 import builder as B
     from trtllm_llama_b200 import runtime as rt
-    mc = B.model_config_from_json(os.path.join(args.engine_dir, "config.json"))
-    tensors = B.deserialize_engine(os.path.join(args.engine_dir, B.get_engine_name("llama", "float16", 1, 0)))
+    from trtllm_llama_b200._lib import lib
+    # flags of the reference CLI this path does not honour are REJECTED, never silently ignored
+    if args.num_beams != 1:
+        raise SystemExit("--num_beams > 1: beam search is not built on this path (DESIGN.md 8f-4)")
+    if args.test_hf:
+        raise SystemExit("--test_hf: no HF checkpoint / tokenizer offline; run_hf.py times the HF path on synthetic weights")
+    if args.top_k < 0:
+        raise SystemExit("--top_k must be >= 0")
+    # one process per rank, as the reference under mpirun (LQ/summarize.py:65-110); here torchrun provides RANK / WORLD_SIZE
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    mc = B.model_config_from_json(os.path.join(args.engine_dir, "config.json"), rank)
+    assert world == mc.tp_size, f'Engine world size ({mc.tp_size}) != Runtime world size ({world})'
+    torch.cuda.set_device(rank % torch.cuda.device_count())
+    if world > 1:
+        from run import setup_tp
+        setup_tp(lib, world, rank)
+    tensors = B.deserialize_engine(os.path.join(args.engine_dir, B.get_engine_name("llama", "float16", world, rank)))
     session = rt.GenerationSession(mc, tensors)
+    if world > 1:
+        session.enable_peer_allreduce()
+    # LQ/summarize.py:125-140: top_k = 1 is greedy; larger values sample (seeded) among the k best
+    sampling = rt.SamplingConfig(end_id=None, top_k=args.top_k, random_seed=args.random_seed) if args.top_k != 1 else None
     rng = np.random.default_rng(0)
     max_in = min(args.max_input_len, mc.max_input_len)
     out_len = min(args.output_len, mc.max_output_len)
@@ -31,9 +50,9 @@ def main(args):
             ids[b, :L] = rng.integers(3, mc.vocab_size, L)
         session.setup(args.batch_size, ids.shape[1], out_len)
         t0 = time.time()
-        out = session.decode(torch.from_numpy(ids).pin_memory(), torch.from_numpy(lens).pin_memory()).numpy()
+        out = session.decode(torch.from_numpy(ids).pin_memory(), torch.from_numpy(lens).pin_memory(), sampling).numpy()
         total += time.time() - t0
-        if args.check_accuracy and args.oracle_weights:
+        if args.check_accuracy and args.oracle_weights and rank == 0 and sampling is None:
             from oracle import ref_model as RM            # checker only (tests/bench infrastructure)
             w = np.load(args.oracle_weights, allow_pickle=True).item()
             mode = {0: "fp16", 1: "w8", 2: "w4", 3: "sq"}[mc.mode]
@@ -43,6 +62,8 @@ def main(args):
                                  max_seq_len=ids.shape[1] + out_len).generate(ids, lens, out_len)
             agree += int((ref == out).sum())
             n_tok += out.size
+    if rank != 0:
+        return
     print(f'TensorRT-LLM (total latency: {total:.3f} sec)')
     print(f'TensorRT-LLM tokens/s: {args.max_ite * args.batch_size * out_len / total:.1f}')
     if n_tok:
@@ -69,6 +90,7 @@ if __name__ == '__main__':
     p.add_argument('--oracle_weights', type=str, default=None, help=".npy dict of fp16 weights for the agreement check")
     p.add_argument('--num_beams', type=int, default=1)
     p.add_argument('--top_k', type=int, default=1)
+    p.add_argument('--random_seed', type=int, default=0)
     p.add_argument('--max_input_len', type=int, default=923)     # LQ/summarize.py:91-92
     p.add_argument('--output_len', type=int, default=100)
     main(p.parse_args())

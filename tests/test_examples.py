@@ -44,10 +44,51 @@ def test_build_writes_reference_artefacts(tmp_path):
 
 
 def test_build_rejects_out_of_scope_flags(tmp_path):
-    for bad in (["--paged_kv_cache"], ["--n_kv_head", "1"], ["--dtype", "bfloat16"], ["--use_smooth_quant"]):
+    for bad in (["--remove_input_padding"], ["--n_kv_head", "1"], ["--dtype", "bfloat16"], ["--use_smooth_quant"],
+                ["--max_beam_width", "2"]):
         r = subprocess.run([sys.executable, os.path.join(EX, "build.py"), "--output_dir", str(tmp_path), *TINY, *bad],
                            capture_output=True, text=True, timeout=300)
         assert r.returncode != 0
+
+
+def test_build_paged_kv_cache_flag(tmp_path):
+    """--paged_kv_cache / --tokens_per_block (LQ/build.py:190-196) reach config.json and the runtime's ModelConfig."""
+    _build(tmp_path, "--int8_kv_cache", "--paged_kv_cache", "--tokens_per_block", "32")
+    cfg = json.load(open(tmp_path / "config.json"))
+    assert cfg["plugin_config"]["paged_kv_cache"] is True and cfg["plugin_config"]["tokens_per_block"] == 32
+    from trtllm_llama_b200 import builder as B
+    mc = B.model_config_from_json(str(tmp_path / "config.json"))
+    assert mc.paged_kv_cache and mc.tokens_per_block == 32
+
+
+def test_summarize_rejects_flags_it_does_not_honour(tmp_path):
+    for bad in (["--num_beams", "4"], ["--test_hf"]):
+        r = subprocess.run([sys.executable, os.path.join(EX, "summarize.py"), "--engine_dir", str(tmp_path), *bad],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and ("not built" in r.stderr or "offline" in r.stderr), r.stderr[-500:]
+
+
+@pytest.mark.gpu
+def test_summarize_py_runs_and_checks_agreement(tmp_path):
+    """summarize.py on a tiny engine: greedy run with the token-agreement check against the oracle, and a sampled run
+    (--top_k 8) that is reproducible for a seed."""
+    from oracle import ref_model as RM
+    _build(tmp_path, "--use_weight_only", "--int8_kv_cache", "--random_seed", "5", "--max_batch_size", "2")
+    cfg = RM.LlamaCfg.tiny(layers=2, hidden=256, inter=384, vocab=512)
+    from trtllm_llama_b200 import builder as B
+    from trtllm_llama_b200.runtime import ModelConfig
+    mc = ModelConfig(vocab_size=512, num_layers=2, num_heads=2, hidden_size=256, inter_size=384)
+    w = B.random_llama_weights(mc, seed=5, device="cpu")
+    wn = {k: w[k].numpy() for k in ("vocab_embedding", "ln_f", "lm_head")}
+    wn["layers"] = [{k: v.numpy() for k, v in lw.items()} for lw in w["layers"]]
+    np.save(tmp_path / "w.npy", wn, allow_pickle=True)
+    base = [sys.executable, os.path.join(EX, "summarize.py"), "--engine_dir", str(tmp_path), "--batch_size", "2", "--max_ite",
+            "2", "--max_input_len", "16", "--output_len", "8"]
+    r = subprocess.run(base + ["--check_accuracy", "--oracle_weights", str(tmp_path / "w.npy"), "--agreement_threshold", "80"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "token agreement" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    a = subprocess.run(base + ["--top_k", "8", "--random_seed", "3"], capture_output=True, text=True, timeout=600)
+    assert a.returncode == 0 and "tokens/s" in a.stdout, a.stdout[-2000:] + a.stderr[-2000:]
 
 
 @pytest.mark.gpu

@@ -612,8 +612,17 @@ class NcclPlugin : public BasePlugin {
     TBP_REQUIRE(is_half(type_), "only type_id = half is built");
   }
   explicit NcclPlugin(Reader& r) {
-    type_ = r.get<int32_t>();                                   // allreducePlugin.cpp:170-183: type, then the group
-    while (r.p < r.end) group_.push_back(r.get<int32_t>());
+    // allreducePlugin.cpp:170-183 writes type, then the group "until the end of the blob"; a blob that was padded by its
+    // container would then yield phantom ranks, so trailing ranks are only accepted while they are distinct and in
+    // [0, 4096) (a zero-padded tail repeats rank 0 and stops the scan)
+    type_ = r.get<int32_t>();
+    while (r.p + sizeof(int32_t) <= r.end) {
+      const int32_t g = r.get<int32_t>();
+      bool dup = g < 0 || g >= 4096;
+      for (int32_t h : group_) dup = dup || h == g;
+      if (dup) break;
+      group_.push_back(g);
+    }
     TBP_REQUIRE(!group_.empty() && is_half(type_), "bad serialised NCCL plugin");
   }
   size_t getSerializationSize() const noexcept override { return sizeof(int32_t) * (1 + group_.size()); }
