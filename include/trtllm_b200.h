@@ -65,6 +65,11 @@ int tb_gemv(int kind, void* y, float* y_f32, const void* x, const void* w, const
 int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
                   const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
                   int swiglu, int prologue, const void* gamma, float eps, tb_stream_t stream);
+/* Optional one-shot hint for the calling thread's NEXT tb_gemv / tb_gemv_fused launch: byte ranges (the head of the weight
+ * matrix the projection after it will stream; two ranges for a gate|up matrix) that its warps request into L2 as they run
+ * out of rows, so HBM keeps streaming through the grid's tail, the launch gap and a short attention kernel in between.
+ * No effect on results.  NULL / 0 clears the hint.                                                   */
+int tb_gemv_hint_next(const void* a, size_t a_bytes, const void* b, size_t b_bytes);
 
 /* ---- tcgen05 GEMM (any M) ---------------------------------------------------------------------
  * kind as tb_gemv.  out_type: 0 fp16, 1 fp32, 2 int32 (SmoothQuantGemm type_id half/float/int32).

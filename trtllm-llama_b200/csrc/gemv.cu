@@ -49,7 +49,18 @@ struct GemvParams {
   int prologue;            // GemvPrologue
   const __half* gamma;     // [K] RMSNorm weight (prologue 1, 2)
   float eps;
+  // optional: the first window(s) of the weights the NEXT projection of the step will stream (tb_gemv_hint_next); every
+  // warp requests its share into L2 when it runs out of rows, so HBM keeps streaming through this grid's tail, the launch
+  // gap and the next kernel's activation prologue.  Measured (B200, graph replay): 8-12 MB windows take the cfg2 step from
+  // 2.68 to 2.57 ms and the SmoothQuant step from 1.71 to 1.64 ms; 48 MB windows LOSE (2.74 / 1.82 ms: the requests queue in
+  // front of the stragglers' demand loads), and a warp requesting its OWN first rows right after griddepcontrol.wait loses
+  // too (2.75 / 1.74 ms: a demand load that meets an in-flight prefetch of the same line is slower than the load alone)
+  const uint8_t* pf[2];
+  unsigned pf_lines[2];    // 128-byte lines per region
 };
+
+struct GemvNextHint { const void* p[2]; size_t bytes[2]; };
+extern thread_local GemvNextHint g_gemv_next;
 
 constexpr int kGemvThreads = 256;
 constexpr int kGemvWarps = kGemvThreads / 32;
@@ -66,6 +77,7 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v))
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // dot of one 16-byte weight chunk with the matching activation chunk(s) for MB rows.
 // xs: staged activations, row stride `xstride` bytes; k0: first k element of this chunk.
@@ -423,6 +435,15 @@ __global__ void __launch_bounds__(kGemvThreads, (MB >= 4 ? 2 : 4)) gemv_kernel(c
       }
     }
   }
+  // out of rows: request this warp's share of the next projection's first weight window into L2 (lines dealt round-robin
+  // over all warps of the grid, so the chip requests one contiguous window front to back)
+  {
+    const unsigned total = p.pf_lines[0] + p.pf_lines[1];
+    for (unsigned l = (unsigned) gw * 32 + lane; l < total; l += (unsigned) tw * 32) {
+      const uint8_t* a = l < p.pf_lines[0] ? p.pf[0] + (size_t) l * 128 : p.pf[1] + (size_t) (l - p.pf_lines[0]) * 128;
+      prefetch_l2_line(a);
+    }
+  }
 }
 
 template <int KIND, int MB, bool SWIGLU>
@@ -466,7 +487,16 @@ static int launch_gemv_m(const GemvParams& p, cudaStream_t stream) {
 
 }  // namespace tb
 
+namespace tb { thread_local GemvNextHint g_gemv_next{}; }
+
 using namespace tb;
+
+// Hint (optional, one-shot, per calling thread): the next tb_gemv / tb_gemv_fused launch also requests these byte ranges —
+// the head of the weights the FOLLOWING projection will stream — into L2 as its warps finish.  NULL / 0 clears it.
+extern "C" int tb_gemv_hint_next(const void* a, size_t a_bytes, const void* b, size_t b_bytes) {
+  g_gemv_next = GemvNextHint{{a, b}, {a ? a_bytes : 0, b ? b_bytes : 0}};
+  return 0;
+}
 
 // rows the decode-shape path accepts for this weight kind and K: 8 on the tensor-core kernel, 4 on the FMA kernel
 extern "C" int tb_gemv_max_rows(int kind, int K) { return gemv_mma_eligible(kind, 8, K) ? 8 : 4; }
@@ -481,6 +511,11 @@ extern "C" int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, con
   p.y = (__half*) y; p.y_f32 = y_f32; p.M = M; p.N = N; p.K = K; p.swiglu = swiglu;
   p.n_out = swiglu ? N / 2 : N;
   p.prologue = prologue; p.gamma = (const __half*) gamma; p.eps = eps;
+  for (int i = 0; i < 2; ++i) {
+    p.pf[i] = static_cast<const uint8_t*>(g_gemv_next.p[i]);
+    p.pf_lines[i] = (unsigned) (g_gemv_next.bytes[i] / 128);
+  }
+  g_gemv_next = GemvNextHint{};
   const int epc = kind == kF16 ? 8 : (kind == kW4 ? 32 : 16);
   if (kind < 0 || kind > 3 || M < 1 || M > tb_gemv_max_rows(kind, K) || K % epc != 0 || (swiglu && (N & 1))) return -1;
   if ((kind == kW8 || kind == kW4) && !w_scale) return -1;

@@ -400,12 +400,31 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
   const void* lin_in = sq ? static_cast<const void*>(xq) : static_cast<const void*>(x);
   // decode shapes: RMSNorm (+ per-token quantisation) rides in the projection's prologue -> 5 kernels per layer
   const bool fused = M <= gemv_rows;
+  // decode shapes: every projection asks L2 for the head of the weights the NEXT projection streams (tb_gemv_hint_next);
+  // the whole dense matrix when the attention kernel runs in between.  TB_PF_MB / TB_PF_ATTN_MB = 0 switch it off.
+  static const size_t pf_mb = getenv("TB_PF_MB") ? (size_t) atoi(getenv("TB_PF_MB")) : 12;
+  static const size_t pf_attn_mb = getenv("TB_PF_ATTN_MB") ? (size_t) atoi(getenv("TB_PF_ATTN_MB")) : 12;
+  auto wbytes = [&](const LinearW& w) -> size_t {
+    return c.mode == TBRT_MODE_FP16 ? (size_t) w.N * w.K * 2 : (c.mode == TBRT_MODE_W4 ? (size_t) w.N * w.K / 2 : (size_t) w.N * w.K);
+  };
+  auto hint = [&](const LinearW* nx, bool swiglu_next, size_t cap_mb) {
+    if (!fused || !nx || !cap_mb) { tb_gemv_hint_next(nullptr, 0, nullptr, 0); return; }
+    size_t total = wbytes(*nx), cap = cap_mb << 20;
+    if (total > cap) total = cap;
+    if (swiglu_next) {   // gate rows [0, inter), up rows [inter, 2 inter): the kernel walks both fronts together
+      const size_t half = (total / 2) & ~(size_t) 127;
+      tb_gemv_hint_next(nx->w, half, static_cast<const uint8_t*>(nx->w) + wbytes(*nx) / 2, half);
+    } else {
+      tb_gemv_hint_next(nx->w, total & ~(size_t) 127, nullptr, 0);
+    }
+  };
 
   __half* cur = h;   // residual stream
   __half* nxt = h2;
   if (!fused) RT_CALL(norm(cur, L[0].ln_in, nullptr, nullptr));
   for (int li = 0; li < c.layers; ++li) {
     const LayerW& l = L[li];
+    hint(&l.dense, false, pf_attn_mb);
     if (fused) RT_CALL(linear(lin_n.get(), l.qkv, cur, xs, qkv, nullptr, M, DataType::kHALF, s, l.ln_in, true));
     else RT_CALL(linear(lin.get(), l.qkv, lin_in, xs, qkv, nullptr, M, DataType::kHALF, s));
     {
@@ -435,6 +454,7 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     const void* dense_in = att;
     if (sq && !(fused && !tp)) { RT_CALL(quant(att, hid_l)); dense_in = xq; }
     (void) row_lin_nores;
+    hint(&l.fc_gate, true, pf_mb);
     if (!tp && fused) {
       RT_CALL(linear(row_lin, l.dense, dense_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, sq));   // nxt = cur + dense(att)
     } else if (!tp) {
@@ -464,6 +484,7 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     }
     std::swap(cur, nxt);
     bool act_quantised = false;
+    hint(&l.proj, false, pf_mb);
     if (fused) {
       RT_CALL(linear(lin_n_swiglu.get(), l.fc_gate, cur, xs, act, nullptr, M, DataType::kHALF, s, l.ln_post, true));
     } else if (fuse_swiglu) {
@@ -483,6 +504,13 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     if (act_quantised) proj_in = xq;
     else if (sq && !(fused && !tp)) { RT_CALL(quant(act, inter_l)); proj_in = xq; }
     const void* next_gamma = li + 1 < c.layers ? L[li + 1].ln_in : nullptr;
+    if (li + 1 < c.layers) {
+      hint(&L[li + 1].qkv, false, pf_mb);
+    } else if (fused && pf_mb) {   // lm_head stays fp16 in every mode
+      size_t b = (size_t) vocab_l * c.hidden * 2;
+      if (b > (pf_mb << 20)) b = pf_mb << 20;
+      tb_gemv_hint_next(lm_head, b & ~(size_t) 127, nullptr, 0);
+    }
     if (!tp && fused) {
       RT_CALL(linear(row_lin, l.proj, proj_in, xs, nxt, cur, M, DataType::kHALF, s, nullptr, sq));
       std::swap(cur, nxt);
