@@ -530,9 +530,13 @@ extern "C" int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, con
   // conversion-bound on FMAs and wins on tensor cores (2.05 vs 2.26 ms).  5..8 rows: tensor-core kernel only.
   static const int mma_min_m_env = getenv("TB_GEMV_MMA_MIN_M") ? atoi(getenv("TB_GEMV_MMA_MIN_M")) : 0;   // A/B switch
   const int mma_min_m = mma_min_m_env > 0 ? mma_min_m_env : (kind == kW4 ? 1 : 5);
-  if (M >= mma_min_m && gemv_mma_eligible(kind, M, K))
+  if (M >= mma_min_m && gemv_mma_eligible(kind, M, K)) {
+    // the next-weights window measured slower on this kernel's workloads (cfg3 int8-KV 3.32 -> 3.40 ms, int4 2.10 -> 2.26 ms)
+    static const bool mma_pf = getenv("TB_MMA_PF") && atoi(getenv("TB_MMA_PF")) != 0;
+    if (!mma_pf) p.pf_lines[0] = p.pf_lines[1] = 0;
     return gemv_mma_launch(kind, y, y_f32, x, w, w_scale, sc, sr, sc_per_channel, sr_per_token, residual, M, N, K, swiglu,
-                           prologue, gamma, eps, stream);
+                           prologue, gamma, eps, reinterpret_cast<const void* const*>(p.pf), p.pf_lines, stream);
+  }
   switch (kind) {
     case kF16:  return swiglu ? launch_gemv_m<kF16, true>(p, stream)  : launch_gemv_m<kF16, false>(p, stream);
     case kW8:   return swiglu ? launch_gemv_m<kW8, true>(p, stream)   : launch_gemv_m<kW8, false>(p, stream);

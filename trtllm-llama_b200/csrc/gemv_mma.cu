@@ -39,6 +39,8 @@ struct GemvMmaParams {
   const __half* gamma;
   float eps;
   int S;   // cluster size (K split across CTAs)
+  const uint8_t* pf[2];    // tb_gemv_hint_next: head of the next projection's weights, requested into L2 at the end (gemv.cu;
+  unsigned pf_lines[2];    // off by default on this kernel: measured slower on its workloads)
 };
 
 constexpr int kMmaThreads = 256;
@@ -135,87 +137,11 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
     // one warp per token row (M <= 8 rows, 8 warps): every row's statistics are warp-local reductions, so the rows
     // proceed in parallel and the whole prologue costs two L2 round trips instead of 2 x M block-wide ones
     const __half* xin = reinterpret_cast<const __half*>(p.x);
-    constexpr int kRegIters = 16;                          // rows up to 16 x 256 halves stay in registers
-    // (only for M <= 4: with all 8 warps bursting a whole row each the projections got slower, 16.2 -> 17.9 us on QKV)
-    const bool in_regs = (K % 256 == 0) && K / 256 <= kRegIters && M <= 4;
+    // (a register-resident row for M <= 4 was measured and removed: int4 B=1 step 2.18 -> 2.03 ms without it; requesting the
+    // first weight batch above griddepcontrol.wait, or every tile's first batch one tile ahead, measured slower at step
+    // level: cfg3 int8-KV 3.15 -> 3.16 / 3.34 ms, tools/mma_ab.sh)
     for (int m = warp; m < M; m += kMmaWarps) {
       const __half* xr = xin + (size_t) m * K;
-      if (in_regs) {
-        // the row in registers: one L2 round trip for the whole prologue; same arithmetic, same order as below
-        const int nit = K / 256;
-        uint4 raw[kRegIters];
-#pragma unroll
-        for (int it = 0; it < kRegIters; ++it)
-          if (it < nit) raw[it] = *reinterpret_cast<const uint4*>(xr + it * 256 + lane * 8);
-        if (p.prologue != kMProQuant) {
-          float sq = 0.f;
-#pragma unroll
-          for (int it = 0; it < kRegIters; ++it) {
-            if (it < nit) {
-              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h[j]);
-                sq += f.x * f.x + f.y * f.y;
-              }
-            }
-          }
-          sq = warp_sum(sq);
-          const float inv = rsqrtf(sq / K + p.eps);
-#pragma unroll
-          for (int it = 0; it < kRegIters; ++it) {
-            if (it < nit) {
-              __half2* h = reinterpret_cast<__half2*>(&raw[it]);
-              const uint4 g4 = *reinterpret_cast<const uint4*>(p.gamma + it * 256 + lane * 8);
-              const __half2* gm = reinterpret_cast<const __half2*>(&g4);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h[j]), gg = __half22float2(gm[j]);
-                h[j] = __floats2half2_rn(f.x * inv * gg.x, f.y * inv * gg.y);
-              }
-            }
-          }
-        }
-        if constexpr (INT) {
-          float amax = 0.f;
-#pragma unroll
-          for (int it = 0; it < kRegIters; ++it) {
-            if (it < nit) {
-              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(h[j]);
-                amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
-              }
-            }
-          }
-          amax = fmaxf(warp_max(amax), __half2float(__float2half_rn(1e-6f)));
-          const float qs = 127.f / amax;
-          if (lane == 0) srow[m] = amax / 127.f;
-#pragma unroll
-          for (int it = 0; it < kRegIters; ++it) {
-            if (it < nit) {
-              const __half2* h = reinterpret_cast<const __half2*>(&raw[it]);
-              float f[8];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 v = __half22float2(h[j]);
-                f[2 * j] = v.x * qs;
-                f[2 * j + 1] = v.y * qs;
-              }
-              uint2 o;
-              o.x = pack4_i8(f[0], f[1], f[2], f[3]);
-              o.y = pack4_i8(f[4], f[5], f[6], f[7]);
-              *reinterpret_cast<uint2*>(xs + (size_t) m * xstride + it * 256 + lane * 8) = o;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int it = 0; it < kRegIters; ++it)
-            if (it < nit) *reinterpret_cast<uint4*>(xs + (size_t) m * xstride + (size_t) (it * 256 + lane * 8) * 2) = raw[it];
-        }
-        continue;
-      }
       float inv = 1.f;
       if (p.prologue != kMProQuant) {
         float sq = 0.f;
@@ -424,6 +350,14 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
     }
     __syncthreads();   // wpart is rewritten by the next tile
   }
+  {
+    const unsigned total = p.pf_lines[0] + p.pf_lines[1];
+    const unsigned gw = blockIdx.x * kMmaWarps + warp, tw = gridDim.x * kMmaWarps;
+    for (unsigned l = gw * 32 + lane; l < total; l += tw * 32) {
+      const uint8_t* a = l < p.pf_lines[0] ? p.pf[0] + (size_t) l * 128 : p.pf[1] + (size_t) (l - p.pf_lines[0]) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
 }
 
 template <int KIND, bool SWIGLU>
@@ -480,8 +414,10 @@ bool gemv_mma_eligible(int kind, int M, int K) {
 
 int gemv_mma_launch(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
                     const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
-                    int swiglu, int prologue, const void* gamma, float eps, cudaStream_t stream) {
+                    int swiglu, int prologue, const void* gamma, float eps, const void* const* pf, const unsigned* pf_lines,
+                    cudaStream_t stream) {
   GemvMmaParams p{};
+  for (int i = 0; i < 2; ++i) { p.pf[i] = static_cast<const uint8_t*>(pf[i]); p.pf_lines[i] = pf_lines[i]; }
   p.x = x; p.w = w; p.w_scale = (const __half*) w_scale; p.sc = sc; p.sr = sr;
   p.sc_per_channel = sc_per_channel; p.sr_per_token = sr_per_token; p.residual = (const __half*) residual;
   p.y = (__half*) y; p.y_f32 = y_f32; p.M = M; p.N = N; p.K = K; p.swiglu = swiglu; p.n_out = swiglu ? N / 2 : N;
