@@ -53,8 +53,12 @@ def parse_arguments():
     args = p.parse_args()
     if args.dtype != 'float16':
         p.error("only --dtype float16 is built on this path")
-    if args.n_kv_head not in (None, args.n_head) or args.remove_input_padding or args.max_beam_width != 1:
-        p.error("multi-query attention, packed input and beam search are out of scope (DESIGN.md)")
+    if args.n_kv_head not in (None, args.n_head) or args.remove_input_padding:
+        p.error("multi-query attention and packed input are out of scope (DESIGN.md)")
+    if not 1 <= args.max_beam_width <= 16:
+        p.error("--max_beam_width must be in [1, 16]")
+    if args.max_beam_width > 1 and args.paged_kv_cache:
+        p.error("beam search reads the contiguous KV cache: --paged_kv_cache needs --max_beam_width 1")
     if args.use_smooth_quant and not (args.per_token and args.per_channel):
         p.error("SmoothQuant is built for --per_token --per_channel")
     return args
@@ -69,7 +73,8 @@ def main():
     os.makedirs(args.output_dir, exist_ok=True)
     qm = B.quant_mode_from_args(args)
     mc = ModelConfig(vocab_size=args.vocab_size, num_layers=args.n_layer, num_heads=args.n_head, hidden_size=args.n_embd,
-                     inter_size=args.inter_size, quant_mode=qm, max_batch_size=args.max_batch_size,
+                     inter_size=args.inter_size, quant_mode=qm,
+                     max_batch_size=args.max_batch_size * args.max_beam_width,     # rows = batch entries x beams
                      max_input_len=args.max_input_len, max_output_len=args.max_output_len, tp_size=args.world_size,
                      paged_kv_cache=args.paged_kv_cache, tokens_per_block=args.tokens_per_block)
     dev = "cuda" if torch.cuda.is_available() else "cpu"       # quantisation is build-time work; a GPU only makes it fast

@@ -72,8 +72,6 @@ def generate(args):
     from trtllm_llama_b200 import builder as B
     from trtllm_llama_b200 import runtime as rt
     from trtllm_llama_b200._lib import lib
-    if args.num_beams != 1:
-        raise SystemExit("beam search is out of scope on this path (DESIGN.md 8f-4)")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     mc = B.model_config_from_json(os.path.join(args.engine_dir, "config.json"), rank)
@@ -91,9 +89,9 @@ def generate(args):
     session = rt.GenerationSession(mc, tensors)
     if world > 1:
         session.enable_peer_allreduce()
-    session.setup(len(rows), max_in, args.max_output_len)
+    session.setup(len(rows), max_in, args.max_output_len, beam_width=args.num_beams)
     host_ids, host_lens = torch.from_numpy(ids).pin_memory(), torch.from_numpy(lens).pin_memory()
-    sampling = rt.SamplingConfig(end_id=EOS_TOKEN, pad_id=PAD_TOKEN, num_beams=1)
+    sampling = rt.SamplingConfig(end_id=EOS_TOKEN, pad_id=PAD_TOKEN, num_beams=args.num_beams)
     lat = []
     for _ in range(args.iterations):
         t0 = time.time()
@@ -104,10 +102,10 @@ def generate(args):
         out = out.numpy()
         for b in range(len(rows)):
             print(f'Input ids: {rows[b].tolist()}')
-            print(f'Output ids: {out[b].tolist()}')
+            print(f'Output ids: {out[b].tolist()}')      # num_beams > 1: [num_beams, output_len], best beam first
         if args.output_csv:
             with open(args.output_csv, 'w') as f:
-                csv.writer(f, delimiter=',').writerows(out.tolist())
+                csv.writer(f, delimiter=',').writerows(out.reshape(-1, out.shape[-1]).tolist())
         if args.output_npy:
             np.save(args.output_npy, out)
         drop = 5 if len(lat) > 5 else 0

@@ -19,8 +19,8 @@ def main(args):
     from trtllm_llama_b200 import runtime as rt
     from trtllm_llama_b200._lib import lib
     # flags of the reference CLI this path does not honour are REJECTED, never silently ignored
-    if args.num_beams != 1:
-        raise SystemExit("--num_beams > 1: beam search is not built on this path (DESIGN.md 8f-4)")
+    if args.num_beams != 1 and args.top_k != 1:
+        raise SystemExit("--num_beams > 1 does not combine with --top_k sampling (as in the reference's decoder)")
     if args.test_hf:
         raise SystemExit("--test_hf: no HF checkpoint / tokenizer offline; run_hf.py times the HF path on synthetic weights")
     if args.top_k < 0:
@@ -39,6 +39,8 @@ def main(args):
         session.enable_peer_allreduce()
     # LQ/summarize.py:125-140: top_k = 1 is greedy; larger values sample (seeded) among the k best
     sampling = rt.SamplingConfig(end_id=None, top_k=args.top_k, random_seed=args.random_seed) if args.top_k != 1 else None
+    if args.num_beams != 1:       # LQ/summarize.py:125-140 passes num_beams to the decoder; the best beam is summarised
+        sampling = rt.SamplingConfig(end_id=2, pad_id=2, num_beams=args.num_beams)
     rng = np.random.default_rng(0)
     max_in = min(args.max_input_len, mc.max_input_len)
     out_len = min(args.output_len, mc.max_output_len)
@@ -48,10 +50,12 @@ def main(args):
         ids = np.full((args.batch_size, int(lens.max())), 2, np.int32)
         for b, L in enumerate(lens):
             ids[b, :L] = rng.integers(3, mc.vocab_size, L)
-        session.setup(args.batch_size, ids.shape[1], out_len)
+        session.setup(args.batch_size, ids.shape[1], out_len, beam_width=args.num_beams)
         t0 = time.time()
         out = session.decode(torch.from_numpy(ids).pin_memory(), torch.from_numpy(lens).pin_memory(), sampling).numpy()
         total += time.time() - t0
+        if args.num_beams != 1:
+            out = out[:, 0]
         if args.check_accuracy and args.oracle_weights and rank == 0 and sampling is None:
             from oracle import ref_model as RM            # checker only (tests/bench infrastructure)
             w = np.load(args.oracle_weights, allow_pickle=True).item()

@@ -113,6 +113,15 @@ int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* se
                        const float* kv_scale_quant_orig, void* workspace, int* counters, int batch, int num_heads,
                        int head_size, int max_seq_len, int past_len, int max_input_len, int len_cap, int rotary_dim,
                        float q_scaling, int int8_kv, int nsplit, tb_stream_t stream);
+/* Beam search (GPTAttention input 7, cache_indirection [batch / beam_width, beam_width, max_seq_len] int32): cached position t
+ * of row (b, w) is read from the cache of row (b, cache_indirection[b][w][t]); the appended position is the row's own
+ * (K/decoderMaskedMultiheadAttention/decoderMaskedMultiheadAttentionTemplate.h:1137-1146,1624-1631).  `batch` counts rows
+ * (batch entries x beams).  Contiguous cache only.  Everything else as tb_mmha_decode_dev. */
+int tb_mmha_decode_beams(void* out, const void* qkv, void* kv_cache, const int* cache_indirection, int beam_width,
+                         const int* seq_lens, const int* input_lengths, const int* masked_tokens, const int* max_input_len_dev,
+                         const float* kv_scale_orig_quant, const float* kv_scale_quant_orig, int batch, int num_heads,
+                         int head_size, int max_seq_len, int past_len, int max_input_len, int len_cap, int rotary_dim,
+                         float q_scaling, int int8_kv, int nsplit, tb_stream_t stream);
 /* Paged KV cache (GPTAttention field paged_kv_cache; K/kvCacheUtils.h:34-112 KVBlockArray, beam width 1): instead of one
  * buffer, block_pointers [B, 2, max_blocks_per_seq] (int64 device addresses; K table then V table per sequence, as
  * T/tensorrt_llm/runtime/kv_cache_manager.py:163-184 builds it) name blocks of tokens_per_block positions laid out
@@ -157,6 +166,7 @@ int tb_finished(int* all_done, int* out_ids, int batch, int out_stride, int n_do
                 tb_stream_t s);
 int tb_half_to_float(float* out, const void* in, int64_t n, tb_stream_t s);
 int tb_fill_int(int* p, int value, int n, tb_stream_t s);
+int tb_tile_int(int* p, int n, int w, tb_stream_t s); /* in place p[i*w + j] = p[i]; n*w <= 1024 (_tile_beam_width) */
 int tb_copy(void* dst, const void* src, size_t bytes, tb_stream_t s); /* device-to-device */
 /* in [tp, rows, vocab_local] fp16 (all-gathered vocab-parallel lm_head) -> out [rows, tp*vocab_local] fp32 */
 int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int tp, tb_stream_t s);
@@ -173,6 +183,28 @@ int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int 
 int tb_sample(int* out_ids, const float* logits, int rows, int vocab, int vocab_stride, int top_k, float top_p,
               float temperature, unsigned long long seed, const int* step_dev, int step, const int* finished,
               int end_id, float* uniform_out, tb_stream_t stream);
+
+/* ---- beam search (SamplingConfig.num_beams > 1; replaces the beam half of DynamicDecodeOp:
+ * K/onlineSoftmaxBeamsearchKernels.cu:112-300,402-592, layers/onlineBeamSearchLayer.cu:30-62,
+ * layers/baseBeamSearchLayer.cu:29-67, K/decodingKernels.cu:31-170 gatherTree) ------------------------------------
+ * rows = batch entries x beam_width (beam fastest).  All state is device-resident:
+ *   cum_log_probs [rows] fp32, finished [rows] int32, beam_lens [rows] int32 (the decoder's sequence lengths),
+ *   out_ids_t / parent_ids_t [max_new][rows] time-major, cache indirections [batch][beam][max_seq_len] int32.
+ * tb_beam_init: cum = {0, -1e20, ...} per batch entry, finished = 0, beam_lens = *max_in_dev, both indirections 0.
+ * tb_beam_search_step: logits fp32 [rows][vocab_stride] (broadcast_rows != 0: [batch][vocab_stride], every beam reads its
+ *   entry's row — the step after the context phase); writes column *step_dev of out_ids_t / parent_ids_t, next_ids [rows],
+ *   updates cum / finished / beam_lens and writes tgt_indir from src_indir for positions [0, *max_in_dev + *step_dev].
+ *   length_penalty 0 = none.  beam_width <= 16.  workspace: tb_beam_workspace_bytes.
+ * tb_gather_tree: out [rows][n_steps] = each final beam's token path through parent_ids, end_id after the first end_id. */
+size_t tb_beam_workspace_bytes(int rows, int beam_width);
+int tb_beam_init(float* cum_log_probs, int* finished, int* beam_lens, int* indir_a, int* indir_b, const int* max_in_dev,
+                 int rows, int beam_width, int max_seq_len, tb_stream_t stream);
+int tb_beam_search_step(const float* logits, int vocab, int vocab_stride, int broadcast_rows, int rows, int beam_width,
+                        float length_penalty, int end_id, const int* step_dev, const int* max_in_dev, float* cum_log_probs,
+                        int* finished, int* beam_lens, int* out_ids_t, int* parent_ids_t, int* next_ids, const int* src_indir,
+                        int* tgt_indir, int max_seq_len, void* workspace, tb_stream_t stream);
+int tb_gather_tree(int* out, const int* out_ids_t, const int* parent_ids_t, int rows, int beam_width, int n_steps, int end_id,
+                   tb_stream_t stream);
 
 /* ---- whole decode step in one persistent kernel (1..tb_decode_step_max_batch() token rows) -----------------------
  * replaces, per generated token, the plugin schedule of GenerationSession.decode's step

@@ -8,7 +8,7 @@
  * 1..4 sequences — runs as one persistent kernel over the same buffers (tbrt_set_decode_mode).
  *
  * Replaces: the serialised TensorRT engine + IExecutionContext (T/tensorrt_llm/runtime/generation.py:61-100)
- * and the step loop of GenerationSession.decode (generation.py:782-997) for greedy, contiguous-KV, beam 1.
+ * and the step loop of GenerationSession.decode (generation.py:782-997) for greedy / sampling / beam search.
  */
 #ifndef TRTLLM_B200_RUNTIME_H
 #define TRTLLM_B200_RUNTIME_H
@@ -90,8 +90,16 @@ int tbrt_set_kv_blocks(tbrt_engine* e, const int32_t* host_block_ids, int batch,
 /* SamplingConfig (T/tensorrt_llm/runtime/generation.py:119-138): top_k = 1 (default) is greedy arg-max; top_k > 1 samples
  * among the k largest logits (top_p > 0 additionally restricts to that share of their mass); top_k = 0 with top_p > 0 is
  * nucleus sampling over the vocabulary; temperature scales the logits first (tb_sample).  The random stream is keyed by
- * (seed, generation step, batch row).  Beam search (num_beams > 1) is not built. */
+ * (seed, generation step, batch row). */
 int tbrt_set_sampling(tbrt_engine* e, int top_k, float top_p, float temperature, unsigned long long seed);
+/* Beam search (SamplingConfig.num_beams > 1; generation.py:365-409,823-997 + DynamicDecodeOp's beam layer):
+ *   tbrt_context(batch rows) -> tbrt_beam_begin (tiles the KV cache, lengths and logits beam_width times as
+ *   generation.py:898-915, redoes the first token as a beam step; the engine then runs batch x beam_width rows, which must
+ *   fit max_batch) -> tbrt_step x (n - 1) -> tbrt_beam_finalize (gather_tree: host_out [batch][beam_width][n_steps], best
+ *   beam first; cum_log_probs_out [batch][beam_width] or NULL).  length_penalty: score = cum_log_prob / length^penalty
+ *   (0 = none; SamplingConfig default 1).  Contiguous KV cache, beam_width in [2, 16]. */
+int tbrt_beam_begin(tbrt_engine* e, int beam_width, float length_penalty, int end_id, tb_stream_t s);
+int tbrt_beam_finalize(tbrt_engine* e, int32_t* host_out, float* cum_log_probs_out, int n_steps, tb_stream_t s);
 /* Generation steps can run as ONE persistent kernel (tb_decode_step_*) whenever the engine's configuration and the batch
  * allow it (mode 1); mode 0 forces the per-operator plugin schedule (IPluginV2DynamicExt::enqueue per operator, CUDA
  * graph) — same weights, caches and step state, so the two can be compared step by step.  Mode -1 (default) picks the

@@ -171,6 +171,47 @@ class OracleLlama:
         self.past += 1
         return self._logits(h)
 
+    def generate_beams(self, input_ids, input_lengths, max_new_tokens, beam_width, end_id, length_penalty=1.0):
+        """Beam search as GenerationSession.decode drives it (generation.py:365-409,823-997): context once per batch entry,
+        cache / lengths / logits tiled beam_width times, cum_log_probs {0, -1e20, ...}, one beam step per token, gather_tree.
+        Returns (ids [B, W, max_new_tokens], cum_log_probs [B, W], min selection margin over all steps)."""
+        c, W = self.cfg, int(beam_width)
+        logits = self.context(input_ids, input_lengths)
+        B = self.B
+        rows = B * W
+        self.cache = [np.repeat(k, W, axis=0) for k in self.cache]
+        self.in_lens = np.repeat(self.in_lens, W)
+        self.B = rows
+        logits = np.repeat(logits, W, axis=0)
+        cum = np.tile(np.array([0.0] + [-1e20] * (W - 1), dtype=F32), B)
+        fin, lens = np.zeros(rows, bool), np.full(rows, self.max_in, np.int64)
+        indir = np.zeros((B, W, self.S_max), np.int32)
+        ids_t, par_t, margin = [], [], np.inf
+        for s in range(max_new_tokens):
+            tok, par, cum, fin, lens, indir, m = R.beam_search_step(logits, cum, fin, lens, indir, self.max_in + s, beam_width=W,
+                                                                    end_id=end_id, length_penalty=length_penalty)
+            margin = min(margin, m)
+            ids_t.append(tok)
+            par_t.append(par)
+            if s + 1 < max_new_tokens:
+                logits = self.step_beams(tok, indir, W)
+        out = R.gather_tree(np.stack(ids_t), np.stack(par_t), W, end_id)
+        return out.reshape(B, W, max_new_tokens), cum.reshape(B, W), margin
+
+    def step_beams(self, token_ids, cache_indir, beam_width):
+        c = self.cfg
+        h = self.w["vocab_embedding"][np.asarray(token_ids).reshape(-1)]
+
+        def attn(li, qkv):
+            return R.mmha_decode_beams(qkv, self.cache[li], cache_indir, beam_width, self.past, self.in_lens, self.max_in,
+                                       num_heads=c.heads, head_size=c.head_size, kv_scale_orig_quant=self.kv_oq,
+                                       kv_scale_quant_orig=self.kv_qo)
+
+        for li in range(c.layers):
+            h = self._layer(li, h, attn)
+        self.past += 1
+        return self._logits(h)
+
     def generate(self, input_ids, input_lengths, max_new_tokens, return_logits=False):
         logits = self.context(input_ids, input_lengths)
         ids, all_logits = [], []

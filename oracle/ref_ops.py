@@ -475,3 +475,114 @@ def sample_top_k_top_p(logits, top_k, top_p, temperature, uniforms):
             ids[b] = order[j] if j < V else order[0]      # never reached: the scan leaves the top token (:957)
             tables.append((order, p, c))
     return ids, tables
+
+
+# --------------------------------------------------------------------------- #
+# f4: beam search (num_beams > 1) — the beam half of DynamicDecodeOp as the Python runtime drives it (no BeamHypotheses)
+# --------------------------------------------------------------------------- #
+def beam_search_step(logits, cum_log_probs, finished, beam_lens, src_indir, pos, *, beam_width, end_id, length_penalty=1.0):
+    """One decoding step.  logits [rows, V] fp32 (rows = batch x beam, beam fastest); cum_log_probs [rows] fp32;
+    finished [rows] bool; beam_lens [rows] int (the decoder's sequence lengths); src_indir [batch, beam, S_max] int;
+    pos = sequence position of the token being chosen (max_input_length + generation step).
+
+    Returns (tokens [rows], parents [rows], cum' [rows], finished' [rows], beam_lens' [rows], tgt_indir, margin) where margin
+    is the smallest gap between a selected and the best rejected normalised score (tolerance-aware tests).
+
+      K/onlineSoftmaxBeamsearchKernels.cu:402-592  per row: the 2W largest logits, log-softmax = l - max - log(sum exp(l - max)),
+          candidate value = cum_log_probs[row] + log-softmax; a finished row proposes end_id with log-probability 0 and
+          nothing else (every other entry is -MAX, i.e. -inf after the subtraction)
+      :112-300 batch_topk_kernel: per batch entry the W best of the 2 W^2 candidates by value / len^length_penalty, where —
+          with no BeamHypotheses — candidate j (0..2W-1) of ANY beam is normalised with the length of beam (j mod W)
+          (`elem_id % K`), len = beam_lens (+1 unless that beam is finished), and len == 1 or length_penalty == 0 skip it
+          (:44-52); the new cum_log_probs is the un-normalised value
+      layers/onlineBeamSearchLayer.cu:30-62 update_kernel: parent = candidate's beam, token, finished' = token == end_id,
+          beam_lens' = the parent's length after its own increment
+      layers/baseBeamSearchLayer.cu:29-67 update_indir_cache: unfinished beams: tgt[beam][t] = src[parent][t] for t < pos,
+          tgt[beam][pos] = beam
+    """
+    logits = np.asarray(logits, dtype=F32)
+    rows, V = logits.shape
+    W, n = int(beam_width), 2 * int(beam_width)
+    batch = rows // W
+    cum = np.asarray(cum_log_probs, dtype=F32)
+    fin = np.asarray(finished).astype(bool)
+    lens = np.asarray(beam_lens, dtype=np.int64)
+    cand_id = np.zeros((rows, n), np.int64)
+    cand_val = np.full((rows, n), -np.inf, dtype=F32)
+    for r in range(rows):
+        if fin[r]:
+            cand_id[r, 0], cand_val[r, 0] = end_id, cum[r]
+            continue
+        l = logits[r]
+        order = np.lexsort((np.arange(V), -l.astype(np.float64)))[:n]
+        m = l.max()
+        d = np.exp((l - m).astype(F32)).astype(F32).sum(dtype=np.float64)
+        lp = ((l[order] - m).astype(F32) - F32(np.log(d))).astype(F32)
+        cand_id[r], cand_val[r] = order, (lp + cum[r]).astype(F32)
+    tokens, parents = np.zeros(rows, np.int32), np.zeros(rows, np.int32)
+    new_cum, new_fin, new_lens = cum.copy(), fin.copy(), lens.copy()
+    tgt = np.array(src_indir, dtype=np.int32, copy=True)
+    margin = np.inf
+    for b in range(batch):
+        base = b * W
+        inc = lens[base:base + W] + (~fin[base:base + W]).astype(np.int64)
+        elem = np.empty(W * n, dtype=F32)
+        for e in range(W * n):
+            i = (e % n) % W
+            v = cand_val[base + e // n, e % n]
+            ln = inc[i]
+            if length_penalty != 0.0 and ln != 1 and np.isfinite(v):
+                v = F32(v / F32(np.power(F32(ln), F32(length_penalty))))
+            elem[e] = v
+        order = np.lexsort((np.arange(W * n), -elem.astype(np.float64)))
+        sel = order[:W]
+        if W * n > W and np.isfinite(elem[order[W]]):
+            margin = min(margin, float(elem[sel[-1]] - elem[order[W]]))
+        for k in range(W - 1):
+            margin = min(margin, float(elem[sel[k]] - elem[sel[k + 1]])) if np.isfinite(elem[sel[k + 1]]) else margin
+        for k, e in enumerate(sel):
+            pb, j = e // n, e % n
+            tokens[base + k] = cand_id[base + pb, j]
+            parents[base + k] = pb
+            new_cum[base + k] = cand_val[base + pb, j]
+            new_fin[base + k] = tokens[base + k] == end_id
+            new_lens[base + k] = inc[pb]
+        for k in range(W):
+            if new_fin[base + k]:
+                continue
+            tgt[b, k, :pos] = np.asarray(src_indir)[b, parents[base + k], :pos]
+            tgt[b, k, pos] = k
+    return tokens, parents, new_cum, new_fin, new_lens, tgt, margin
+
+
+def gather_tree(out_ids_t, parent_ids_t, beam_width, end_id):
+    """out_ids_t / parent_ids_t [n_steps, rows] -> [rows, n_steps]: each final beam's path through the parent pointers, then
+    end_id after the first end_id (K/decodingKernels.cu:31-170 for the generated part)."""
+    out_ids_t, parent_ids_t = np.asarray(out_ids_t), np.asarray(parent_ids_t)
+    n, rows = out_ids_t.shape
+    W = int(beam_width)
+    out = np.zeros((rows, n), np.int32)
+    for r in range(rows):
+        base, beam = r // W * W, r % W
+        for c in range(n - 1, -1, -1):
+            out[r, c] = out_ids_t[c, base + beam]
+            beam = parent_ids_t[c, base + beam]
+        hit = np.nonzero(out[r] == end_id)[0]
+        if hit.size:
+            out[r, hit[0]:] = end_id
+    return out
+
+
+def mmha_decode_beams(qkv, kv_cache, cache_indir, beam_width, past_len, input_lengths, max_input_len, **kw):
+    """mmha_decode with beam search: cached position t of row (b, w) is read from row (b, cache_indir[b][w][t]); the
+    position appended now is the row's own (decoderMaskedMultiheadAttentionTemplate.h:1137-1146,1624-1631).  kv_cache
+    [rows, 2, H, S_max, Dh] is updated in place at ``past_len`` only."""
+    rows, W, t = kv_cache.shape[0], int(beam_width), int(past_len)
+    ind = np.asarray(cache_indir).reshape(rows, -1)
+    gathered = kv_cache.copy()
+    for r in range(rows):
+        src = r // W * W + ind[r, :t]
+        gathered[r, :, :, :t, :] = kv_cache[src, :, :, np.arange(t), :].transpose(1, 2, 0, 3)
+    out = mmha_decode(qkv, gathered, past_len, input_lengths, max_input_len, **kw)
+    kv_cache[:, :, :, t, :] = gathered[:, :, :, t, :]
+    return out

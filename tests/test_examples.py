@@ -45,7 +45,7 @@ def test_build_writes_reference_artefacts(tmp_path):
 
 def test_build_rejects_out_of_scope_flags(tmp_path):
     for bad in (["--remove_input_padding"], ["--n_kv_head", "1"], ["--dtype", "bfloat16"], ["--use_smooth_quant"],
-                ["--max_beam_width", "2"]):
+                ["--max_beam_width", "17"], ["--max_beam_width", "2", "--paged_kv_cache"]):
         r = subprocess.run([sys.executable, os.path.join(EX, "build.py"), "--output_dir", str(tmp_path), *TINY, *bad],
                            capture_output=True, text=True, timeout=300)
         assert r.returncode != 0
@@ -62,10 +62,38 @@ def test_build_paged_kv_cache_flag(tmp_path):
 
 
 def test_summarize_rejects_flags_it_does_not_honour(tmp_path):
-    for bad in (["--num_beams", "4"], ["--test_hf"]):
+    for bad in (["--num_beams", "4", "--top_k", "8"], ["--test_hf"]):
         r = subprocess.run([sys.executable, os.path.join(EX, "summarize.py"), "--engine_dir", str(tmp_path), *bad],
                            capture_output=True, text=True, timeout=300)
-        assert r.returncode != 0 and ("not built" in r.stderr or "offline" in r.stderr), r.stderr[-500:]
+        assert r.returncode != 0 and ("does not combine" in r.stderr or "offline" in r.stderr), r.stderr[-500:]
+
+
+def test_build_max_beam_width_sizes_the_engine_rows(tmp_path):
+    """--max_beam_width (LQ/build.py:35): the engine holds max_batch_size x max_beam_width rows."""
+    _build(tmp_path, "--int8_kv_cache", "--max_batch_size", "2", "--max_beam_width", "3")
+    cfg = json.load(open(tmp_path / "config.json"))
+    assert cfg["builder_config"]["max_batch_size"] == 6
+
+
+@pytest.mark.gpu
+def test_run_py_beam_search(tmp_path):
+    """run.py --num_beams 3 (LQ/run.py:56-59): [batch, beams, output_len] ids, best beam first, equal to the runtime API."""
+    _build(tmp_path, "--use_weight_only", "--int8_kv_cache", "--max_batch_size", "2", "--max_beam_width", "3")
+    ids = np.random.default_rng(4).integers(3, 512, (2, 9)).astype(np.int32)
+    np.save(tmp_path / "in.npy", ids)
+    r = subprocess.run([sys.executable, os.path.join(EX, "run.py"), "--max_output_len", "8", "--engine_dir", str(tmp_path),
+                        "--input_tokens", str(tmp_path / "in.npy"), "--output_npy", str(tmp_path / "out.npy"), "--num_beams", "3",
+                        "--iterations", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mean latency" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    out = np.load(tmp_path / "out.npy")
+    from trtllm_llama_b200 import builder as B
+    from trtllm_llama_b200 import runtime as rt
+    mc = B.model_config_from_json(str(tmp_path / "config.json"))
+    sess = rt.GenerationSession(mc, B.deserialize_engine(str(tmp_path / "llama_float16_tp1_rank0.engine")))
+    sess.setup(2, 9, 8, beam_width=3)
+    sc = rt.SamplingConfig(end_id=2, pad_id=2, num_beams=3)
+    ref = sess.decode(torch.from_numpy(ids).pin_memory(), torch.full((2,), 9, dtype=torch.int32).pin_memory(), sc).numpy()
+    assert out.shape == (2, 3, 8) and np.array_equal(out, ref)
 
 
 @pytest.mark.gpu
@@ -78,9 +106,9 @@ def test_summarize_py_runs_and_checks_agreement(tmp_path):
     from trtllm_llama_b200 import builder as B
     from trtllm_llama_b200.runtime import ModelConfig
     mc = ModelConfig(vocab_size=512, num_layers=2, num_heads=2, hidden_size=256, inter_size=384)
-    w = B.random_llama_weights(mc, seed=5, device="cpu")
-    wn = {k: w[k].numpy() for k in ("vocab_embedding", "ln_f", "lm_head")}
-    wn["layers"] = [{k: v.numpy() for k, v in lw.items()} for lw in w["layers"]]
+    w = B.random_llama_weights(mc, seed=5, device="cuda")        # build.py draws on the GPU's generator when there is one
+    wn = {k: w[k].cpu().numpy() for k in ("vocab_embedding", "ln_f", "lm_head")}
+    wn["layers"] = [{k: v.cpu().numpy() for k, v in lw.items()} for lw in w["layers"]]
     np.save(tmp_path / "w.npy", wn, allow_pickle=True)
     base = [sys.executable, os.path.join(EX, "summarize.py"), "--engine_dir", str(tmp_path), "--batch_size", "2", "--max_ite",
             "2", "--max_input_len", "16", "--output_len", "8"]

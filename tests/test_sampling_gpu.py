@@ -133,7 +133,7 @@ def test_engine_sampling_config():
         assert not np.array_equal(p, greedy)
         # back to greedy: identical to the first run (the fused step is re-enabled for B <= 4)
         assert np.array_equal(sess.decode(host(ids_r), host(lens_r)).numpy(), greedy)
-    with pytest.raises(NotImplementedError):
-        sess.decode(host(ids_r), host(lens_r), SamplingConfig(num_beams=2))
+    with pytest.raises(NotImplementedError):      # beam search is a decoder of its own (tests/test_beam_search_gpu.py)
+        sess.decode(host(ids_r), host(lens_r), SamplingConfig(num_beams=2, top_k=4))
     with pytest.raises(NotImplementedError):
         sess.decode(host(ids_r), host(lens_r), SamplingConfig(repetition_penalty=1.2))

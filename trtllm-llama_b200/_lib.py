@@ -58,6 +58,13 @@ SIGNATURES = {
     "tb_advance_step": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
     "tb_half_to_float": (i32, [vp, vp, i64, vp]),
     "tb_fill_int": (i32, [vp, i32, i32, vp]),
+    "tb_tile_int": (i32, [vp, i32, i32, vp]),
+    "tb_mmha_decode_beams": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32,
+                                   i32, i32, vp]),
+    "tb_beam_workspace_bytes": (sz, [i32, i32]),
+    "tb_beam_init": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "tb_beam_search_step": (i32, [vp, i32, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]),
+    "tb_gather_tree": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "tb_copy": (i32, [vp, vp, sz, vp]),
     "tb_gather_logits": (i32, [vp, vp, i32, i32, i32, vp]),
     "tb_sample": (i32, [vp, vp, i32, i32, i32, i32, f32, f32, C.c_uint64, vp, i32, vp, i32, vp, vp]),
@@ -143,6 +150,8 @@ SIGNATURES.update({
     "tbrt_kv_max_blocks_per_seq": (i32, [vp]),
     "tbrt_set_kv_blocks": (i32, [vp, vp, i32, i32, vp]),
     "tbrt_set_sampling": (i32, [vp, i32, f32, f32, C.c_uint64]),
+    "tbrt_beam_begin": (i32, [vp, i32, f32, i32, vp]),
+    "tbrt_beam_finalize": (i32, [vp, vp, vp, i32, vp]),
     "tbrt_fused_step_available": (i32, [vp]),
     "tbrt_last_steps": (i32, [vp]),
     "tb_finished": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp]),

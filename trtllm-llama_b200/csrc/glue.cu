@@ -168,6 +168,12 @@ __global__ void half_to_float_kernel(float* out, const __half* in, int64_t n) {
     out[i] = __half2float(in[i]);
 }
 
+__global__ void tile_int_kernel(int* p, int n, int w) {
+  const int t = threadIdx.x;
+  const int v = t < n * w ? p[t / w] : 0;
+  __syncthreads();
+  if (t < n * w) p[t] = v;
+}
 __global__ void fill_int_kernel(int* p, int v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -249,6 +255,13 @@ int tb_copy(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 
 int tb_fill_int(int* p, int value, int n, cudaStream_t s) {
   fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, value, n);
+  return (int) cudaGetLastError();
+}
+
+// in place: p[i * w + j] = p[i] for i < n, j < w (generation.py:30-38 _tile_beam_width on a 1-D tensor); n * w <= 1024
+int tb_tile_int(int* p, int n, int w, cudaStream_t s) {
+  if (n < 1 || w < 1 || n * w > 1024) return -1;
+  tile_int_kernel<<<1, 1024, 0, s>>>(p, n, w);
   return (int) cudaGetLastError();
 }
 

@@ -39,6 +39,10 @@ struct MmhaParams {
   // blocks laid out [H, tokens_per_block, Dh]; NULL: contiguous kv_cache [B, 2, H, S_max, Dh]
   const long long* block_ptrs;
   int tpb_log2, max_blocks;
+  // beam search (BEAMS): cache_indirection [batch, beam, S_max] — cached position t of row (batch, beam) lives in the cache
+  // of row (batch, cache_indir[batch][beam][t]) (decoderMaskedMultiheadAttentionTemplate.h:1137-1146,1624-1631)
+  const int* cache_indir;
+  int beam_width;
   const float* kv_scale_orig_quant;
   const float* kv_scale_quant_orig;
   float* partial;            // [B*H*nsplit*(Dh+2)] fp32 workspace
@@ -101,9 +105,10 @@ __device__ __forceinline__ uint32_t mmha_pack_h2(float a, float b) { return mmha
 // column 0 of B.  P.V: A = V^T with lane g owning dims [16g, 16g + 16) (row g of MMA m = dim 16g + m, row g + 8 = dim
 // 16g + 8 + m), so a lane loads 16 contiguous bytes of 4 keys; key pairs are interleaved with PRMT before the
 // expansion; the fp16 probabilities sit in column 0 of B.
-template <bool INT8, bool MMA = false, bool PAGED = false>
+template <bool INT8, bool MMA = false, bool PAGED = false, bool BEAMS = false>
 __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_decode_kernel(MmhaParams p) {
   static_assert(!MMA || INT8, "the tensor-core loops are for int8 caches");
+  static_assert(!BEAMS || (!MMA && !PAGED), "beam search reads the contiguous cache through the FMA loops");
   using TR = KvTraits<INT8>;
   constexpr int LPK = TR::kLanesPerKey, DPL = TR::kDimsPerLane, KPI = TR::kKeysPerIter;
   constexpr int ELT = INT8 ? 1 : 2;
@@ -141,10 +146,18 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
   // row of cached position t of this (sequence, head): contiguous cache, or KVBlockArray addressing — block t >> log2(tpb)
   // of the sequence's K (V) table, row (h * tpb + (t & (tpb - 1))) of the block (kvCacheUtils.h:58-112 getKVLocalIdx)
   const long long* ktab = PAGED ? p.block_ptrs + (size_t) b * 2 * p.max_blocks : nullptr;
+  // BEAMS: cached positions come from the row the indirection names; the appended position tlen is the row's own
+  const int* indir = BEAMS ? p.cache_indir + (size_t) b * p.S_max : nullptr;
+  const int beam0 = BEAMS ? b / p.beam_width * p.beam_width : 0;
+  auto beam_shift = [&](int t) -> ptrdiff_t {
+    return t < tlen ? ((ptrdiff_t) (beam0 + indir[t]) - b) * (ptrdiff_t) seq_stride : 0;
+  };
   auto krow = [&](int t) -> uint8_t* {
     if constexpr (PAGED)
       return reinterpret_cast<uint8_t*>(ktab[t >> p.tpb_log2]) +
              ((size_t) (h << p.tpb_log2) + (t & ((1 << p.tpb_log2) - 1))) * kDh * ELT;
+    else if constexpr (BEAMS)
+      return kbase + beam_shift(t) + (size_t) t * kDh * ELT;
     else
       return kbase + (size_t) t * kDh * ELT;
   };
@@ -152,6 +165,8 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
     if constexpr (PAGED)
       return reinterpret_cast<uint8_t*>(ktab[p.max_blocks + (t >> p.tpb_log2)]) +
              ((size_t) (h << p.tpb_log2) + (t & ((1 << p.tpb_log2) - 1))) * kDh * ELT;
+    else if constexpr (BEAMS)
+      return vbase + beam_shift(t) + (size_t) t * kDh * ELT;
     else
       return vbase + (size_t) t * kDh * ELT;
   };
@@ -160,7 +175,7 @@ __global__ void __launch_bounds__(kMmhaThreads, MMA ? 2 : (INT8 ? 0 : 4)) mmha_d
   // short of what HBM needs at 2048-token contexts, and the V range is not touched until the Q.K^T pass and the softmax
   // are done (cfg3, fp16 KV: 1260 -> 1295 tokens/s).  The int8 variant is issue-bound on the dequantisation (3
   // instructions per element), not on memory: the same prefetch costs it 2 %, so it is compiled out there.
-  if constexpr (!INT8 && !PAGED) {
+  if constexpr (!INT8 && !PAGED && !BEAMS) {
     if (len >= 256) {
       const uint32_t range = (uint32_t) len * kDh * ELT, piece = 16384;
       const uint32_t npiece = (range + piece - 1) / piece;
@@ -536,7 +551,7 @@ static int mmha_launch(void* out, const void* qkv, void* kv_cache, const long lo
                        const int* max_input_len_dev, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
                        void* workspace, int* counters, int batch, int num_heads, int head_size, int max_seq_len,
                        int past_len, int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv,
-                       int nsplit, cudaStream_t stream);
+                       int nsplit, cudaStream_t stream, const int* cache_indir = nullptr, int beam_width = 1);
 
 int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* seq_lens, const int* input_lengths,
                        const int* masked_tokens, const int* max_input_len_dev, const float* kv_scale_orig_quant,
@@ -546,6 +561,18 @@ int tb_mmha_decode_dev(void* out, const void* qkv, void* kv_cache, const int* se
   return mmha_launch(out, qkv, kv_cache, nullptr, 0, 0, seq_lens, input_lengths, masked_tokens, max_input_len_dev,
                      kv_scale_orig_quant, kv_scale_quant_orig, workspace, counters, batch, num_heads, head_size, max_seq_len,
                      past_len, max_input_len, len_cap, rotary_dim, q_scaling, int8_kv, nsplit, stream);
+}
+
+int tb_mmha_decode_beams(void* out, const void* qkv, void* kv_cache, const int* cache_indirection, int beam_width,
+                         const int* seq_lens, const int* input_lengths, const int* masked_tokens, const int* max_input_len_dev,
+                         const float* kv_scale_orig_quant, const float* kv_scale_quant_orig, int batch, int num_heads,
+                         int head_size, int max_seq_len, int past_len, int max_input_len, int len_cap, int rotary_dim,
+                         float q_scaling, int int8_kv, int nsplit, cudaStream_t stream) {
+  if (!cache_indirection || beam_width < 1) return -1;
+  return mmha_launch(out, qkv, kv_cache, nullptr, 0, 0, seq_lens, input_lengths, masked_tokens, max_input_len_dev,
+                     kv_scale_orig_quant, kv_scale_quant_orig, nullptr, nullptr, batch, num_heads, head_size, max_seq_len,
+                     past_len, max_input_len, len_cap, rotary_dim, q_scaling, int8_kv, nsplit, stream, cache_indirection,
+                     beam_width);
 }
 
 int tb_mmha_decode_paged(void* out, const void* qkv, const int64_t* block_pointers, int tokens_per_block,
@@ -564,6 +591,12 @@ int tb_mmha_decode_paged(void* out, const void* qkv, const int64_t* block_pointe
 
 template <bool INT8, bool MMA>
 static int mmha_launch_t(const cudaLaunchConfig_t& cfg, const MmhaParams& p, size_t smem, bool paged) {
+  if constexpr (!MMA) {
+    if (p.cache_indir) {
+      if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<INT8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<INT8, false, false, true>, p);
+    }
+  }
   if (paged) {
     if (smem > 48 * 1024) TB_CHECK_CUDA(cudaFuncSetAttribute(mmha_decode_kernel<INT8, MMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     return (int) cudaLaunchKernelEx(&cfg, mmha_decode_kernel<INT8, MMA, true>, p);
@@ -577,8 +610,9 @@ static int mmha_launch(void* out, const void* qkv, void* kv_cache, const long lo
                        const int* max_input_len_dev, const float* kv_scale_orig_quant, const float* kv_scale_quant_orig,
                        void* workspace, int* counters, int batch, int num_heads, int head_size, int max_seq_len,
                        int past_len, int max_input_len, int len_cap, int rotary_dim, float q_scaling, int int8_kv,
-                       int nsplit, cudaStream_t stream) {
-  if (head_size != kDh) return -1;                 // LLaMA-7B head size; other sizes are not built
+                       int nsplit, cudaStream_t stream, const int* cache_indir, int beam_width) {
+  if (head_size != kDh) return -1;
+  if (cache_indir && (block_ptrs || beam_width < 1 || batch % beam_width)) return -1;   // beams read the contiguous cache                 // LLaMA-7B head size; other sizes are not built
   if (rotary_dim != 0 && rotary_dim != kDh) return -1;
   if (past_len + 1 > max_seq_len || len_cap + 1 > max_seq_len + 1) return -2;
   if (int8_kv && (!kv_scale_orig_quant || !kv_scale_quant_orig)) return -1;
@@ -594,12 +628,13 @@ static int mmha_launch(void* out, const void* qkv, void* kv_cache, const long lo
   p.past_len = past_len; p.max_input_len = max_input_len; p.S_max = max_seq_len; p.H = num_heads;
   p.rotary_dim = rotary_dim; p.inv_sqrt_dh = 1.f / (sqrtf((float) head_size) * q_scaling);
   p.block_ptrs = block_ptrs; p.max_blocks = max_blocks;
+  p.cache_indir = cache_indir; p.beam_width = beam_width;
   p.tpb_log2 = 0;
   while (block_ptrs && (1 << p.tpb_log2) < tokens_per_block) ++p.tpb_log2;
   const bool paged = block_ptrs != nullptr;
   // int8 caches with long contexts: tensor-core loops, two CTAs per SM, so no more splits than fit one wave
   const int mma_env = g_mma_mode;   // A/B switch (TB_MMHA_MMA / tb_mmha_set_mode): 0 off, 1 always, -1 automatic
-  const bool use_mma = int8_kv && (mma_env == 1 || (mma_env != 0 && len_cap >= 512));
+  const bool use_mma = int8_kv && !cache_indir && (mma_env == 1 || (mma_env != 0 && len_cap >= 512));
   if (use_mma) {
     const int fit = (2 * kNumSMs) / (batch * num_heads);
     if (nsplit > fit) nsplit = fit < 1 ? 1 : fit;

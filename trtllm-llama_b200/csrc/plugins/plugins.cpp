@@ -128,7 +128,7 @@ class GPTAttentionPlugin : public BasePlugin {
       const int64_t* block_ptrs = paged_kv_ ? static_cast<const int64_t*>(in[bp_idx]) : nullptr;
       if (paged_kv_) {
         TBP_REQUIRE(block_ptrs != nullptr && max_blocks > 0, "paged_kv_cache needs the block_pointers input");
-        TBP_REQUIRE(id[bp_idx].dims.nbDims < 2 || id[bp_idx].dims.d[1] == 1, "beam width 1 only");
+        TBP_REQUIRE(id[bp_idx].dims.nbDims < 2 || id[bp_idx].dims.d[1] == 1, "paged cache: beam width 1 only");
       }
       const int S_max = paged_kv_ ? tpb * max_blocks : id[1].dims.d[3];
       const int* host_len = static_cast<const int*>(in[3]);          // HOST tensor {past_len, is_context}
@@ -160,6 +160,17 @@ class GPTAttentionPlugin : public BasePlugin {
                                     static_cast<const int*>(in[5]), static_cast<const int*>(in[4]), max_in_dev, s_oq, s_qo, B,
                                     num_heads_, head_size_, device_lengths_ ? 0 : past_len, max_in, cap, rotary_dim_,
                                     q_scaling_, int8_kv_, nsplit, stream);
+      // beam search: cache_indirection [B / beam, beam, S_max] with beam > 1 selects, per cached position, which beam's
+      // cache row is read (gptAttentionCommon.cpp:700-712 passes it to the kernel whenever beam_width > 1)
+      const int beam = (in[7] && id[7].dims.nbDims == 3) ? id[7].dims.d[1] : 1;
+      if (beam > 1) {
+        TBP_REQUIRE(B % beam == 0 && id[7].dims.d[0] * beam == B && id[7].dims.d[2] == S_max,
+                    "cache_indirection must be [batch / beam, beam, max_seq_len]");
+        return tb_mmha_decode_beams(out[0], in[0], cache, static_cast<const int*>(in[7]), beam, static_cast<const int*>(in[2]),
+                                    static_cast<const int*>(in[5]), static_cast<const int*>(in[4]), max_in_dev, s_oq, s_qo, B,
+                                    num_heads_, head_size_, S_max, device_lengths_ ? 0 : past_len, max_in, cap, rotary_dim_,
+                                    q_scaling_, int8_kv_, nsplit, stream);
+      }
       return tb_mmha_decode_dev(out[0], in[0], cache, static_cast<const int*>(in[2]), static_cast<const int*>(in[5]),
                                 static_cast<const int*>(in[4]), max_in_dev, s_oq, s_qo, workspace, nullptr, B, num_heads_,
                                 head_size_, S_max, device_lengths_ ? 0 : past_len, max_in, cap, rotary_dim_, q_scaling_,

@@ -146,6 +146,15 @@ struct tbrt_engine {
   float top_p = 0.f, temperature = 1.f;
   unsigned long long seed = 0;
   bool sampling() const { return top_k != 1 && !(top_k == 0 && top_p <= 0.f); }
+  // beam search (SamplingConfig.num_beams > 1, generation.py:365-409,823-997): rows = batch entries x beams after
+  // tbrt_beam_begin; all decoder state is device-resident so the step stays one replayable graph
+  int beam_W = 1, beam_end_id = -1;
+  float beam_length_penalty = 0.f;
+  float* d_cum = nullptr;
+  int *d_fin = nullptr, *d_beam_lens = nullptr, *d_ids_t = nullptr, *d_parent_t = nullptr, *d_indir[2] = {nullptr, nullptr},
+      *d_beam_out = nullptr;
+  void* d_beam_ws = nullptr;
+  int beam_step(bool broadcast, cudaStream_t s);
   tb_ar* ar = nullptr;          // peer-memory all-reduce of the decode path (tensor parallel)
   bool ar_open = false;
   int ar_site = 0;              // call-site parity, reset per step (two calls per layer: even per step)
@@ -178,7 +187,7 @@ struct tbrt_engine {
   void build_decode_step();
   bool fused_step() const {
     const bool want = decode_mode < 0 ? c.tp_size > 1 : decode_mode != 0;
-    return ds && want && !sampling() && B <= tb_decode_step_max_batch();
+    return ds && want && !sampling() && beam_W == 1 && B <= tb_decode_step_max_batch();
   }
 };
 
@@ -445,6 +454,10 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
         id[bp] = desc({Bq, 1, 2, 2 * max_blocks}, DataType::kINT32);
         in[bp] = d_block_tables + (size_t) li * c.max_batch * 2 * max_blocks;
       }
+      if (beam_W > 1 && !context) {   // cache_indirection [batch, beam, S_max]: which beam's cache row holds position t
+        id[7] = desc({Bq / beam_W, beam_W, S_max}, DataType::kINT32);
+        in[7] = d_indir[0];
+      }
       void* out[2] = {att, kv[li]};
       launches += context ? 2 : 1;
       RT_CALL(attn->enqueue(id, od, in, out, workspace, s));
@@ -575,7 +588,9 @@ int tbrt_engine::head(int rows, const __half* src, cudaStream_t s) {
     RT_CALL(allgather->enqueue(id, od, in, out, workspace, s));
     RT_CALL(tb_gather_logits(logits, logits_h + (size_t) rows * vocab_l, rows, vocab_l, c.tp_size, s));
   }
-  if (sampling()) {
+  if (beam_W > 1) {
+    if (beam_step(false, s)) return -1;
+  } else if (sampling()) {
     // the generation step (column of output_ids being produced) keys the random stream: read on the device, so the
     // captured step graph draws fresh numbers on every replay
     RT_CALL(tb_sample(d_next, logits, rows, c.vocab, c.vocab, top_k, top_p > 0.f ? top_p : 1.f, temperature, seed, d_step_pos, 0,
@@ -584,6 +599,18 @@ int tbrt_engine::head(int rows, const __half* src, cudaStream_t s) {
     RT_CALL(tb_argmax(d_next, logits, rows, c.vocab, c.vocab, s));
   }
   RT_CALL(tb_advance_step(d_next, d_ids, d_out_ids, d_seq_lens, d_step_pos, rows, c.max_output_len, s));
+  return 0;
+}
+
+// one beam-search decoding step on the logits of all rows: candidates, selection, bookkeeping, cache indirection
+// (tgt written from src, then copied back so the attention plugin always reads d_indir[0])
+int tbrt_engine::beam_step(bool broadcast, cudaStream_t s) {
+  const int rows = broadcast ? B * beam_W : B;
+  launches += 2;
+  RT_CALL(tb_beam_search_step(logits, c.vocab, c.vocab, broadcast ? 1 : 0, rows, beam_W, beam_length_penalty, beam_end_id,
+                              d_step_pos, d_max_in, d_cum, d_fin, d_beam_lens, d_ids_t, d_parent_t, d_next, d_indir[0],
+                              d_indir[1], S_max, d_beam_ws, s));
+  RT_CUDA(cudaMemcpyAsync(d_indir[0], d_indir[1], (size_t) rows * S_max * 4, cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
@@ -788,6 +815,7 @@ int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_length
   if (batch < 1 || batch > e->c.max_batch || seq < 1 || seq > e->c.max_input_len) return fail("batch / seq outside the engine limits");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
   e->B = batch; e->S_in = seq; e->steps_done = 0; e->launches = 0; e->ar_site = 0; e->last_step_fused = false;
+  e->beam_W = 1;
   const int M = batch * seq;
   // step state: the first generated token lands in column 0; every sequence of the padded batch sits at
   // position seq afterwards (sequence_length = max_input_len + step, generation.py:686-687)
@@ -803,6 +831,61 @@ int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_length
   return e->head(batch, e->hl, s);
 }
 
+// Beam search over the request tbrt_context just ran (generation.py:898-915: the context phase runs once per batch entry,
+// then the KV cache, lengths and logits are tiled beam_width times).  Afterwards the engine's rows are batch x beam_width:
+// tbrt_step advances all beams, tbrt_beam_finalize walks the parent pointers (gather_tree).
+int tbrt_beam_begin(tbrt_engine* e, int beam_width, float length_penalty, int end_id, tb_stream_t st) {
+  if (!e->finalized || e->B == 0 || e->steps_done != 0 || e->beam_W != 1) return fail("tbrt_beam_begin must follow tbrt_context");
+  if (beam_width < 2 || beam_width > 16) return fail("beam_width must be in [2, 16]");
+  const int Bq = e->B, W = beam_width, rows = Bq * W;
+  if (rows > e->c.max_batch) return fail("batch x beam_width exceeds the engine's max_batch (build with max_batch_size x max_beam_width rows)");
+  if (e->tpb) return fail("beam search reads the contiguous KV cache (paged_kv_cache engines: beam width 1)");
+  if (e->c.tp_size > 1 && rows > 8) return fail("tensor parallel decode handles at most 8 rows");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
+  if (!e->d_cum) {
+    const size_t mb = (size_t) e->c.max_batch;
+    if (e->alloc(e->d_cum, mb * 4) || e->alloc(e->d_fin, mb * 4) || e->alloc(e->d_beam_lens, mb * 4) ||
+        e->alloc(e->d_ids_t, mb * e->c.max_output_len * 4) || e->alloc(e->d_parent_t, mb * e->c.max_output_len * 4) ||
+        e->alloc(e->d_indir[0], mb * e->S_max * 4) || e->alloc(e->d_indir[1], mb * e->S_max * 4) ||
+        e->alloc(e->d_beam_out, mb * e->c.max_output_len * 4) || e->alloc(e->d_beam_ws, tb_beam_workspace_bytes((int) mb, 16)))
+      return -1;
+  }
+  // tile the cache rows: row b -> rows [b W, b W + W), highest entry first so no source row is overwritten before it is read
+  const size_t row_bytes = (size_t) 2 * e->Hl * e->S_max * e->c.head_size * (e->c.int8_kv ? 1 : 2);
+  for (int li = 0; li < e->c.layers; ++li) {
+    char* base = static_cast<char*>(e->kv[li]);
+    for (int b = Bq - 1; b >= 0; --b)
+      for (int w = W - 1; w >= 0; --w) {
+        const int dst = b * W + w;
+        if (dst == b) continue;
+        RT_CUDA(cudaMemcpyAsync(base + (size_t) dst * row_bytes, base + (size_t) b * row_bytes, row_bytes, cudaMemcpyDeviceToDevice, s));
+      }
+  }
+  RT_CALL(tb_tile_int(e->d_in_lens, Bq, W, s));
+  e->beam_W = W; e->beam_end_id = end_id; e->beam_length_penalty = length_penalty;
+  RT_CALL(tb_beam_init(e->d_cum, e->d_fin, e->d_beam_lens, e->d_indir[0], e->d_indir[1], e->d_max_in, rows, W, e->S_max, s));
+  // the context phase chose column 0 greedily; redo it as the first beam step on the same logits (every beam of an entry
+  // reads the entry's one logits row; cum_log_probs {0, -1e20, ...} make the W candidates come from that one distribution)
+  RT_CUDA(cudaMemsetAsync(e->d_step_pos, 0, 4, s));
+  RT_CALL(tb_fill_int(e->d_seq_lens, e->S_in - 1, rows, s));
+  if (e->beam_step(true, s)) return -1;
+  e->B = rows;
+  RT_CALL(tb_advance_step(e->d_next, e->d_ids, e->d_out_ids, e->d_seq_lens, e->d_step_pos, rows, e->c.max_output_len, s));
+  return 0;
+}
+
+// host_out [batch][beam_width][n_steps] (best beam first), cum_log_probs_out [batch][beam_width] or NULL
+int tbrt_beam_finalize(tbrt_engine* e, int32_t* host_out, float* cum_log_probs_out, int n_steps, tb_stream_t st) {
+  if (e->beam_W < 2) return fail("tbrt_beam_finalize without tbrt_beam_begin");
+  if (n_steps < 1 || n_steps > e->steps_done + 1) return fail("n_steps exceeds the steps run");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
+  RT_CALL(tb_gather_tree(e->d_beam_out, e->d_ids_t, e->d_parent_t, e->B, e->beam_W, n_steps, e->beam_end_id, s));
+  RT_CUDA(cudaMemcpyAsync(host_out, e->d_beam_out, (size_t) e->B * n_steps * 4, cudaMemcpyDeviceToHost, s));
+  if (cum_log_probs_out) RT_CUDA(cudaMemcpyAsync(cum_log_probs_out, e->d_cum, (size_t) e->B * 4, cudaMemcpyDeviceToHost, s));
+  RT_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
 int tbrt_step(tbrt_engine* e, tb_stream_t st) {
   if (!e->finalized || e->B == 0) return fail("tbrt_step before tbrt_context");
   if (e->S_in + e->steps_done + 1 >= e->S_max) return fail("KV cache is full");
@@ -815,11 +898,12 @@ int tbrt_step(tbrt_engine* e, tb_stream_t st) {
     return 0;
   }
   if (!e->c.use_cuda_graph) { e->launches = 0; return e->step_body(s); }
-  auto it = e->graphs.find(e->B);
+  const int gkey = e->B | (e->beam_W << 16);   // a beam-search step graph holds different kernels than a greedy one
+  auto it = e->graphs.find(gkey);
   if (it == e->graphs.end()) {
     // the first step at a batch size runs eagerly (plugins allocate their counters, kernels set their
     // attributes); the second is captured; every later one replays the graph
-    if (e->eager_steps[e->B]++ == 0) { e->launches = 0; return e->step_body(s); }
+    if (e->eager_steps[gkey]++ == 0) { e->launches = 0; return e->step_body(s); }
     // capture on a private stream (the caller's may be the legacy default stream, which cannot capture);
     // nothing executes during capture, the instantiated graph is then launched on the caller's stream
     cudaGraph_t g = nullptr;
@@ -835,11 +919,11 @@ int tbrt_step(tbrt_engine* e, tb_stream_t st) {
     cudaGraphExec_t ge = nullptr;
     RT_CUDA(cudaGraphInstantiate(&ge, g, 0));
     RT_CUDA(cudaGraphDestroy(g));
-    e->graphs[e->B] = ge;
-    e->graph_nodes[e->B] = (int64_t) nodes;
-    it = e->graphs.find(e->B);
+    e->graphs[gkey] = ge;
+    e->graph_nodes[gkey] = (int64_t) nodes;
+    it = e->graphs.find(gkey);
   }
-  e->launches = e->graph_nodes[e->B];
+  e->launches = e->graph_nodes[gkey];
   RT_CUDA(cudaGraphLaunch(it->second, s));
   return 0;
 }

@@ -271,3 +271,54 @@ def argmax(logits):
     out = torch.empty(logits.shape[:-1], dtype=torch.int32, device=logits.device)
     check(lib.tb_argmax(_p(out), _p(logits), rows, vocab, vocab, _stream()), "tb_argmax")
     return out
+
+
+def mmha_decode_beams(qkv, kv_cache, cache_indirection, past_len, *, num_heads, head_size, max_input_len, input_lengths=None,
+                      kv_scale_orig_quant=None, kv_scale_quant_orig=None, q_scaling=1.0, nsplit=0):
+    """GPTAttention plugin, generation phase with beam search: cache_indirection [batch, beam, S_max] int32 names, per cached
+    position, the beam whose cache row is read (T/tensorrt_llm/functional.py:2695-2928, input 7)."""
+    _chk_cuda(qkv, kv_cache, cache_indirection, input_lengths, kv_scale_orig_quant, kv_scale_quant_orig)
+    rows, S_max = qkv.shape[0], kv_cache.shape[3]
+    beam = cache_indirection.shape[1]
+    if nsplit <= 0:
+        nsplit = lib.tb_mmha_num_splits(rows, num_heads, past_len, 32)
+    out = torch.empty((rows, num_heads * head_size), dtype=torch.float16, device=qkv.device)
+    check(lib.tb_mmha_decode_beams(_p(out), _p(qkv), _p(kv_cache), _p(cache_indirection), beam, None, _p(input_lengths), None,
+                                   None, _p(kv_scale_orig_quant), _p(kv_scale_quant_orig), rows, num_heads, head_size, S_max,
+                                   int(past_len), int(max_input_len), int(past_len), head_size, float(q_scaling),
+                                   int(kv_cache.dtype == torch.int8), nsplit, _stream()), "tb_mmha_decode_beams")
+    return out
+
+
+class BeamSearchState:
+    """Device-resident decoder state of tb_beam_search_step (the beam half of DynamicDecodeOp)."""
+
+    def __init__(self, batch, beam_width, max_new, max_seq_len, max_input_len, device="cuda"):
+        rows = batch * beam_width
+        i32 = dict(dtype=torch.int32, device=device)
+        self.rows, self.W, self.S_max = rows, beam_width, max_seq_len
+        self.cum = torch.empty(rows, dtype=torch.float32, device=device)
+        self.finished, self.lens, self.next_ids = (torch.empty(rows, **i32) for _ in range(3))
+        self.ids_t, self.parent_t = (torch.zeros((max_new, rows), **i32) for _ in range(2))
+        self.indir = [torch.empty((batch, beam_width, max_seq_len), **i32) for _ in range(2)]
+        self.step = torch.zeros(1, **i32)
+        self.max_in = torch.full((1,), max_input_len, **i32)
+        self.ws = _workspace(lib.tb_beam_workspace_bytes(rows, beam_width), device)
+        check(lib.tb_beam_init(_p(self.cum), _p(self.finished), _p(self.lens), _p(self.indir[0]), _p(self.indir[1]),
+                               _p(self.max_in), rows, beam_width, max_seq_len, _stream()), "tb_beam_init")
+
+    def advance(self, logits, end_id, length_penalty=1.0, broadcast=False):
+        """logits fp32 [rows, V] ([batch, V] with broadcast) -> writes column ``step`` and the target indirection."""
+        check(lib.tb_beam_search_step(_p(logits), logits.shape[1], logits.stride(0), int(broadcast), self.rows, self.W,
+                                      float(length_penalty), int(end_id), _p(self.step), _p(self.max_in), _p(self.cum),
+                                      _p(self.finished), _p(self.lens), _p(self.ids_t), _p(self.parent_t), _p(self.next_ids),
+                                      _p(self.indir[0]), _p(self.indir[1]), self.S_max, _p(self.ws), _stream()),
+              "tb_beam_search_step")
+        self.indir[0].copy_(self.indir[1])
+        self.step += 1
+
+    def gather_tree(self, n, end_id):
+        out = torch.empty((self.rows, n), dtype=torch.int32, device=self.cum.device)
+        check(lib.tb_gather_tree(_p(out), _p(self.ids_t), _p(self.parent_t), self.rows, self.W, n, int(end_id), _stream()),
+              "tb_gather_tree")
+        return out

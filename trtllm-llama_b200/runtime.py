@@ -53,8 +53,9 @@ class ModelConfig:
 @dataclass
 class SamplingConfig:
     """generation.py:119-138.  top_k = 1 (default) is greedy; top_k > 1, top_p in (0, 1] and temperature select the
-    sampling kernel (tb_sample: top-k, top-p, top-k + top-p), seeded by ``random_seed``.  Beam search (num_beams > 1),
-    repetition / length penalties and min_length are not built and are rejected, not ignored."""
+    sampling kernel (tb_sample: top-k, top-p, top-k + top-p), seeded by ``random_seed``.  num_beams > 1 is beam search
+    (tbrt_beam_*; ``length_penalty`` normalises the beam scores as the reference's beam layer does).  Repetition penalty and
+    min_length are not built and are rejected, not ignored."""
     end_id: int = 2
     pad_id: int = 2
     num_beams: int = 1
@@ -225,10 +226,13 @@ class GenerationSession:
 
     def setup(self, batch_size, max_input_length, max_new_tokens, beam_width=1):
         """generation.py:413-488: fixes the shapes of the next decode (buffers were sized at engine build)."""
-        if beam_width != 1:
-            raise NotImplementedError("beam search is out of scope (SURVEY 8f-4)")
         mc = self.cfg
-        if batch_size > mc.max_batch_size or max_input_length > mc.max_input_len or max_new_tokens > mc.max_output_len:
+        if not 1 <= beam_width <= 16:
+            raise ValueError("beam_width must be in [1, 16]")
+        if beam_width > 1 and self.kv_cache_manager is not None:
+            raise NotImplementedError("beam search needs the contiguous KV cache (paged engines: beam width 1)")
+        self.beam_width = beam_width
+        if batch_size * beam_width > mc.max_batch_size or max_input_length > mc.max_input_len or max_new_tokens > mc.max_output_len:
             raise ValueError("setup() exceeds the limits the engine was built with")
         self.batch_size, self.max_input_len, self.max_new_tokens = batch_size, max_input_length, max_new_tokens
 
@@ -293,10 +297,10 @@ class GenerationSession:
         tensors (pinned for asynchronous copies); returns HOST output ids [B, max_new_tokens] — the host<->device
         copies are part of the call, as in the reference's run.py timing (LQ/run.py:117-198)."""
         sc = sampling_config or SamplingConfig()
+        if sc.repetition_penalty != 1.0 or sc.min_length > 1 or (sc.num_beams == 1 and sc.length_penalty != 1.0):
+            raise NotImplementedError("repetition_penalty / min_length (and length_penalty without beams) are not built (SURVEY 8f-4)")
         if sc.num_beams != 1:
-            raise NotImplementedError("beam search (num_beams > 1) is not built (SURVEY 8f-4)")
-        if sc.repetition_penalty != 1.0 or sc.length_penalty != 1.0 or sc.min_length > 1:
-            raise NotImplementedError("repetition_penalty / length_penalty / min_length are not built (SURVEY 8f-4)")
+            return self._decode_beams(input_ids, input_lengths, sc, max_new_tokens or self.max_new_tokens, out)
         if lib.tbrt_set_sampling(self._e, int(sc.top_k), float(sc.top_p), float(sc.temperature), int(sc.random_seed)):
             raise _err("tbrt_set_sampling")
         B, S = input_ids.shape
@@ -326,6 +330,37 @@ class GenerationSession:
             raise _err("tbrt_generate")
         self._B = B
         self.last_steps = lib.tbrt_last_steps(self._e)
+        return out
+
+    def _decode_beams(self, input_ids, input_lengths, sc, n, out):
+        """generation.py:365-409,823-997 with num_beams > 1: the context phase runs once per batch entry, the engine tiles the
+        cache beam_width times and every later step advances all beams; returns HOST ids [B, num_beams, n], best beam first
+        (``self.cum_log_probs`` [B, num_beams] holds the final scores)."""
+        B, S = input_ids.shape
+        W = int(sc.num_beams)
+        if sc.top_k != 1 or sc.top_p != 0.0:
+            raise NotImplementedError("beam search does not combine with top-k / top-p sampling (as in the reference's decoder)")
+        if self.kv_cache_manager is not None:
+            raise NotImplementedError("beam search needs the contiguous KV cache (paged engines: beam width 1)")
+        if input_ids.is_cuda or input_ids.dtype != torch.int32 or not input_ids.is_contiguous():
+            raise ValueError("decode() takes contiguous host int32 input_ids")
+        if out is None:
+            out = torch.empty((B, W, n), dtype=torch.int32, pin_memory=True)
+        if lib.tbrt_set_sampling(self._e, 1, 0.0, 1.0, 0):
+            raise _err("tbrt_set_sampling")
+        self.context(input_ids, input_lengths.to(dtype=torch.int32))
+        end_id = int(sc.end_id) if sc.end_id is not None else -1
+        if lib.tbrt_beam_begin(self._e, W, float(sc.length_penalty), end_id, self._stream()):
+            raise _err("tbrt_beam_begin")
+        self._B = B * W
+        for _ in range(n - 1):
+            if lib.tbrt_step(self._e, self._stream()):
+                raise _err("tbrt_step")
+        cum = torch.empty((B, W), dtype=torch.float32, pin_memory=True)
+        if lib.tbrt_beam_finalize(self._e, out.data_ptr(), cum.data_ptr(), n, self._stream()):
+            raise _err("tbrt_beam_finalize")
+        self.cum_log_probs = cum
+        self.last_steps = n
         return out
 
 
