@@ -166,7 +166,12 @@ int tb_finished(int* all_done, int* out_ids, int batch, int out_stride, int n_do
                 tb_stream_t s);
 int tb_half_to_float(float* out, const void* in, int64_t n, tb_stream_t s);
 int tb_fill_int(int* p, int value, int n, tb_stream_t s);
-int tb_tile_int(int* p, int n, int w, tb_stream_t s); /* in place p[i*w + j] = p[i]; n*w <= 1024 (_tile_beam_width) */
+int tb_tile_int(int* p, int n, int w, tb_stream_t s);
+/* packed <-> padded token rows (GPTAttention remove_input_padding, gptAttentionCommon.cpp:467-478): sequence b owns packed
+ * rows [sum(lens[:b]), + lens[b]) and padded rows [b * seq, b * seq + lens[b]); lens is a DEVICE array; unpack zero-fills the
+ * padded tail rows.  row_bytes: a multiple of 16. */
+int tb_unpack_rows(void* padded, const void* packed, const int* lens, int batch, int seq, int row_bytes, tb_stream_t s);
+int tb_pack_rows(void* packed, const void* padded, const int* lens, int batch, int seq, int row_bytes, tb_stream_t s); /* in place p[i*w + j] = p[i]; n*w <= 1024 (_tile_beam_width) */
 int tb_copy(void* dst, const void* src, size_t bytes, tb_stream_t s); /* device-to-device */
 /* in [tp, rows, vocab_local] fp16 (all-gathered vocab-parallel lm_head) -> out [rows, tp*vocab_local] fp32 */
 int tb_gather_logits(float* out, const void* in, int rows, int vocab_local, int tp, tb_stream_t s);

@@ -265,3 +265,134 @@ def test_gpt_attention_plugin_context_then_generation(L, int8_kv):
         assert d.max() <= 1 and (d != 0).mean() < 1e-2
     else:
         np.testing.assert_allclose(kv.astype(np.float32), cache_ref.astype(np.float32), atol=4e-3)
+
+
+def _attention_fields(H, Dh, int8_kv, remove_padding, ifb, paged=0):
+    return [("num_heads", H, "i32"), ("head_size", Dh, "i32"), ("unidirectional", 1, "i32"), ("q_scaling", 1.0, "f32"),
+            ("rotary_embedding_dim", Dh, "i32"), ("neox_rotary_style", 1, "i8"), ("context_fmha_type", 0, "i8"),
+            ("multi_block_mode", 0, "i8"), ("multi_query_mode", 0, "i8"), ("int8_kv_cache", int(int8_kv), "i32"),
+            ("fp8_kv_cache", 0, "i32"), ("remove_input_padding", int(remove_padding), "i8"), ("mask_type", 1, "i32"),
+            ("paged_kv_cache", paged, "i32"), ("type_id", 1, "i32"), ("in_flight_batching", int(ifb), "i32")]
+
+
+def _enqueue(L, p, ins, outs):
+    """enqueue with caller-owned outputs (the KV cache is aliased); host tensors are passed by their host address"""
+    n_in = len(ins)
+    idesc, odesc = p._descs(ins), p._descs(outs)
+    ws = torch.empty(max(L.tbp_workspace_size(p.h, idesc, n_in, odesc, len(outs)), 16), dtype=torch.uint8, device="cuda")
+    ws.fill_(0xAB)
+    in_ptrs = (C.c_void_p * n_in)(*[t.data_ptr() for t in ins])
+    out_ptrs = (C.c_void_p * len(outs))(*[t.data_ptr() for t in outs])
+    assert L.tbp_enqueue(p.h, idesc, odesc, in_ptrs, out_ptrs, ws.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("int8_kv", [True, False])
+def test_gpt_attention_plugin_packed_input(L, int8_kv):
+    """remove_input_padding (LQ/build.py --remove_input_padding; gptAttentionCommon.cpp:467-478): the context input is
+    [1, num_tokens, 3*hidden] with the sequences back to back; same results as the padded protocol, same cache."""
+    rng = np.random.default_rng(45)
+    B, H, Dh, S, S_max, steps = 3, 4, 128, 20, 48, 3
+    hidden = H * Dh
+    in_lens = np.array([S, 7, 13], np.int32)
+    T = int(in_lens.sum())
+    p = Plugin(L, "GPTAttention", _attention_fields(H, Dh, int8_kv, True, False)).roundtrip()
+    kv_np = np.int8 if int8_kv else np.float16
+    cache = torch.zeros((B, 2, H, S_max, Dh), dtype=torch.int8 if int8_kv else torch.float16, device="cuda")
+    cache_ref = np.zeros((B, 2, H, S_max, Dh), kv_np)
+    s_q, s_dq = (np.float32(127.0 / 3.0), np.float32(3.0 / 127.0)) if int8_kv else (None, None)
+    scales = [dev(np.array([s_q], np.float32)), dev(np.array([s_dq], np.float32))] if int8_kv else []
+    masked = np.zeros((B, S_max), np.int32)
+    for b in range(B):
+        masked[b, in_lens[b]:S] = 1
+    fixed = [dev(masked), dev(in_lens), torch.zeros(S, dtype=torch.int32, device="cuda"),
+             torch.zeros((B, 1, S_max), dtype=torch.int32, device="cuda")]
+
+    padded = (rng.standard_normal((B, S, 3 * hidden)) * 0.5).astype(np.float16)
+    packed = np.concatenate([padded[b, :in_lens[b]] for b in range(B)])[None]
+    out = torch.zeros((1, T, hidden), dtype=torch.float16, device="cuda")
+    _enqueue(L, p, [dev(packed), cache, torch.full((B,), S, dtype=torch.int32, device="cuda"),
+                    torch.tensor([0, 1], dtype=torch.int32)] + fixed + scales, [out, cache])
+    ref = R.context_attention(padded, cache_ref, in_lens, num_heads=H, head_size=Dh, kv_scale_orig_quant=s_q)
+    ref_packed = np.concatenate([ref[b, :in_lens[b]] for b in range(B)])
+    np.testing.assert_allclose(out[0].cpu().numpy().astype(np.float32), ref_packed.astype(np.float32), atol=5e-3)
+    for step in range(steps):                        # generation: [1, B, 3*hidden], one token per sequence
+        qkv = (rng.standard_normal((1, B, 3 * hidden)) * 0.5).astype(np.float16)
+        past = S + step
+        o = torch.zeros((1, B, hidden), dtype=torch.float16, device="cuda")
+        _enqueue(L, p, [dev(qkv), cache, torch.full((B,), past, dtype=torch.int32, device="cuda"),
+                        torch.tensor([past, 0], dtype=torch.int32)] + fixed + scales, [o, cache])
+        want = R.mmha_decode(qkv[0], cache_ref, past, in_lens, S, num_heads=H, head_size=Dh, kv_scale_orig_quant=s_q,
+                             kv_scale_quant_orig=s_dq)
+        tol = 2e-3 * max(1.0, float(np.abs(want.astype(np.float32)).max()))
+        np.testing.assert_allclose(o[0].cpu().numpy().astype(np.float32), want.astype(np.float32), atol=tol, err_msg=f"step {step}")
+
+
+@pytest.mark.parametrize("int8_kv", [True, False])
+def test_gpt_attention_plugin_in_flight_batching(L, int8_kv):
+    """in_flight_batching (gptAttentionPlugin.cpp:150-200): one enqueue carries requests in different phases — two that are
+    generating, an idle slot, and two arriving with their prompts — told apart by the HOST tensors host_input_lengths /
+    host_request_types; each group runs on its slice of the packed tokens and of the cache.  Every request must get exactly
+    what it gets when it is served alone through the padded protocol."""
+    rng = np.random.default_rng(46)
+    H, Dh, S_max, max_in = 4, 128, 64, 24
+    hidden = H * Dh
+    p = Plugin(L, "GPTAttention", _attention_fields(H, Dh, int8_kv, True, True)).roundtrip()
+    kv_t = torch.int8 if int8_kv else torch.float16
+    s_q, s_dq = (np.float32(127.0 / 3.0), np.float32(3.0 / 127.0)) if int8_kv else (None, None)
+    scales = [dev(np.array([s_q], np.float32)), dev(np.array([s_dq], np.float32))] if int8_kv else []
+    nseq = 5
+    cache = torch.zeros((nseq, 2, H, S_max, Dh), dtype=kv_t, device="cuda")
+    ref_cache = np.zeros((nseq, 2, H, S_max, Dh), np.int8 if int8_kv else np.float16)
+
+    def ctx_ref(slot, qkv):
+        c = ref_cache[slot:slot + 1]
+        o = R.context_attention(qkv[None], c, np.array([qkv.shape[0]], np.int32), num_heads=H, head_size=Dh, kv_scale_orig_quant=s_q)
+        return o[0]
+
+    def gen_ref(slot, qkv, past):
+        c = ref_cache[slot:slot + 1]
+        return R.mmha_decode(qkv[None], c, past, np.array([past], np.int32), past, num_heads=H, head_size=Dh,
+                             kv_scale_orig_quant=s_q, kv_scale_quant_orig=s_dq)[0]
+
+    def enqueue(types, host_lens, seq_lens, tokens):
+        ins = [dev(tokens[None]), cache, dev(np.asarray(seq_lens, np.int32)), torch.tensor([0, 0], dtype=torch.int32),
+               torch.zeros((nseq, S_max), dtype=torch.int32, device="cuda"), dev(np.asarray(host_lens, np.int32)),
+               torch.zeros(max_in, dtype=torch.int32, device="cuda"), torch.zeros((nseq, 1, S_max), dtype=torch.int32, device="cuda")]
+        ins += scales + [torch.tensor(host_lens, dtype=torch.int32), torch.tensor(types, dtype=torch.int32)]
+        out = torch.zeros((1, tokens.shape[0], hidden), dtype=torch.float16, device="cuda")
+        _enqueue(L, p, ins, [out, cache])
+        return out[0].cpu().numpy()
+
+    def close(got, want, what):
+        tol = 5e-3 * max(1.0, float(np.abs(want.astype(np.float32)).max()))
+        np.testing.assert_allclose(got.astype(np.float32), want.astype(np.float32), atol=tol, err_msg=what)
+
+    q = lambda n: (rng.standard_normal((n, 3 * hidden)) * 0.5).astype(np.float16)  # noqa: E731
+    # round 1: slots 0 and 1 arrive (context), the others are idle
+    l0, l1 = 17, 9
+    t0, t1 = q(l0), q(l1)
+    got = enqueue([0, 0, 2, 2, 2], [l0, l1, 0, 0, 0], [l0, l1, 0, 0, 0], np.concatenate([t0, t1]))
+    close(got[:l0], ctx_ref(0, t0), "slot 0 context")
+    close(got[l0:], ctx_ref(1, t1), "slot 1 context")
+    # round 2: slots 0, 1 generate; slot 2 idle; slots 3, 4 arrive — one enqueue, three groups
+    l3, l4 = 24, 5
+    g0, g1, t3, t4 = q(1), q(1), q(l3), q(l4)
+    got = enqueue([1, 1, 2, 0, 0], [1, 1, 0, l3, l4], [l0, l1, 0, l3, l4], np.concatenate([g0, g1, t3, t4]))
+    close(got[0], gen_ref(0, g0[0], l0), "slot 0 generation")
+    close(got[1], gen_ref(1, g1[0], l1), "slot 1 generation")
+    close(got[2:2 + l3], ctx_ref(3, t3), "slot 3 context")
+    close(got[2 + l3:], ctx_ref(4, t4), "slot 4 context")
+    # round 3: everybody generates at their own position
+    lens = [l0 + 1, l1 + 1, 0, l3, l4]
+    toks = [q(1) for _ in range(4)]
+    got = enqueue([1, 1, 2, 1, 1], [1, 1, 0, 1, 1], lens, np.concatenate(toks))
+    for k, slot in enumerate([0, 1, 3, 4]):
+        close(got[k], gen_ref(slot, toks[k][0], lens[slot]), f"slot {slot} generation, round 3")
+    kv = cache.cpu().numpy()
+    if int8_kv:
+        d = np.abs(kv.astype(np.int32) - ref_cache.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).mean() < 1e-2
+    else:
+        np.testing.assert_allclose(kv.astype(np.float32), ref_cache.astype(np.float32), atol=4e-3)
+    assert np.all(kv[2] == 0)                          # the idle slot's cache is untouched

@@ -59,6 +59,8 @@ SIGNATURES = {
     "tb_half_to_float": (i32, [vp, vp, i64, vp]),
     "tb_fill_int": (i32, [vp, i32, i32, vp]),
     "tb_tile_int": (i32, [vp, i32, i32, vp]),
+    "tb_unpack_rows": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "tb_pack_rows": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "tb_mmha_decode_beams": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32,
                                    i32, i32, vp]),
     "tb_beam_workspace_bytes": (sz, [i32, i32]),

@@ -168,6 +168,27 @@ __global__ void half_to_float_kernel(float* out, const __half* in, int64_t n) {
     out[i] = __half2float(in[i]);
 }
 
+// packed <-> padded token rows (remove_input_padding): sequence b owns packed rows [sum(lens[:b]), +lens[b]) and padded rows
+// [b * S, b * S + lens[b]); padded tail rows are zero-filled.  One CTA per (s, b); the prefix sum is a warp loop (B is small).
+__global__ void pack_rows_kernel(uint4* dst, const uint4* src, const int* lens, int S, int row16, int to_packed) {
+  __shared__ int off_s;
+  const int s = blockIdx.x, b = blockIdx.y, len = lens[b];
+  if (threadIdx.x < 32) {
+    int a = 0;
+    for (int j = threadIdx.x; j < b; j += 32) a += lens[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) off_s = a;
+  }
+  __syncthreads();
+  const size_t packed = (size_t) (off_s + s) * row16, padded = ((size_t) b * S + s) * row16;
+  if (to_packed) {
+    if (s < len)
+      for (int i = threadIdx.x; i < row16; i += blockDim.x) dst[packed + i] = src[padded + i];
+  } else {
+    for (int i = threadIdx.x; i < row16; i += blockDim.x) dst[padded + i] = s < len ? src[packed + i] : make_uint4(0, 0, 0, 0);
+  }
+}
 __global__ void tile_int_kernel(int* p, int n, int w) {
   const int t = threadIdx.x;
   const int v = t < n * w ? p[t / w] : 0;
@@ -255,6 +276,17 @@ int tb_copy(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 
 int tb_fill_int(int* p, int value, int n, cudaStream_t s) {
   fill_int_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, value, n);
+  return (int) cudaGetLastError();
+}
+
+int tb_unpack_rows(void* padded, const void* packed, const int* lens, int batch, int seq, int row_bytes, cudaStream_t s) {
+  if (batch < 1 || seq < 1 || row_bytes < 16 || (row_bytes & 15)) return -1;
+  pack_rows_kernel<<<dim3(seq, batch), 128, 0, s>>>((uint4*) padded, (const uint4*) packed, lens, seq, row_bytes / 16, 0);
+  return (int) cudaGetLastError();
+}
+int tb_pack_rows(void* packed, const void* padded, const int* lens, int batch, int seq, int row_bytes, cudaStream_t s) {
+  if (batch < 1 || seq < 1 || row_bytes < 16 || (row_bytes & 15)) return -1;
+  pack_rows_kernel<<<dim3(seq, batch), 128, 0, s>>>((uint4*) packed, (const uint4*) padded, lens, seq, row_bytes / 16, 1);
   return (int) cudaGetLastError();
 }
 

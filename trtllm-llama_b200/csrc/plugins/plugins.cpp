@@ -3,6 +3,7 @@
 // ("tensorrt_llm"), field names, input order, output shapes/types and serialisation order follow the
 // reference plugin of the same name (cited per class) so an engine builder that looks these creators up
 // finds drop-in replacements.  Fields marked [ext] are additions (absent => reference behaviour).
+#include <cuda_fp16.h>
 #include <cmath>
 
 #include "pluginBase.h"
@@ -30,6 +31,9 @@ bool linear(const PluginTensorDesc& d, DataType t) { return d.type == t && d.for
 //         7 cache_indirection [B,beam,S_max]  (8 kv_orig_quant_scale [1], 9 kv_quant_orig_scale [1] iff int8 KV)
 //         (next: block_pointers [B,beam,2,2*max_blocks] int32 view of int64 addresses iff paged_kv_cache — then input 1 is
 //          the block pool [blocks,2,H,tokens_per_block,Dh]; P/gptAttentionPlugin/gptAttentionPlugin.cpp:204-235)
+//         (last two iff in_flight_batching: host_input_lengths [B] int32 HOST, host_request_types [B] int32 HOST —
+//          0 context, 1 generation, 2 none; gptAttentionPlugin.h:106-170)
+//         remove_input_padding: input 0 is [1, num_tokens, 3*H*Dh], sequences packed back to back, output 0 likewise
 // outputs 0 context [B,S,H*Dh]   1 present_key_value (same buffer as input 1: updated in place)
 // =====================================================================================================
 class GPTAttentionPlugin : public BasePlugin {
@@ -105,18 +109,26 @@ class GPTAttentionPlugin : public BasePlugin {
     if (pos >= 2 && pos <= 7) return linear(io[pos], DataType::kINT32);
     if (int8_kv_ && (pos == 8 || pos == 9)) return linear(io[pos], DataType::kFLOAT);
     if (paged_kv_ && pos == (int8_kv_ ? 10 : 8)) return linear(io[pos], DataType::kINT32);
+    if (ifb_ && (pos == nb_in - 2 || pos == nb_in - 1)) return linear(io[pos], DataType::kINT32);
     if (int8_kv_ && (pos == 1 || pos == nb_in + 1)) return linear(io[pos], DataType::kINT8);
     return linear(io[pos], (DataType) type_);
   }
   size_t getWorkspaceSize(const PluginTensorDesc* in, int32_t, const PluginTensorDesc*, int32_t) const noexcept override {
     // generation: split-L partials.  context: V^T for the tcgen05 kernel, 2 * B*S*hidden bytes (the reference sizes
     // ~6.4 GB of score buffers here, gptAttentionCommon.cpp:267-305).
+    if (remove_padding_) {   // packed input: padded staging copies of qkv and of the output, then the padded kernels' own
+      const size_t nseq = in[5].dims.d[0], max_in = in[6].dims.d[0], hid = (size_t) num_heads_ * head_size_;
+      return align128(nseq * max_in * 3 * hid * 2) + align128(nseq * max_in * hid * 2) +
+             align128(tb_context_attention_workspace_bytes((int) nseq, (int) max_in, num_heads_)) +
+             align128(tb_mmha_workspace_bytes((int) nseq, num_heads_, kMaxSplits));
+    }
     const size_t gen = tb_mmha_workspace_bytes(in[0].dims.d[0], num_heads_, kMaxSplits);
     const size_t ctx = tb_context_attention_workspace_bytes(in[0].dims.d[0], in[0].dims.d[1], num_heads_);
     return align128(gen > ctx ? gen : ctx);
   }
   int32_t enqueue(const PluginTensorDesc* id, const PluginTensorDesc*, const void* const* in, void* const* out,
                   void* workspace, cudaStream_t stream) noexcept override {
+    if (remove_padding_) return enqueue_packed(id, nb_inputs(), in, out, workspace, stream);
     return guarded("GPTAttention::enqueue", [&]() -> int {
       const int B = id[0].dims.d[0], S = id[0].dims.d[1];
       const int max_in = id[6].dims.d[0];
@@ -179,14 +191,104 @@ class GPTAttentionPlugin : public BasePlugin {
   }
 
  private:
+  int nb_inputs() const { return 8 + (int8_kv_ ? 2 : 0) + (paged_kv_ ? 1 : 0) + (ifb_ ? 2 : 0); }
+
+  // remove_input_padding (+ in_flight_batching): P/gptAttentionPlugin/gptAttentionPlugin.cpp:150-200 enqueueImpl groups
+  // consecutive requests of one type and runs each group (:202-372 enqueueSome) on its slice of the packed tokens, the
+  // sequence-indexed inputs and the cache.  A context group is staged into the padded layout the tcgen05 prefill kernel
+  // consumes (tb_unpack_rows), attended, and packed back; a generation group is one token per sequence already.
+  int32_t enqueue_packed(const PluginTensorDesc* id, int nb_in, const void* const* in, void* const* out, void* workspace,
+                         cudaStream_t stream) noexcept {
+    return guarded("GPTAttention::enqueue (packed)", [&]() -> int {
+      const int nseq = id[5].dims.d[0], max_in = id[6].dims.d[0];
+      const int hid = num_heads_ * head_size_;
+      const int bp_idx = int8_kv_ ? 10 : 8;
+      const int tpb = paged_kv_ ? id[1].dims.d[3] : 0;
+      const int max_blocks = paged_kv_ ? id[bp_idx].dims.d[id[bp_idx].dims.nbDims - 1] / 2 : 0;
+      const int S_max = paged_kv_ ? tpb * max_blocks : id[1].dims.d[3];
+      const int* host_len = static_cast<const int*>(in[3]);
+      TBP_REQUIRE(host_len != nullptr, "past_key_value_length must be a host tensor");
+      const float* s_oq = int8_kv_ ? static_cast<const float*>(in[8]) : nullptr;
+      const float* s_qo = int8_kv_ ? static_cast<const float*>(in[9]) : nullptr;
+      char* cache = static_cast<char*>(out[1] ? out[1] : const_cast<void*>(in[1]));
+      const size_t seq_stride = paged_kv_ ? 0 : (size_t) 2 * num_heads_ * S_max * head_size_ * (int8_kv_ ? 1 : 2);
+      const __half* x = static_cast<const __half*>(in[0]);
+      __half* y = static_cast<__half*>(out[0]);
+      const int* seq_lens = static_cast<const int*>(in[2]);
+      const int* in_lens = static_cast<const int*>(in[5]);
+      const int64_t* block_ptrs = paged_kv_ ? static_cast<const int64_t*>(in[bp_idx]) : nullptr;
+      char* ws = static_cast<char*>(workspace);
+      __half* pad_qkv = reinterpret_cast<__half*>(ws);
+      __half* pad_out = reinterpret_cast<__half*>(ws + align128((size_t) nseq * max_in * 3 * hid * 2));
+      void* sub_ws = reinterpret_cast<char*>(pad_out) + align128((size_t) nseq * max_in * hid * 2);
+
+      auto some = [&](int seq0, int n, int tok0, bool is_context, int S) -> int {
+        const int64_t* bp = block_ptrs ? block_ptrs + (size_t) seq0 * 2 * max_blocks : nullptr;
+        if (is_context) {
+          if (int rc = tb_unpack_rows(pad_qkv, x + (size_t) tok0 * 3 * hid, in_lens + seq0, n, S, 3 * hid * 2, stream)) return rc;
+          int rc = paged_kv_ ? tb_context_attention_paged(pad_out, pad_qkv, bp, tpb, max_blocks, in_lens + seq0, s_oq, sub_ws, n, S,
+                                                          num_heads_, head_size_, rotary_dim_, q_scaling_, int8_kv_, stream)
+                             : tb_context_attention(pad_out, pad_qkv, cache + seq0 * seq_stride, in_lens + seq0, s_oq, sub_ws, n, S,
+                                                    num_heads_, head_size_, S_max, rotary_dim_, q_scaling_, int8_kv_, stream);
+          if (rc) return rc;
+          return tb_pack_rows(y + (size_t) tok0 * hid, pad_out, in_lens + seq0, n, S, hid * 2, stream);
+        }
+        // generation: per-request lengths on the device.  In-flight batching has no padded batch: every request sits at its own
+        // position and nothing is masked (the reference passes input_seq_length = 1, gptAttentionPlugin.cpp:287-290)
+        const bool own_len = ifb_ || device_lengths_;
+        const int cap = own_len ? S_max - 1 : host_len[0];
+        const int nsplit = tb_mmha_num_splits(n, num_heads_, cap, kMaxSplits);
+        const int* lens_arg = ifb_ ? nullptr : in_lens + seq0;
+        const int* mask_arg = (ifb_ || !in[4]) ? nullptr : static_cast<const int*>(in[4]) + (size_t) seq0 * S_max;
+        const int* max_in_dev = (!ifb_ && device_lengths_) ? static_cast<const int*>(in[6]) : nullptr;
+        if (paged_kv_)
+          return tb_mmha_decode_paged(y + (size_t) tok0 * hid, x + (size_t) tok0 * 3 * hid, bp, tpb, max_blocks, seq_lens + seq0,
+                                      lens_arg, mask_arg, max_in_dev, s_oq, s_qo, n, num_heads_, head_size_, own_len ? 0 : host_len[0],
+                                      ifb_ ? 1 : max_in, cap, rotary_dim_, q_scaling_, int8_kv_, nsplit, stream);
+        return tb_mmha_decode_dev(y + (size_t) tok0 * hid, x + (size_t) tok0 * 3 * hid, cache + seq0 * seq_stride, seq_lens + seq0,
+                                  lens_arg, mask_arg, max_in_dev, s_oq, s_qo, sub_ws, nullptr, n, num_heads_, head_size_, S_max,
+                                  own_len ? 0 : host_len[0], ifb_ ? 1 : max_in, cap, rotary_dim_, q_scaling_, int8_kv_, nsplit,
+                                  stream);
+      };
+
+      if (!ifb_) return some(0, nseq, 0, host_len[1] != 0, max_in);
+      const int* host_in_lens = static_cast<const int*>(in[nb_in - 2]);      // HOST
+      const int* req_types = static_cast<const int*>(in[nb_in - 1]);         // HOST: 0 context, 1 generation, 2 none
+      TBP_REQUIRE(host_in_lens && req_types, "in_flight_batching needs host_input_lengths and host_request_types");
+      TBP_REQUIRE(!in[7] || id[7].dims.nbDims < 3 || id[7].dims.d[1] == 1, "in-flight batching: beam width 1 only");
+      int seq0 = 0, tok0 = 0, tok1 = 0, ref = req_types[0];
+      for (int i = 0; i <= nseq; ++i) {
+        if (i < nseq && req_types[i] == ref) {
+          tok1 += host_in_lens[i];
+          continue;
+        }
+        if (ref != 2) {
+          TBP_REQUIRE(ref == 0 || ref == 1, "host_request_types holds 0 (context), 1 (generation) or 2 (none)");
+          int S = 1;
+          if (ref == 0)
+            for (int j = seq0; j < i; ++j) S = host_in_lens[j] > S ? host_in_lens[j] : S;
+          TBP_REQUIRE(S <= max_in, "a context request is longer than max_input_length");
+          if (int rc = some(seq0, i - seq0, tok0, ref == 0, S)) return rc;
+        }
+        if (i < nseq) {
+          seq0 = i;
+          ref = req_types[i];
+          tok0 = tok1;
+          tok1 += host_in_lens[i];
+        }
+      }
+      return 0;
+    });
+  }
+
   static constexpr int kMaxSplits = 32;
   void validate() const {
     TBP_REQUIRE(head_size_ == 128, "only head_size 128 (LLaMA-7B) is built");
     TBP_REQUIRE(rotary_dim_ == 0 || rotary_dim_ == head_size_, "rotary_embedding_dim must be 0 or head_size");
     TBP_REQUIRE(rotary_dim_ == 0 || neox_, "only neox-style rotary embedding is built");
     TBP_REQUIRE(is_half(type_), "only type_id = half is built");
-    TBP_REQUIRE(!multi_query_ && !fp8_kv_ && !ifb_ && !remove_padding_,
-                "multi-query / fp8 KV / in-flight batching / packed input are out of scope (SURVEY 8f)");
+    TBP_REQUIRE(!multi_query_ && !fp8_kv_, "multi-query / fp8 KV are out of scope (SURVEY 8f)");
+    TBP_REQUIRE(!ifb_ || remove_padding_, "in_flight_batching needs remove_input_padding (gptAttentionPlugin.cpp:285)");
     TBP_REQUIRE(unidirectional_ == 1, "causal attention only");
   }
   int32_t num_heads_ = 0, head_size_ = 0, unidirectional_ = 1, rotary_dim_ = 0, context_fmha_ = 0, mask_type_ = 1;
