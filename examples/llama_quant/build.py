@@ -53,8 +53,8 @@ def parse_arguments():
     args = p.parse_args()
     if args.dtype != 'float16':
         p.error("only --dtype float16 is built on this path")
-    if args.n_kv_head not in (None, args.n_head) or args.remove_input_padding:
-        p.error("multi-query attention and packed input are out of scope (DESIGN.md)")
+    if args.n_kv_head not in (None, args.n_head):
+        p.error("multi-query attention is out of scope (DESIGN.md)")
     if not 1 <= args.max_beam_width <= 16:
         p.error("--max_beam_width must be in [1, 16]")
     if args.max_beam_width > 1 and args.paged_kv_cache:
@@ -76,7 +76,8 @@ def main():
                      inter_size=args.inter_size, quant_mode=qm,
                      max_batch_size=args.max_batch_size * args.max_beam_width,     # rows = batch entries x beams
                      max_input_len=args.max_input_len, max_output_len=args.max_output_len, tp_size=args.world_size,
-                     paged_kv_cache=args.paged_kv_cache, tokens_per_block=args.tokens_per_block)
+                     paged_kv_cache=args.paged_kv_cache, tokens_per_block=args.tokens_per_block,
+                     remove_input_padding=args.remove_input_padding)
     dev = "cuda" if torch.cuda.is_available() else "cpu"       # quantisation is build-time work; a GPU only makes it fast
     weights = (B.load_from_ft_llama(args.model_dir, mc, dev) if args.model_dir
                else B.random_llama_weights(mc, seed=args.random_seed or 0, device=dev))
@@ -92,7 +93,7 @@ def main():
                                  "weight_only_quant_matmul_plugin": "float16" if args.use_weight_only else False,
                                  "rmsnorm_quantization_plugin": "float16" if args.use_smooth_quant else False,
                                  "nccl_plugin": "float16" if args.world_size > 1 else False,
-                                 "remove_input_padding": False, "paged_kv_cache": bool(args.paged_kv_cache),
+                                 "remove_input_padding": bool(args.remove_input_padding), "paged_kv_cache": bool(args.paged_kv_cache),
                                  "tokens_per_block": args.tokens_per_block})
     print(f"Total time of building all {args.world_size} engines: {time.strftime('%H:%M:%S', time.gmtime(time.time() - tik))}")
 

@@ -156,6 +156,8 @@ int tb_swiglu_quant(int8_t* dst, float* scales, const void* gate, const void* up
 int tb_add(void* out, const void* a, const void* b, int64_t n, tb_stream_t s);
 int tb_gather_last_token(void* out, const void* in, const int* last_ids, int batch, int seq, int hidden,
                          tb_stream_t s);
+/* the same for packed rows (remove_input_padding): in [sum(lens), hidden], sequence b ends at row sum(lens[:b+1]) - 1 */
+int tb_gather_last_token_packed(void* out, const void* in, const int* lens, int batch, int hidden, tb_stream_t s);
 int tb_argmax(int* out, const float* logits, int rows, int vocab, int vocab_stride, tb_stream_t s);
 int tb_advance_step(const int* new_ids, int* input_ids, int* output_ids, int* seq_lens, int* step_pos, int batch,
                     int out_stride, tb_stream_t s);

@@ -59,6 +59,11 @@ size_t tbrt_device_bytes(const tbrt_engine* e);
 /* Context phase over a padded batch: ids [B,S] int32 and input_lengths [B] are DEVICE pointers. */
 int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_lengths, int batch, int seq, tb_stream_t s);
 /* One generation step for every sequence (token ids come from the previous step's argmax). */
+/* tbrt_context on packed input (build.py --remove_input_padding; generation.py:355-363): device ids [tokens] = the prompts
+ * back to back, device input_lengths [batch], seq = the longest prompt.  The projections run on `tokens` rows instead of
+ * batch x seq; cache layout and generation steps are those of the padded batch. */
+int tbrt_context_packed(tbrt_engine* e, const int32_t* ids, const int32_t* input_lengths, int batch, int tokens, int seq,
+                        tb_stream_t s);
 int tbrt_step(tbrt_engine* e, tb_stream_t s);
 /* fp32 logits [B, vocab] of the last context/step call (device pointer). */
 const float* tbrt_logits(const tbrt_engine* e);

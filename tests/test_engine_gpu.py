@@ -168,3 +168,39 @@ def test_graph_replay_survives_a_change_of_prompt_length_and_batch():
             a = sg.decode(host(ids), host(lens)).numpy().copy()
             b = se.decode(host(ids), host(lens)).numpy().copy()
             assert np.array_equal(a, b), f"{mode}: graph replay differs from eager at B={B}, S={S}"
+
+
+@pytest.mark.parametrize("mode,int8_kv", [("fp16", False), ("w8", True), ("sq", True)])
+def test_packed_input_equals_the_padded_batch(mode, int8_kv):
+    """remove_input_padding (LQ/build.py --remove_input_padding, generation.py:355-363): the context phase runs on the real
+    tokens only; logits, greedy ids and the KV cache must equal the padded run's (the SmoothQuant per-token scales and every
+    row-wise op see the same rows; only the padding rows are gone)."""
+    import dataclasses
+    from trtllm_llama_b200 import runtime as rt
+    cfg = RM.LlamaCfg.tiny(layers=2, hidden=256, inter=384, vocab=512)
+    w = RM.random_weights(cfg, seed=3, std=0.05)
+    B, S, new = 4, 21, 5
+    lens = [S, 3, 12, 17]
+    ids, lens = _prompts(np.random.default_rng(9), cfg, B, S, lens)
+    sess, mc = _session(cfg, w, mode, int8_kv, max_batch=B, max_in=S, max_out=new)
+    sess.setup(B, S, new)
+    a_logits = sess.context(torch.from_numpy(ids), torch.from_numpy(lens)).cpu().numpy()
+    for _ in range(new - 1):
+        sess.step()
+    a_ids, a_kv = sess.output_ids(new).cpu().numpy(), sess.kv_cache(1).cpu().numpy()
+    del sess
+    mc2 = dataclasses.replace(mc, remove_input_padding=True)
+    tensors = rt.build_engine_tensors(_to_torch(w), mc2, kv_scale=4.0 / 127.0)
+    packed = rt.GenerationSession(mc2, tensors)
+    packed.setup(B, S, new)
+    b_logits = packed.context(torch.from_numpy(ids), torch.from_numpy(lens)).cpu().numpy()
+    for _ in range(new - 1):
+        packed.step()
+    b_ids, b_kv = packed.output_ids(new).cpu().numpy(), packed.kv_cache(1).cpu().numpy()
+    np.testing.assert_array_equal(b_logits, a_logits)
+    np.testing.assert_array_equal(b_ids, a_ids)
+    for b in range(B):      # cached positions of the real tokens and of the generated ones
+        np.testing.assert_array_equal(b_kv[b, :, :, :lens[b]], a_kv[b, :, :, :lens[b]])
+        np.testing.assert_array_equal(b_kv[b, :, :, S:S + new - 1], a_kv[b, :, :, S:S + new - 1])
+    out = packed.decode(torch.from_numpy(ids), torch.from_numpy(lens), max_new_tokens=new)
+    np.testing.assert_array_equal(out.numpy(), a_ids)

@@ -44,7 +44,7 @@ def test_build_writes_reference_artefacts(tmp_path):
 
 
 def test_build_rejects_out_of_scope_flags(tmp_path):
-    for bad in (["--remove_input_padding"], ["--n_kv_head", "1"], ["--dtype", "bfloat16"], ["--use_smooth_quant"],
+    for bad in (["--n_kv_head", "1"], ["--dtype", "bfloat16"], ["--use_smooth_quant"],
                 ["--max_beam_width", "17"], ["--max_beam_width", "2", "--paged_kv_cache"]):
         r = subprocess.run([sys.executable, os.path.join(EX, "build.py"), "--output_dir", str(tmp_path), *TINY, *bad],
                            capture_output=True, text=True, timeout=300)

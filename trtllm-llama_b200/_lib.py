@@ -54,6 +54,7 @@ SIGNATURES = {
     "tb_swiglu_quant": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),
     "tb_add": (i32, [vp, vp, vp, i64, vp]),
     "tb_gather_last_token": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+    "tb_gather_last_token_packed": (i32, [vp, vp, vp, i32, i32, vp]),
     "tb_argmax": (i32, [vp, vp, i32, i32, i32, vp]),
     "tb_advance_step": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
     "tb_half_to_float": (i32, [vp, vp, i64, vp]),
@@ -141,6 +142,7 @@ SIGNATURES.update({
     "tbrt_finalize": (i32, [vp]),
     "tbrt_device_bytes": (sz, [vp]),
     "tbrt_context": (i32, [vp, vp, vp, i32, i32, vp]),
+    "tbrt_context_packed": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "tbrt_step": (i32, [vp, vp]),
     "tbrt_logits": (vp, [vp]),
     "tbrt_output_ids": (vp, [vp]),

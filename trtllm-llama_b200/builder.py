@@ -88,7 +88,8 @@ def model_config_from_json(path, rank=0) -> ModelConfig:
     with open(path) as f:
         full = json.load(f)
     c, pc = full["builder_config"], full.get("plugin_config", {})
-    return ModelConfig(paged_kv_cache=bool(pc.get("paged_kv_cache", False)), tokens_per_block=int(pc.get("tokens_per_block", 64)),
+    return ModelConfig(remove_input_padding=bool(pc.get("remove_input_padding", False)),
+                       paged_kv_cache=bool(pc.get("paged_kv_cache", False)), tokens_per_block=int(pc.get("tokens_per_block", 64)),
                        vocab_size=c["vocab_size"], num_layers=c["num_layers"], num_heads=c["num_heads"],
                        hidden_size=c["hidden_size"], inter_size=c["inter_size"], rms_eps=c.get("rms_eps", 1e-6),
                        quant_mode=QuantMode(c.get("quant_mode", 0)), max_batch_size=c["max_batch_size"],

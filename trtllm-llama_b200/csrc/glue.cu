@@ -68,6 +68,23 @@ __global__ void gather_last_kernel(__half* out, const __half* in, const int* las
   for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
 }
 
+// packed rows (remove_input_padding): sequence b ends at packed row sum(lens[:b + 1]) - 1
+__global__ void gather_last_packed_kernel(__half* out, const __half* in, const int* lens, int hidden) {
+  __shared__ int row_s;
+  const int b = blockIdx.x;
+  if (threadIdx.x < 32) {
+    int a = 0;
+    for (int j = threadIdx.x; j <= b; j += 32) a += lens[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) row_s = a > 0 ? a - 1 : 0;
+  }
+  __syncthreads();
+  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t) row_s * hidden);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t) b * hidden);
+  for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = src[i];
+}
+
 // argmax over fp32 logits [B, V]; lowest index wins ties.  One CTA per row.
 __global__ void __launch_bounds__(1024) argmax_kernel(int* out, const float* logits, int vocab, int vocab_stride) {
   __shared__ float sv[32];
@@ -247,6 +264,12 @@ int tb_gather_last_token(void* out, const void* in, const int* last_ids, int bat
                          cudaStream_t s) {
   if (hidden % 8) return -1;
   gather_last_kernel<<<batch, 128, 0, s>>>((__half*) out, (const __half*) in, last_ids, seq, hidden);
+  return (int) cudaGetLastError();
+}
+
+int tb_gather_last_token_packed(void* out, const void* in, const int* lens, int batch, int hidden, cudaStream_t s) {
+  if (hidden % 8) return -1;
+  gather_last_packed_kernel<<<batch, 128, 0, s>>>((__half*) out, (const __half*) in, lens, hidden);
   return (int) cudaGetLastError();
 }
 

@@ -102,7 +102,8 @@ struct tbrt_engine {
   bool finalized = false;
 
   // plugins (one instance per distinct configuration, shared by all layers)
-  PluginPtr lin, lin_res, lin_swiglu, lm, attn, normq, qpt, allreduce, allgather;
+  PluginPtr lin, lin_res, lin_swiglu, lm, attn, attn_packed, normq, qpt, allreduce, allgather;
+  int packed_B = 0;            // > 0 while a packed (remove_input_padding) context phase runs: its sequence count
   // paged KV cache: per-layer pools live in kv[]; one device table [layers][max_batch][2][max_blocks] of block addresses
   int tpb = 0, max_blocks = 0, pool_blocks = 0;
   long long* d_block_tables = nullptr;
@@ -313,6 +314,28 @@ int tbrt_engine::build_plugins() {
     fl.add<int32_t>("device_lengths", PluginFieldType::kINT32, 1);
     if (!(attn = make_plugin("GPTAttention", fl))) return -1;
   }
+  {
+    // the same operator for packed input (build.py --remove_input_padding): input 0 is [1, num_tokens, 3 * hidden]
+    FieldList fl;
+    fl.add<int32_t>("num_heads", PluginFieldType::kINT32, Hl);
+    fl.add<int32_t>("head_size", PluginFieldType::kINT32, c.head_size);
+    fl.add<int32_t>("unidirectional", PluginFieldType::kINT32, 1);
+    fl.add<float>("q_scaling", PluginFieldType::kFLOAT32, 1.f);
+    fl.add<int32_t>("rotary_embedding_dim", PluginFieldType::kINT32, c.head_size);
+    fl.add<int8_t>("neox_rotary_style", PluginFieldType::kINT8, 1);
+    fl.add<int8_t>("context_fmha_type", PluginFieldType::kINT8, 1);
+    fl.add<int8_t>("multi_block_mode", PluginFieldType::kINT8, 1);
+    fl.add<int8_t>("multi_query_mode", PluginFieldType::kINT8, 0);
+    fl.add<int32_t>("int8_kv_cache", PluginFieldType::kINT32, c.int8_kv);
+    fl.add<int32_t>("fp8_kv_cache", PluginFieldType::kINT32, 0);
+    fl.add<int8_t>("remove_input_padding", PluginFieldType::kINT8, 1);
+    fl.add<int32_t>("mask_type", PluginFieldType::kINT32, 1);
+    fl.add<int32_t>("paged_kv_cache", PluginFieldType::kINT32, c.paged_kv_tokens_per_block > 0 ? 1 : 0);
+    fl.add<int32_t>("type_id", PluginFieldType::kINT32, half_t);
+    fl.add<int32_t>("in_flight_batching", PluginFieldType::kINT32, 0);
+    fl.add<int32_t>("device_lengths", PluginFieldType::kINT32, 1);
+    if (!(attn_packed = make_plugin("GPTAttention", fl))) return -1;
+  }
   if (c.mode == TBRT_MODE_SQ) {
     FieldList fl;
     fl.add<float>("eps", PluginFieldType::kFLOAT32, c.rms_eps);
@@ -370,7 +393,8 @@ int tbrt_engine::linear(IPluginV2DynamicExt* p, const LinearW& w, const void* in
 }
 
 int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
-  const int hid = c.hidden, Bq = context ? M / S : M;
+  const bool packed = context && packed_B > 0;          // M = number of real tokens, S = the longest prompt
+  const int hid = c.hidden, Bq = context ? (packed ? packed_B : M / S) : M;
   const bool sq = c.mode == TBRT_MODE_SQ, tp = c.tp_size > 1;
   const int kind = c.mode;   // TBRT_MODE_* == tb_gemv kind
   int gemv_rows = tb_gemv_max_rows(kind, c.hidden);
@@ -438,13 +462,13 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     else RT_CALL(linear(lin.get(), l.qkv, lin_in, xs, qkv, nullptr, M, DataType::kHALF, s));
     {
       const DataType kvt = c.int8_kv ? DataType::kINT8 : DataType::kHALF;
-      PluginTensorDesc id[11] = {desc({Bq, context ? S : 1, 3 * hid_l}, DataType::kHALF),
+      PluginTensorDesc id[11] = {packed ? desc({1, M, 3 * hid_l}, DataType::kHALF) : desc({Bq, context ? S : 1, 3 * hid_l}, DataType::kHALF),
                                  tpb ? desc({pool_blocks, 2, Hl, tpb, c.head_size}, kvt) : desc({Bq, 2, Hl, S_max, c.head_size}, kvt),
                                  desc({Bq}, DataType::kINT32), desc({2}, DataType::kINT32),
                                  desc({Bq, S_max}, DataType::kINT32), desc({Bq}, DataType::kINT32),
                                  desc({S_in}, DataType::kINT32), desc({Bq, 1, S_max}, DataType::kINT32),
                                  desc({1}, DataType::kFLOAT), desc({1}, DataType::kFLOAT)};
-      PluginTensorDesc od[2] = {desc({Bq, context ? S : 1, hid_l}, DataType::kHALF), id[1]};
+      PluginTensorDesc od[2] = {packed ? desc({1, M, hid_l}, DataType::kHALF) : desc({Bq, context ? S : 1, hid_l}, DataType::kHALF), id[1]};
       // masked_tokens = NULL: derived from input_lengths / max_input_length on the device ([ext])
       // input 6: max_input_length as one device int (device_lengths [ext]) — a replayed step graph must not bake S_in
       const void* in[11] = {qkv, kv[li], d_seq_lens, host_len, nullptr, d_in_lens, context ? nullptr : d_max_in, nullptr,
@@ -460,7 +484,7 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
       }
       void* out[2] = {att, kv[li]};
       launches += context ? 2 : 1;
-      RT_CALL(attn->enqueue(id, od, in, out, workspace, s));
+      RT_CALL((packed ? attn_packed : attn)->enqueue(id, od, in, out, workspace, s));
     }
     IPluginV2DynamicExt* row_lin = (fused && sq) ? lin_q_res.get() : lin_res.get();   // QuantizePerToken fused in
     IPluginV2DynamicExt* row_lin_nores = (fused && sq) ? nullptr : lin.get();
@@ -725,6 +749,13 @@ int tbrt_finalize(tbrt_engine* e) {
     const size_t w = tb_gemm_tc_workspace_bytes(c.max_batch, c.hidden, e->hid_l);
     if (w > ws) ws = w;
   }
+  {
+    // packed input: the attention plugin stages padded copies of qkv and of its output in front of the kernels' own space
+    const size_t a = ((Mmax * 3 * e->hid_l * 2 + 127) & ~(size_t) 127) + ((Mmax * e->hid_l * 2 + 127) & ~(size_t) 127);
+    const size_t w = a + tb_context_attention_workspace_bytes(c.max_batch, c.max_input_len, e->Hl) + 256 +
+                     tb_mmha_workspace_bytes(c.max_batch, e->Hl, 32) + 256;
+    if (w > ws) ws = w;
+  }
   e->workspace_bytes = ws + 1024;
   if (e->alloc(e->workspace, e->workspace_bytes)) return -1;
   if (e->alloc(e->d_ids, (size_t) c.max_batch * 4) || e->alloc(e->d_in_lens, (size_t) c.max_batch * 4) ||
@@ -884,6 +915,32 @@ int tbrt_beam_finalize(tbrt_engine* e, int32_t* host_out, float* cum_log_probs_o
   if (cum_log_probs_out) RT_CUDA(cudaMemcpyAsync(cum_log_probs_out, e->d_cum, (size_t) e->B * 4, cudaMemcpyDeviceToHost, s));
   RT_CUDA(cudaStreamSynchronize(s));
   return 0;
+}
+
+// Context phase on packed input (build.py --remove_input_padding; generation.py:355-363): ids [tokens] holds the prompts back
+// to back, input_lengths [batch] on the device, seq = the longest prompt.  Every projection runs on `tokens` rows instead of
+// batch x seq; the KV cache and the generation steps are those of the padded batch.
+int tbrt_context_packed(tbrt_engine* e, const int32_t* ids, const int32_t* input_lengths, int batch, int tokens, int seq,
+                        tb_stream_t st) {
+  if (!e->finalized) return fail("engine not finalized");
+  if (batch < 1 || batch > e->c.max_batch || seq < 1 || seq > e->c.max_input_len || tokens < batch || tokens > batch * seq)
+    return fail("batch / seq / tokens outside the engine limits");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(st);
+  e->B = batch; e->S_in = seq; e->steps_done = 0; e->launches = 0; e->ar_site = 0; e->last_step_fused = false;
+  e->beam_W = 1;
+  RT_CUDA(cudaMemsetAsync(e->d_step_pos, 0, 4, s));
+  RT_CALL(tb_fill_int(e->d_seq_lens, seq - 1, batch, s));
+  RT_CALL(tb_fill_int(e->d_max_in, seq, 1, s));
+  RT_CUDA(cudaMemcpyAsync(e->d_in_lens, input_lengths, (size_t) batch * 4, cudaMemcpyDeviceToDevice, s));
+  e->launches += 1;
+  RT_CALL(tb_embedding(e->h, e->emb, ids, tokens, e->c.hidden, e->c.vocab, s));
+  e->packed_B = batch;
+  const int rc = e->layers_forward(tokens, seq, true, s);
+  e->packed_B = 0;
+  if (rc) return -1;
+  e->launches += 1;
+  RT_CALL(tb_gather_last_token_packed(e->hl, e->h, e->d_in_lens, batch, e->c.hidden, s));
+  return e->head(batch, e->hl, s);
 }
 
 int tbrt_step(tbrt_engine* e, tb_stream_t st) {

@@ -29,6 +29,7 @@ class ModelConfig:
     multi_query_mode: bool = False
     remove_input_padding: bool = False
     paged_kv_cache: bool = False
+    remove_input_padding: bool = False  # LQ/build.py --remove_input_padding: the context phase runs on packed tokens
     tokens_per_block: int = 64          # paged KV cache block size (LQ/build.py --tokens_per_block; a power of two >= 16)
     rms_eps: float = 1e-6
     quant_mode: QuantMode = QuantMode(0)
@@ -256,7 +257,13 @@ class GenerationSession:
             self._upload_kv_blocks(B)
         ids = input_ids.to(device="cuda", dtype=torch.int32).contiguous()
         lens = input_lengths.to(device="cuda", dtype=torch.int32).contiguous()
-        if lib.tbrt_context(self._e, ids.data_ptr(), lens.data_ptr(), B, S, self._stream()):
+        if self.cfg.remove_input_padding:
+            # generation.py:355-363: with remove_input_padding the engine's input_ids is [1, num_tokens], prompts back to back
+            keep = torch.arange(S, device="cuda")[None, :] < lens[:, None]
+            packed = ids[keep].contiguous()
+            if lib.tbrt_context_packed(self._e, packed.data_ptr(), lens.data_ptr(), B, packed.numel(), S, self._stream()):
+                raise _err("tbrt_context_packed")
+        elif lib.tbrt_context(self._e, ids.data_ptr(), lens.data_ptr(), B, S, self._stream()):
             raise _err("tbrt_context")
         self._B = B
         return self.logits()
@@ -314,9 +321,10 @@ class GenerationSession:
         # whether every sequence has produced end_id, stops early, and pads finished sequences with end_id
         end_id = sampling_config.end_id if (sampling_config is not None and sampling_config.end_id is not None) else -1
         lib.tbrt_set_end_id(self._e, int(end_id))
-        if self.kv_cache_manager is not None:
+        if self.kv_cache_manager is not None or self.cfg.remove_input_padding:
             # paged KV cache: the block tables change while the request runs, so the step loop is driven from the host as
-            # in the reference (generation.py:852-997); the stop criterion is applied to the finished ids
+            # in the reference (generation.py:852-997); the stop criterion is applied to the finished ids.  Packed input
+            # takes the same route (the host packs the prompts)
             self.context(input_ids, lens)
             for _ in range(n - 1):
                 self.step()
