@@ -85,6 +85,14 @@ int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, co
                const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
                void* workspace, size_t workspace_bytes, int* counters, int force_splits, int force_nt,
                tb_stream_t stream);
+/* The gate / up projection of the GatedMLP with SwiGLU in the tcgen05 epilogue (prefill shapes; north_star's "fused dequant +
+ * SwiGLU epilogue"): w [N = 2*inter, K] holds the gate rows, then the up rows; c fp16 [M, inter] = silu(x.gate^T) * (x.up^T)
+ * (T/tensorrt_llm/layers/mlp.py:43-73).  kind 0 fp16 | 3 SmoothQuant int8 (sc per-channel [N] or [1], sr per-token [M] or [1],
+ * scale grouping of CE/epilogue/threadblock/epilogue_per_row_per_col_scale.h:279-349).  CTA-pair kernel: each stage holds the
+ * pair's gate rows and the matching up rows, two tcgen05.mma per k-step accumulate them side by side in TMEM.  Bit-identical
+ * to tb_gemm_tc + tb_swiglu. */
+int tb_gemm_tc_swiglu(int kind, void* c, const void* x, const void* w, const float* sc, const float* sr, int sc_per_channel,
+                      int sr_per_token, int M, int N, int K, tb_stream_t stream);
 
 /* ---- attention --------------------------------------------------------------------------------
  * decode step: replaces masked_multihead_attention(params, kvbuf, stream)

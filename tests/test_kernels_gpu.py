@@ -420,3 +420,27 @@ def test_glue(ops):
     logits = rng.standard_normal((5, 32000)).astype(np.float32)
     logits[2, 100] = logits[2, 7] = 99.0   # tie -> lowest index
     assert np.array_equal(host(ops.argmax(dev(logits))), R.greedy_argmax(logits))
+
+
+@pytest.mark.parametrize("kind", ["sq", "fp16"])
+@pytest.mark.parametrize("M,inter,K", [(100, 384, 256), (2048 + 77, 1280, 512), (4096, 11008, 4096)])
+def test_gate_up_gemm_with_swiglu_epilogue_is_bit_identical_to_the_two_kernels(ops, kind, M, inter, K):
+    """tb_gemm_tc_swiglu (CTA-pair tcgen05 kernel, gate and up accumulated side by side in TMEM, silu(gate) * up in the
+    drain) against tb_gemm_tc followed by tb_swiglu on the same operands: identical bits.  inter = 384 / 1280 leave the
+    second CTA of the last pair without channels; M = 100 / 2125 leave ragged token tiles."""
+    g = torch.Generator(device="cuda").manual_seed(M + inter)
+    if kind == "sq":
+        x = torch.randint(-127, 128, (M, K), device="cuda", dtype=torch.int8, generator=g)
+        w = torch.randint(-127, 128, (2 * inter, K), device="cuda", dtype=torch.int8, generator=g)
+        sr = torch.rand((M, 1), device="cuda", generator=g) * 2e-3 + 1e-4
+        sc = torch.rand((1, 2 * inter), device="cuda", generator=g) * 2e-3 + 1e-4
+        two = ops.swiglu(ops.gemm_tc(ops.KIND_A8W8, x, w, sc=sc, sr=sr))
+        one = ops.gemm_tc_swiglu(ops.KIND_A8W8, x, w, sc=sc, sr=sr)
+    else:
+        x = (torch.randn((M, K), device="cuda", generator=g) * 0.5).half()
+        w = (torch.randn((2 * inter, K), device="cuda", generator=g) * 0.05).half()
+        two = ops.swiglu(ops.gemm_tc(ops.KIND_F16, x, w))
+        one = ops.gemm_tc_swiglu(ops.KIND_F16, x, w)
+    assert one.shape == (M, inter)
+    assert torch.equal(one.view(torch.int16), two.view(torch.int16))
+    assert float(one.float().abs().max()) > 0

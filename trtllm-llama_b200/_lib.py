@@ -36,6 +36,7 @@ SIGNATURES = {
     "tb_gemm_tc_workspace_bytes": (sz, [i32, i32, i32]),
     "tb_gemm_tc_counter_bytes": (sz, []),
     "tb_gemm_tc": (i32, [i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, vp, sz, vp, i32, i32, vp]),
+    "tb_gemm_tc_swiglu": (i32, [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "tb_mmha_workspace_bytes": (sz, [i32, i32, i32]),
     "tb_mmha_num_splits": (i32, [i32, i32, i32, i32]),
     "tb_mmha_counter_bytes": (sz, [i32, i32]),

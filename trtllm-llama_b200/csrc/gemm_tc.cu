@@ -500,6 +500,9 @@ static int dispatch_nt(const GemmTcParams& p, const void* x, const void* w, void
 int gemm_tc_pair(int kind, void* c, int out_type, const void* x, const void* w, const float* sc, const float* sr,
                  int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K, cudaStream_t stream);
 
+int gemm_tc_pair_swiglu(int kind, void* c, const void* x, const void* w, const float* sc, const float* sr, int sc_per_channel,
+                        int sr_per_token, int M, int N, int K, cudaStream_t stream);
+
 // TB_GEMM_TC_PAIR=0 keeps every shape on the one-CTA kernel (A/B measurements)
 static bool pair_enabled() {
   static const bool on = [] { const char* e = getenv("TB_GEMM_TC_PAIR"); return !(e && e[0] == '0'); }();
@@ -572,4 +575,16 @@ int tb_gemm_tc(int kind, void* c, int out_type, const void* x, const void* w, co
   }
   return -1;
 }
+}
+
+// Gate / up projection with SwiGLU in the tcgen05 epilogue (prefill shapes): w holds [N = 2 * inter, K] (gate rows, then up
+// rows), c is fp16 [M, inter] = silu(x . gate^T) * (x . up^T).  kind 0 (fp16) or 3 (SmoothQuant int8 with per-token /
+// per-channel scales).  Bit-identical to tb_gemm_tc followed by tb_swiglu.
+extern "C" int tb_gemm_tc_swiglu(int kind, void* c, const void* x, const void* w, const float* sc, const float* sr,
+                                 int sc_per_channel, int sr_per_token, int M, int N, int K, cudaStream_t stream) {
+  if (M < 1 || N < 2 || (N & 1) || K < 1) return -1;
+  if (kind == kGI8 && (!sc || !sr || K % 16)) return -1;
+  if (kind == kGF16 && K % 8) return -1;
+  const int rc = gemm_tc_pair_swiglu(kind, c, x, w, sc, sr, sc_per_channel, sr_per_token, M, N, K, stream);
+  return rc == -100 ? -1 : rc;
 }

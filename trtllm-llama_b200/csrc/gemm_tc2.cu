@@ -35,6 +35,7 @@ struct GemmTc2Params {
   int sc_per_channel, sr_per_token;
   int M, N, K;
   int n_pairs, m_tiles, kb_total, band;
+  int n_out;               // SWIGLU: W holds [2 * n_out, K] (gate rows, then up rows), C is [M, n_out] = silu(gate) * up
 };
 
 constexpr int k2TileN = 128;     // output channels per CTA (UMMA_M = 256 over the pair)
@@ -44,6 +45,17 @@ constexpr int k2ABytes = k2TileN * 128;        // 16 KB
 constexpr int k2BBytes = (k2NT / 2) * 128;     // 16 KB
 constexpr int k2Threads = 192;
 constexpr size_t k2SmemBytes = (size_t) k2Stages * (k2ABytes + k2BBytes) + 1024 + 256 + 4 * k2NT * sizeof(float);
+// SWIGLU variant (the gate / up projection with silu(gate) * up computed in the TMEM drain): a stage holds the pair's gate
+// rows AND the matching up rows (2 x 16 KB per CTA) and a 128-token tile (8 KB per CTA); two MMAs per k-step accumulate
+// gate and up side by side in TMEM (2 x 128 columns per buffer, still double-buffered), so the thread that owns channel n
+// holds both values of every token.  40 KB per stage per CTA for the same MMA work as the plain kernel's 32 KB.
+template <bool SWIGLU> struct Tc2Cfg {
+  static constexpr int NT = SWIGLU ? 128 : k2NT;
+  static constexpr int ABytes = SWIGLU ? 2 * k2ABytes : k2ABytes;
+  static constexpr int BBytes = (NT / 2) * 128;
+  static constexpr int Stages = SWIGLU ? 5 : k2Stages;
+  static constexpr size_t Smem = (size_t) Stages * (ABytes + BBytes) + 1024 + 256 + 4 * NT * sizeof(float);
+};
 
 __device__ __forceinline__ uint32_t cta_rank_in_cluster() {
   uint32_t r;
@@ -115,11 +127,15 @@ __device__ __forceinline__ void pair_coords(const GemmTc2Params& p, int it, int&
   mt = b * p.band + (r - np * bw);
 }
 
-template <int KIND>
+__device__ __forceinline__ float tc2_silu(float v) { return v / (1.f + __expf(-v)); }
+
+template <int KIND, bool SWIGLU = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                 const GemmTc2Params p) {
-  constexpr int ST = k2Stages;
+  using CF = Tc2Cfg<SWIGLU>;
+  constexpr int ST = CF::Stages;
+  constexpr int k2NT = CF::NT, k2ABytes = CF::ABytes, k2BBytes = CF::BBytes;   // shadow the plain kernel's constants
   constexpr int kKElems = KIND == k2I8 ? 128 : 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
@@ -175,6 +191,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           const uint32_t fb = map_to_cta(&full[stage], 0);
           mbar_expect_tx_cluster(fb, k2ABytes + k2BBytes);
           tma_load_2d_pair(sA + (size_t) stage * k2ABytes, &tmap_w, fb, kb * kKElems, nt * k2TileN, pol_w);
+          if constexpr (SWIGLU)
+            tma_load_2d_pair(sA + (size_t) stage * k2ABytes + k2TileN * 128, &tmap_w, fb, kb * kKElems,
+                             p.n_out + nt * k2TileN, pol_w);
           tma_load_2d_pair(sB + (size_t) stage * k2BBytes, &tmap_x, fb, kb * kKElems,
                            mt * k2NT + (int) rank * (k2NT / 2), pol_x);
           if (++stage == ST) { stage = 0; phase ^= 1; }
@@ -189,7 +208,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       for (int it = cluster_id; it < items; it += n_clusters) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + (uint32_t) (acc * k2NT);
+        const uint32_t d_addr = tmem_base + (uint32_t) (acc * 256);
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -199,6 +218,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           for (int k = 0; k < 4; ++k) {
             if constexpr (KIND == k2I8) umma_pair_i8(d_addr, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             else umma_pair_f16(d_addr, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if constexpr (SWIGLU) {   // the up rows of the same channels against the same token tile, next to gate in TMEM
+            const uint64_t au = umma_desc_sw128(smem_u32(sA + (size_t) stage * k2ABytes + k2TileN * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if constexpr (KIND == k2I8) umma_pair_i8(d_addr + k2NT, au + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else umma_pair_f16(d_addr + k2NT, au + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit_pair(&empty[stage]);
           if (++stage == ST) { stage = 0; phase ^= 1; }
@@ -220,16 +247,48 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       const int m0 = mt * k2NT;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * k2NT);
-      float chan = 1.f;
+      const uint32_t t_addr = tmem_base + ((uint32_t) (q * 32) << 16) + (uint32_t) (acc * 256);
+      float chan = 1.f, chan_up = 1.f;
       if constexpr (KIND == k2I8) {
         if (n < p.N) chan = p.sc[p.sc_per_channel ? n : 0];
+        if (SWIGLU && n < p.n_out) chan_up = p.sc[p.sc_per_channel ? p.n_out + n : 0];
         // the tile's per-token scales into a warp-private stash (no dependent global load inside the drain loop)
         __syncwarp();
         for (int i = lane; i < k2NT; i += 32)
           s_sr[i] = p.sr_per_token ? (m0 + i < p.M ? p.sr[m0 + i] : 0.f) : p.sr[0];
         __syncwarp();
       }
+      if constexpr (SWIGLU) {
+        // C[m, n] = fp16( fp16(silu(g)) * u ) with g, u the fp16-rounded gate / up projections: the arithmetic of the plain
+        // kernel followed by tb_swiglu, bit for bit (mlp.py:68-73)
+#pragma unroll 1
+        for (int c = 0; c < k2NT / 16; ++c) {
+          uint32_t vg[16], vu[16];
+          tmem_ld16(t_addr + c * 16, vg);
+          tmem_ld16(t_addr + k2NT + c * 16, vu);
+          tmem_ld_wait();
+          const int mc = m0 + c * 16;
+          if (n < p.n_out) {
+            __half* cp = reinterpret_cast<__half*>(p.c) + (size_t) mc * p.n_out + n;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float g, u;
+              if constexpr (KIND == k2I8) {
+                g = (float) (int) vg[j] * (chan * s_sr[c * 16 + j]);
+                u = (float) (int) vu[j] * (chan_up * s_sr[c * 16 + j]);
+              } else {
+                g = __uint_as_float(vg[j]);
+                u = __uint_as_float(vu[j]);
+              }
+              g = __half2float(__float2half_rn(g));
+              u = __half2float(__float2half_rn(u));
+              const float o = __half2float(__float2half_rn(tc2_silu(g))) * u;
+              if (mc + j < p.M) cp[(size_t) j * p.n_out] = __float2half_rn(o);
+            }
+          }
+          __syncwarp();
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < k2NT / 16; ++c) {
         uint32_t v[16];
@@ -290,8 +349,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
-template <int KIND>
+template <int KIND, bool SWIGLU = false>
 static int launch_gemm_tc2(GemmTc2Params p, const void* x, const void* w, cudaStream_t stream) {
+  using CF = Tc2Cfg<SWIGLU>;
+  constexpr int k2NT = CF::NT;
+  constexpr size_t k2SmemBytes = CF::Smem;
   CUtensorMap tw, tx;
   int rc;
   if constexpr (KIND == k2F16) {
@@ -305,7 +367,7 @@ static int launch_gemm_tc2(GemmTc2Params p, const void* x, const void* w, cudaSt
   }
   if (rc) return rc;
   constexpr int kKElems = KIND == k2I8 ? 128 : 64;
-  const int n_tiles = (p.N + k2TileN - 1) / k2TileN;
+  const int n_tiles = ((SWIGLU ? p.n_out : p.N) + k2TileN - 1) / k2TileN;
   p.n_pairs = (n_tiles + 1) / 2;
   p.m_tiles = (p.M + k2NT - 1) / k2NT;
   p.band = p.m_tiles < 16 ? p.m_tiles : 16;
@@ -313,7 +375,7 @@ static int launch_gemm_tc2(GemmTc2Params p, const void* x, const void* w, cudaSt
   const int items = p.n_pairs * p.m_tiles;
   const int max_clusters = kNumSMs / 2;
   const int grid = 2 * (items < max_clusters ? items : max_clusters);
-  auto kern = gemm_tc2_kernel<KIND>;
+  auto kern = gemm_tc2_kernel<KIND, SWIGLU>;
   TB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) k2SmemBytes));
   kern<<<grid, k2Threads, k2SmemBytes, stream>>>(tw, tx, p);
   return (int) cudaGetLastError();
@@ -328,6 +390,18 @@ int gemm_tc_pair(int kind, void* c, int out_type, const void* x, const void* w, 
   p.sc = sc; p.sr = sr; p.sc_per_channel = sc_per_channel; p.sr_per_token = sr_per_token;
   p.M = M; p.N = N; p.K = K;
   return kind == k2F16 ? launch_gemm_tc2<k2F16>(p, x, w, stream) : launch_gemm_tc2<k2I8>(p, x, w, stream);
+}
+
+// C[M, N / 2] = silu(X . Wgate^T) * (X . Wup^T) with W = [gate rows; up rows] ([N, K]) — the gate / up projection of the
+// GatedMLP (T/tensorrt_llm/layers/mlp.py:43-73) with SwiGLU in the epilogue; bit-identical to gemm_tc_pair + tb_swiglu.
+int gemm_tc_pair_swiglu(int kind, void* c, const void* x, const void* w, const float* sc, const float* sr, int sc_per_channel,
+                        int sr_per_token, int M, int N, int K, cudaStream_t stream) {
+  if ((kind != k2F16 && kind != k2I8) || (N & 1)) return -100;
+  GemmTc2Params p{};
+  p.c = c; p.out_type = 0; p.residual = nullptr;
+  p.sc = sc; p.sr = sr; p.sc_per_channel = sc_per_channel; p.sr_per_token = sr_per_token;
+  p.M = M; p.N = N; p.K = K; p.n_out = N / 2;
+  return kind == k2F16 ? launch_gemm_tc2<k2F16, true>(p, x, w, stream) : launch_gemm_tc2<k2I8, true>(p, x, w, stream);
 }
 
 }  // namespace tb

@@ -372,7 +372,9 @@ class SmoothQuantGemmPlugin : public BasePlugin {
       if (M <= tb_gemv_max_rows(3, K) && is_half(type_))
         return tb_gemv_fused(3, out[0], nullptr, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K,
                              swiglu_, prologue_, gamma, eps_, stream);
-      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= tb_gemv_max_rows) path");
+      if (swiglu_ && !prologue_ && !res && is_half(type_))   // prefill shapes: SwiGLU in the tcgen05 epilogue (gemm_tc2.cu)
+        return tb_gemm_tc_swiglu(3, out[0], in[0], in[1], sc, st, per_channel_, per_token_, M, N, K, stream);
+      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_prologue is only available on the decode (M <= tb_gemv_max_rows) path");
       const int ot = is_half(type_) ? 0 : (type_ == (int32_t) DataType::kFLOAT ? 1 : 2);
       (void) od;
       return tb_gemm_tc(3, out[0], ot, in[0], in[1], nullptr, sc, st, per_channel_, per_token_, res, M, N, K, workspace,
@@ -553,7 +555,9 @@ class GemmPlugin : public BasePlugin {
       if (M <= tb_gemv_max_rows(0, K))
         return tb_gemv_fused(0, out_fp32_ ? nullptr : out[0], out_fp32_ ? static_cast<float*>(out[0]) : nullptr, in[0],
                              in[1], nullptr, nullptr, nullptr, 0, 0, res, M, N, K, swiglu_, prologue_, gamma, eps_, stream);
-      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_swiglu / fused_prologue are only available on the decode (M <= tb_gemv_max_rows) path");
+      if (swiglu_ && !prologue_ && !res && !out_fp32_)       // prefill shapes: SwiGLU in the tcgen05 epilogue (gemm_tc2.cu)
+        return tb_gemm_tc_swiglu(0, out[0], in[0], in[1], nullptr, nullptr, 0, 0, M, N, K, stream);
+      TBP_REQUIRE(!swiglu_ && !prologue_, "fused_prologue is only available on the decode (M <= tb_gemv_max_rows) path");
       return tb_gemm_tc(0, out[0], out_fp32_ ? 1 : 0, in[0], in[1], nullptr, nullptr, nullptr, 0, 0, res, M, N, K,
                         workspace, tb_gemm_tc_workspace_bytes(M, N, K), counters_.get(tb_gemm_tc_counter_bytes()), 0, 0,
                         stream);

@@ -401,6 +401,13 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
   if (tb_gemv_max_rows(kind, hid_l) < gemv_rows) gemv_rows = tb_gemv_max_rows(kind, hid_l);
   if (tb_gemv_max_rows(kind, inter_l) < gemv_rows) gemv_rows = tb_gemv_max_rows(kind, inter_l);
   const bool fuse_swiglu = M <= gemv_rows;
+  // SwiGLU in the tcgen05 epilogue (tb_gemm_tc_swiglu) is built, bit-identical and reachable through the plugins' fused_swiglu
+  // field at any M, but NOT the default here: measured at M = 16384 (tools/swiglu_tc_bench.py) the fused GEMM runs 1.46 ms
+  // (2.0 POPS) against 0.98 ms (3.0 POPS) for the plain one — two 128-token accumulators per stage move 40 KB of operands
+  // through shared memory per 512 MMA cycles instead of 32 KB — so GEMM + SwiGLU/quantise in two kernels (1.22 ms) beats
+  // fused GEMM + quantise (1.59 ms).  TB_SWIGLU_TC = 1 opts in.
+  static const int swiglu_tc_env = getenv("TB_SWIGLU_TC") ? atoi(getenv("TB_SWIGLU_TC")) : 0;
+  const bool fuse_swiglu_tc = swiglu_tc_env != 0 && M >= 2048 && inter_l % 128 == 0;
   int host_len[2] = {context ? 0 : c.max_input_len, context ? 1 : 0};   // device_lengths [ext]: step position is on the device
 
   auto norm = [&](const __half* src, const void* gamma, const __half* residual, __half* sum_out) -> int {
@@ -525,6 +532,10 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     if (fused) {
       RT_CALL(linear(lin_n_swiglu.get(), l.fc_gate, cur, xs, act, nullptr, M, DataType::kHALF, s, l.ln_post, true));
     } else if (fuse_swiglu) {
+      RT_CALL(linear(lin_swiglu.get(), l.fc_gate, lin_in, xs, act, nullptr, M, DataType::kHALF, s));
+    } else if (fuse_swiglu_tc && (sq || c.mode == TBRT_MODE_FP16)) {
+      // prefill shapes: silu(gate) * up computed in the tcgen05 epilogue (two accumulators side by side in TMEM); the
+      // SmoothQuant per-token quantisation then reads the fp16 activation once (QuantizePerToken below)
       RT_CALL(linear(lin_swiglu.get(), l.fc_gate, lin_in, xs, act, nullptr, M, DataType::kHALF, s));
     } else if (sq && inter_l <= 16384) {
       // SmoothQuant prefill: SwiGLU and the per-token quantisation of its output in one pass over the GEMM output

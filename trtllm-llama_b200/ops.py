@@ -322,3 +322,15 @@ class BeamSearchState:
         check(lib.tb_gather_tree(_p(out), _p(self.ids_t), _p(self.parent_t), self.rows, self.W, n, int(end_id), _stream()),
               "tb_gather_tree")
         return out
+
+
+def gemm_tc_swiglu(kind, x, w_gate_up, *, sc=None, sr=None):
+    """The gate / up projection with SwiGLU in the tcgen05 epilogue: w_gate_up [2*inter, K] (gate rows, then up rows) ->
+    fp16 [..., inter] = silu(x.gate^T) * (x.up^T).  kind KIND_F16 or KIND_A8W8.  Bit-identical to gemm_tc + swiglu."""
+    _chk_cuda(x, w_gate_up, sc, sr)
+    M, K = x.numel() // x.shape[-1], x.shape[-1]
+    N = w_gate_up.shape[0]
+    c = torch.empty(x.shape[:-1] + (N // 2,), dtype=torch.float16, device=x.device)
+    check(lib.tb_gemm_tc_swiglu(kind, _p(c), _p(x), _p(w_gate_up), _p(sc), _p(sr), int(sc is not None and sc.numel() > 1),
+                                int(sr is not None and sr.numel() > 1), M, N, K, _stream()), "tb_gemm_tc_swiglu")
+    return c
