@@ -458,6 +458,52 @@ def tp_parity(cx, name, tp_ids):
             "rule": f"ids identical until a step whose tp=1 top-2 margin <= {tol:.3g} (2e-2 x |logits|max)"}
 
 
+def tp_parity_forced(cx, name, n_steps=32):
+    """COLLECTIVE (every rank): the tensor-parallel engine and — on rank 0 — a tp = 1 engine of the same weights are stepped
+    along the SAME token path (tbrt_force_ids: the tp = 1 arg-max is broadcast and forced into both), and rank 0 compares
+    their fp32 logits after the context phase and after every one of ``n_steps`` generation steps.  Unlike the id
+    comparison this does not end at the first near-tie, so the sharding, both all-reduces per layer, the vocabulary-parallel
+    head and the decode path the engine selects under tensor parallelism (the fused step kernel) are checked on every
+    step.  Tolerance: 2e-2 x max(1, |logits|max), the engine-vs-oracle logit tolerance of tests/test_engine_gpu.py."""
+    torch, dist = cx.torch, cx.dist
+    mode, int8_kv, B, in_len, out_len, _ = WORKLOADS[name]
+    n_steps = min(n_steps, out_len - 1)
+    sess, tensors = build_session(cx, mode, int8_kv, B, in_len, out_len, cx.world, cx.rank, graph=not cx.args.no_graph,
+                                  peer_ar=not cx.args.nccl_only)
+    one = one_t = None
+    if cx.rank == 0:
+        one, one_t = build_session(cx, mode, int8_kv, B, in_len, out_len, 1, 0, graph=True, peer_ar=False)
+    g = torch.Generator().manual_seed(1234)
+    ids = torch.randint(3, LLAMA7B["vocab"], (B, in_len), generator=g, dtype=torch.int32)
+    lens = torch.full((B,), in_len, dtype=torch.int32)
+    lg_tp = sess.context(ids, lens)
+    lg_1 = one.context(ids, lens) if one is not None else None
+    worst, scale, argmax_equal = 0.0, 1.0, 0
+    for s in range(n_steps + 1):
+        tok = torch.zeros(B, dtype=torch.int32, device="cuda")
+        if cx.rank == 0:
+            worst = max(worst, float((lg_tp - lg_1).abs().max()))
+            scale = max(scale, float(lg_1.abs().max()))
+            argmax_equal += int(torch.equal(lg_tp.argmax(-1), lg_1.argmax(-1)))
+            tok = lg_1.argmax(-1).to(torch.int32)
+        dist.broadcast(tok, 0)
+        if s == n_steps:
+            break
+        sess.force_ids(tok)
+        lg_tp = sess.step()
+        if one is not None:
+            one.force_ids(tok)
+            lg_1 = one.step()
+    path = "fused step kernel" if cx.lib.tbrt_last_launches(sess._e) == 1 else "per-operator plugin schedule"
+    del sess, tensors, one, one_t
+    gc.collect()
+    torch.cuda.empty_cache()
+    tol = 2e-2 * scale
+    return {"ok": worst <= tol, "steps_compared": n_steps + 1, "max_abs_logit_diff": round(worst, 5), "tolerance": round(tol, 5),
+"argmax_equal_steps": argmax_equal, "decode_path": path, "rule": "teacher-forced: both engines follow the tp=1 arg-max path; fp32 logits "
+            "compared after the context phase and after every generation step"}
+
+
 def int8_peak(cx):
     """tcgen05 kind::i8 tensor-pipe peak of this GPU at its sustained clock: back-to-back MMAs on resident operands,
     one CTA per SM, CUDA events (csrc/peak.cu).  Also kind::f16 the same way, for calibration against cuBLAS bf16."""
@@ -633,6 +679,11 @@ def main():
         if rank == 0:
             parity = tp_parity(cx, name, ids)
         cx.barrier()
+        forced = tp_parity_forced(cx, name)
+        cx.barrier()
+        if rank == 0:
+            parity["logits"] = forced
+            parity["ok"] = bool(parity["ok"] and forced["ok"])
 
     side = {}
     if not args.only_headline:

@@ -177,6 +177,9 @@ int tb_finished(int* all_done, int* out_ids, int batch, int out_stride, int n_do
 int tb_half_to_float(float* out, const void* in, int64_t n, tb_stream_t s);
 int tb_fill_int(int* p, int value, int n, tb_stream_t s);
 int tb_tile_int(int* p, int n, int w, tb_stream_t s);
+/* teacher forcing (parity checks): the token of the column produced last (*step_pos - 1) becomes ids[b], in the next step's
+ * input ids and in output_ids [batch, out_stride] */
+int tb_force_ids(const int* ids, int* input_ids, int* output_ids, const int* step_pos, int batch, int out_stride, tb_stream_t s);
 /* packed <-> padded token rows (GPTAttention remove_input_padding, gptAttentionCommon.cpp:467-478): sequence b owns packed
  * rows [sum(lens[:b]), + lens[b]) and padded rows [b * seq, b * seq + lens[b]); lens is a DEVICE array; unpack zero-fills the
  * padded tail rows.  row_bytes: a multiple of 16. */

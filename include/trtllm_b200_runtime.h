@@ -65,6 +65,9 @@ int tbrt_context(tbrt_engine* e, const int32_t* ids, const int32_t* input_length
 int tbrt_context_packed(tbrt_engine* e, const int32_t* ids, const int32_t* input_lengths, int batch, int tokens, int seq,
                         tb_stream_t s);
 int tbrt_step(tbrt_engine* e, tb_stream_t s);
+/* Teacher forcing for parity checks: replaces the token the last tbrt_context / tbrt_step chose by ids [batch] (device), so
+ * two engines (e.g. tp = 1 and tp = N) can be stepped along the same token path while their logits are compared. */
+int tbrt_force_ids(tbrt_engine* e, const int32_t* ids, tb_stream_t s);
 /* fp32 logits [B, vocab] of the last context/step call (device pointer). */
 const float* tbrt_logits(const tbrt_engine* e);
 /* generated ids so far: device int32 [B, max_output_len] (column j = j-th new token). */

@@ -61,6 +61,7 @@ SIGNATURES = {
     "tb_half_to_float": (i32, [vp, vp, i64, vp]),
     "tb_fill_int": (i32, [vp, i32, i32, vp]),
     "tb_tile_int": (i32, [vp, i32, i32, vp]),
+    "tb_force_ids": (i32, [vp, vp, vp, vp, i32, i32, vp]),
     "tb_unpack_rows": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "tb_pack_rows": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "tb_mmha_decode_beams": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, f32,
@@ -145,6 +146,7 @@ SIGNATURES.update({
     "tbrt_context": (i32, [vp, vp, vp, i32, i32, vp]),
     "tbrt_context_packed": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "tbrt_step": (i32, [vp, vp]),
+    "tbrt_force_ids": (i32, [vp, vp, vp]),
     "tbrt_logits": (vp, [vp]),
     "tbrt_output_ids": (vp, [vp]),
     "tbrt_kv_cache": (vp, [vp, i32]),

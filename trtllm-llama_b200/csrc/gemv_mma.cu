@@ -273,9 +273,21 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
 #pragma unroll
       for (int u = 0; u < kMmaU; ++u) consume(lo[u], hi[u], ks + u);
     }
-    for (; ks < ks1; ++ks) {
-      const uint4 lo = ldg_nc_v4(p_lo + (size_t) ks * 64), hi = ldg_nc_v4(p_hi + (size_t) ks * 64);
-      consume(lo, hi, ks);
+    if (ks < ks1) {
+      // tail (< kMmaU steps; the whole slab for int4 at K = 4096): still ONE batch of requests, predicated warp-uniformly —
+      // a step-at-a-time tail cost one full memory round trip per step
+      uint4 lo[kMmaU], hi[kMmaU];
+#pragma unroll
+      for (int u = 0; u < kMmaU; ++u) {
+        if (ks + u < ks1) {
+          lo[u] = ldg_nc_v4(p_lo + (size_t) (ks + u) * 64);
+          hi[u] = ldg_nc_v4(p_hi + (size_t) (ks + u) * 64);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kMmaU; ++u) {
+        if (ks + u < ks1) consume(lo[u], hi[u], ks + u);
+      }
     }
 
     // ---- reduce: warps (shared memory, warp order) then cluster ranks (DSMEM, rank order) -----------------------------

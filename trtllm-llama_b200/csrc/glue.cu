@@ -206,6 +206,14 @@ __global__ void pack_rows_kernel(uint4* dst, const uint4* src, const int* lens, 
     for (int i = threadIdx.x; i < row16; i += blockDim.x) dst[padded + i] = s < len ? src[packed + i] : make_uint4(0, 0, 0, 0);
   }
 }
+// teacher forcing: the token chosen for the column produced last (step_pos - 1) is replaced by ids[b]
+__global__ void force_ids_kernel(const int* ids, int* input_ids, int* output_ids, const int* step_pos, int batch, int out_stride) {
+  const int b = threadIdx.x;
+  if (b >= batch) return;
+  const int col = step_pos[0] - 1;
+  input_ids[b] = ids[b];
+  if (col >= 0 && col < out_stride) output_ids[(size_t) b * out_stride + col] = ids[b];
+}
 __global__ void tile_int_kernel(int* p, int n, int w) {
   const int t = threadIdx.x;
   const int v = t < n * w ? p[t / w] : 0;
@@ -310,6 +318,12 @@ int tb_unpack_rows(void* padded, const void* packed, const int* lens, int batch,
 int tb_pack_rows(void* packed, const void* padded, const int* lens, int batch, int seq, int row_bytes, cudaStream_t s) {
   if (batch < 1 || seq < 1 || row_bytes < 16 || (row_bytes & 15)) return -1;
   pack_rows_kernel<<<dim3(seq, batch), 128, 0, s>>>((uint4*) packed, (const uint4*) padded, lens, seq, row_bytes / 16, 1);
+  return (int) cudaGetLastError();
+}
+
+int tb_force_ids(const int* ids, int* input_ids, int* output_ids, const int* step_pos, int batch, int out_stride, cudaStream_t s) {
+  if (batch < 1 || batch > 1024) return -1;
+  force_ids_kernel<<<1, ((batch + 31) / 32) * 32, 0, s>>>(ids, input_ids, output_ids, step_pos, batch, out_stride);
   return (int) cudaGetLastError();
 }
 

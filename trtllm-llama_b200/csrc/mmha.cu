@@ -525,6 +525,8 @@ size_t tb_mmha_counter_bytes(int batch, int num_heads) { return (size_t) batch *
 
 // split count: enough CTAs for >= 2 waves of 148 SMs, at least 64 cached keys per split
 int tb_mmha_num_splits(int batch, int num_heads, int len_hint, int max_splits) {
+  static const int forced = getenv("TB_MMHA_NSPLIT") ? atoi(getenv("TB_MMHA_NSPLIT")) : 0;   // A/B switch
+  if (forced > 0) return forced > kMaxClusterSplits ? kMaxClusterSplits : forced;
   const int base = batch * num_heads;
   int want = (2 * kNumSMs + base - 1) / base;
   int by_len = len_hint / 64;

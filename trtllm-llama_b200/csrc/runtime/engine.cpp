@@ -996,6 +996,13 @@ int tbrt_step(tbrt_engine* e, tb_stream_t st) {
   return 0;
 }
 
+int tbrt_force_ids(tbrt_engine* e, const int32_t* ids, tb_stream_t st) {
+  if (!e->finalized || e->B == 0 || !ids) return fail("tbrt_force_ids before tbrt_context");
+  if (e->beam_W != 1) return fail("tbrt_force_ids: not during beam search");
+  RT_CALL(tb_force_ids(ids, e->d_ids, e->d_out_ids, e->d_step_pos, e->B, e->c.max_output_len, reinterpret_cast<cudaStream_t>(st)));
+  return 0;
+}
+
 int tbrt_generate(tbrt_engine* e, const int32_t* host_ids, const int32_t* host_lengths, int batch, int seq, int max_new,
                   int32_t* host_out_ids, tb_stream_t st) {
   if (!e->finalized) return fail("engine not finalized");

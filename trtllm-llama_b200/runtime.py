@@ -277,6 +277,12 @@ class GenerationSession:
             raise _err("tbrt_step")
         return self.logits()
 
+    def force_ids(self, ids: torch.Tensor):
+        """teacher forcing (parity checks): the token chosen by the last context() / step() becomes ``ids`` [B]."""
+        t = ids.to(device="cuda", dtype=torch.int32).contiguous()
+        if lib.tbrt_force_ids(self._e, t.data_ptr(), self._stream()):
+            raise _err("tbrt_force_ids")
+
     def logits(self) -> torch.Tensor:
         """fp32 [B, vocab] copy of the engine's logits buffer."""
         n = self._B * self.cfg.vocab_size
