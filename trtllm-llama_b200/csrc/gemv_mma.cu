@@ -7,12 +7,13 @@
 // (tcgen05 would need the weights in shared memory; for a stream that is read exactly once the registers are
 // the shorter path — gemm_tc.cu is the tcgen05 kernel for M > 8.)
 //
-// Mapping: a CTA (8 warps) owns a tile of 16 weight rows (SwiGLU: 8 gate rows + the 8 matching up rows).  K is cut
-// into 8 x S slabs: one per warp of each CTA of a thread-block cluster of S CTAs (S = 1, 2, 4 chosen by the host so
-// that small-N projections still cover the chip).  In a k-step lane (g = lane / 4, t = lane % 4) loads 16 bytes of
-// row g and 16 bytes of row g + 8 at byte offset 64 * step + 16 * t: every request is 64 contiguous bytes per row,
-// consecutive steps continue the same rows.  The logical k order inside an MMA is a fixed permutation applied to
-// both operands (a lane's 8 halves feed k-slots {2t,2t+1,2t+8,2t+9} of two MMAs), which a dot product allows.
+// Mapping: a CTA (16 warps, one CTA per SM, persistent) owns a tile of 16 weight rows at a time (SwiGLU: 8 gate rows + the
+// 8 matching up rows).  K is cut into 16 x S slabs: one per warp of each CTA of a thread-block cluster of S CTAs (S > 1 only
+// when there are fewer tiles than SMs, or when the staged activations of the whole K would not fit beside the weight ring).
+// In a k-step lane (g = lane / 4, t = lane % 4) owns 16 bytes of row g and 16 bytes of row g + 8 at byte offset
+// 64 * step + 16 * t: every request is 64 contiguous bytes per row, consecutive steps continue the same rows.  The logical
+// k order inside an MMA is a fixed permutation applied to both operands (a lane's 8 halves feed k-slots {2t,2t+1,2t+8,2t+9}
+// of two MMAs), which a dot product allows.
 // Partial accumulators are reduced in warp order through shared memory, then in CTA-rank order through
 // distributed shared memory: deterministic, no atomics.
 // Fused prologues / epilogues and programmatic dependent launch as in gemv.cu.
@@ -116,6 +117,13 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // entry, the first tiles' requests, issued ABOVE griddepcontrol.wait and the activation prologue (weights do not depend
 // on the previous kernel) — are in flight while the CTA reduces and writes the current one.  A lane only ever reads
 // bytes it copied itself: cp.async.wait_group is the only synchronisation the ring needs.
+// (The previous form of this kernel loaded a tile's slab into registers, consumed it, reduced, and only then requested the
+// next tile: 2.1-3.5 TB/s; ncu of this form: profiles/r02_gemv_mma_*.)
+// Measured on top of this form and not kept (same-run A/B at step level, tools/mma_ab.sh): CTA pairs sharing the norm
+// prologue through distributed shared memory, each normalising half of the token rows and storing into both (cfg3 int8-KV
+// 3.00 vs 3.00 ms, int4 B=8 2.17 vs 2.18: two cluster barriers cost what the halved work saves); RMSNorm as its own
+// PDL-chained kernel from 5 rows on (2.934 vs 2.941 ms, kept as TB_FUSE_NORM_ROWS); the next-projection L2 window
+// (TB_MMA_PF=1: 3.05 vs 3.17 ms).
 //
 // Activations: always staged in shared memory (the K range of this CTA only), transformed by the fused prologue or copied
 // as they are, in a layout whose 16-byte chunks are permuted so that the B-fragment loads of a quarter-warp (4 k-groups

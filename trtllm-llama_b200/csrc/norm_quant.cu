@@ -48,6 +48,10 @@ struct NormParams {
 template <int ITER>
 __global__ void __launch_bounds__(kNormThreads) norm_quant_kernel(NormParams p) {
   __shared__ float red[32];
+  // programmatic dependent launch (decode steps: this kernel sits between two projection kernels of a CUDA graph): start as
+  // the previous kernel drains, let the next one (which prefetches weights before it waits) start at once
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int row = blockIdx.x;
   const int nvec = p.hidden >> 3;
   const size_t base = (size_t) row * p.hidden;
@@ -151,12 +155,20 @@ __global__ void __launch_bounds__(kNormThreads) norm_quant_kernel(NormParams p) 
 static int launch_norm(const NormParams& p, int rows, cudaStream_t stream) {
   if (p.hidden % 8 != 0 || p.hidden > kNormThreads * 8 * kNormMaxIter || rows <= 0) return -1;
   const int iters = (p.hidden / 8 + kNormThreads - 1) / kNormThreads;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(rows);
+  cfg.blockDim = dim3(kNormThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = rows <= 64 ? 1 : 0;      // decode shapes only
   switch (iters) {
-    case 1: norm_quant_kernel<1><<<rows, kNormThreads, 0, stream>>>(p); break;
-    case 2: norm_quant_kernel<2><<<rows, kNormThreads, 0, stream>>>(p); break;
-    default: norm_quant_kernel<4><<<rows, kNormThreads, 0, stream>>>(p); break;
+    case 1: return (int) cudaLaunchKernelEx(&cfg, norm_quant_kernel<1>, p);
+    case 2: return (int) cudaLaunchKernelEx(&cfg, norm_quant_kernel<2>, p);
+    default: return (int) cudaLaunchKernelEx(&cfg, norm_quant_kernel<4>, p);
   }
-  return (int) cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -440,6 +440,11 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
   const void* lin_in = sq ? static_cast<const void*>(xq) : static_cast<const void*>(x);
   // decode shapes: RMSNorm (+ per-token quantisation) rides in the projection's prologue -> 5 kernels per layer
   const bool fused = M <= gemv_rows;
+  // A/B switch TB_FUSE_NORM_ROWS=4: from 5 rows on run RMSNorm once as its own PDL-chained kernel instead of in the prologue of
+  // every CTA of the tensor-core GEMV (48 % of the QKV launch at 8 rows before the CTA pairs shared it).  Measured equal at
+  // step level (cfg3 int8-KV 2.934 vs 2.941 ms, int4 B=8 2.042 vs 2.025 ms): the extra launches cost what the prologue did.
+  static const int fuse_norm_rows = getenv("TB_FUSE_NORM_ROWS") ? atoi(getenv("TB_FUSE_NORM_ROWS")) : 8;
+  const bool fuse_norm = fused && (sq || M <= fuse_norm_rows);
   // decode shapes: every projection asks L2 for the head of the weights the NEXT projection streams (tb_gemv_hint_next);
   // the whole dense matrix when the attention kernel runs in between.  TB_PF_MB / TB_PF_ATTN_MB = 0 switch it off.
   static const size_t pf_mb = getenv("TB_PF_MB") ? (size_t) atoi(getenv("TB_PF_MB")) : 12;
@@ -465,8 +470,12 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
   for (int li = 0; li < c.layers; ++li) {
     const LayerW& l = L[li];
     hint(&l.dense, false, pf_attn_mb);
-    if (fused) RT_CALL(linear(lin_n.get(), l.qkv, cur, xs, qkv, nullptr, M, DataType::kHALF, s, l.ln_in, true));
-    else RT_CALL(linear(lin.get(), l.qkv, lin_in, xs, qkv, nullptr, M, DataType::kHALF, s));
+    if (fuse_norm) {
+      RT_CALL(linear(lin_n.get(), l.qkv, cur, xs, qkv, nullptr, M, DataType::kHALF, s, l.ln_in, true));
+    } else {
+      if (fused) RT_CALL(norm(cur, l.ln_in, nullptr, nullptr));
+      RT_CALL(linear(lin.get(), l.qkv, lin_in, xs, qkv, nullptr, M, DataType::kHALF, s));
+    }
     {
       const DataType kvt = c.int8_kv ? DataType::kINT8 : DataType::kHALF;
       PluginTensorDesc id[11] = {packed ? desc({1, M, 3 * hid_l}, DataType::kHALF) : desc({Bq, context ? S : 1, 3 * hid_l}, DataType::kHALF),
@@ -529,8 +538,11 @@ int tbrt_engine::layers_forward(int M, int S, bool context, cudaStream_t s) {
     std::swap(cur, nxt);
     bool act_quantised = false;
     hint(&l.proj, false, pf_mb);
-    if (fused) {
+    if (fuse_norm) {
       RT_CALL(linear(lin_n_swiglu.get(), l.fc_gate, cur, xs, act, nullptr, M, DataType::kHALF, s, l.ln_post, true));
+    } else if (fused) {
+      RT_CALL(norm(cur, l.ln_post, nullptr, nullptr));
+      RT_CALL(linear(lin_swiglu.get(), l.fc_gate, lin_in, xs, act, nullptr, M, DataType::kHALF, s));
     } else if (fuse_swiglu) {
       RT_CALL(linear(lin_swiglu.get(), l.fc_gate, lin_in, xs, act, nullptr, M, DataType::kHALF, s));
     } else if (fuse_swiglu_tc && (sq || c.mode == TBRT_MODE_FP16)) {
