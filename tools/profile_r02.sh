@@ -19,3 +19,12 @@ ncu $NV $F -k regex:decode_step -c 1 -o gpurun_out/r02_decode_step_sq python too
 for r in gemv_fp16_m1 gemv_sq_m1 decode_step_cfg2 decode_step_sq; do $S full gpurun_out/r02_$r.ncu-rep gpurun_out/r02_${r}_full.txt; done
 rm -f gpurun_out/r02_decode_step_cfg2.ncu-rep gpurun_out/r02_decode_step_sq.ncu-rep gpurun_out/r02_gemv_sq_m1.ncu-rep
 ls -la gpurun_out/r02_*
+# tensor-core decode GEMV (gemv_mma.cu, cp.async ring form): the kernel alone on the LLaMA-7B shapes
+ncu $F -k regex:gemv_mma -s 8 -c 1 -o gpurun_out/mma4_w8m8_qkv python tools/gemv_mma_bench.py w8 8 qkv > gpurun_out/mma4_a.log 2>&1
+ncu $F -k regex:gemv_mma -s 8 -c 1 -o gpurun_out/mma4_w8m8_down python tools/gemv_mma_bench.py w8 8 down > gpurun_out/mma4_b.log 2>&1
+ncu $F -k regex:gemv_mma -s 8 -c 1 -o gpurun_out/mma4_w4m1_gu python tools/gemv_mma_bench.py w4 1 gate_up > gpurun_out/mma4_c.log 2>&1
+for r in w8m8_qkv w8m8_down w4m1_gu; do $S full gpurun_out/mma4_$r.ncu-rep gpurun_out/r02_gemv_mma_${r}_full.txt; python tools/ncu_hotspots.py gpurun_out/mma4_$r.ncu-rep >> gpurun_out/r02_gemv_mma_${r}_full.txt; done
+# launch lists of the tree with the new GEMV
+ncu $NV $L --log-file gpurun_out/r02b_cfg3_int8kv_decode_launches.csv python tools/ncu_decode.py --workload cfg3_int8kv --steps 2 > gpurun_out/r02_p8.log 2>&1
+ncu $NV $L --log-file gpurun_out/r02b_cfg5_decode_launches.csv python tools/ncu_decode.py --workload cfg5 --steps 2 > gpurun_out/r02_p9.log 2>&1
+for w in cfg3_int8kv_decode cfg5_decode; do $S launches gpurun_out/r02b_${w}_launches.csv gpurun_out/r02b_${w}_launches.txt; done

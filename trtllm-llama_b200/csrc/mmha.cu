@@ -637,7 +637,8 @@ static int mmha_launch(void* out, const void* qkv, void* kv_cache, const long lo
   // int8 caches with long contexts: tensor-core loops, two CTAs per SM, so no more splits than fit one wave
   const int mma_env = g_mma_mode;   // A/B switch (TB_MMHA_MMA / tb_mmha_set_mode): 0 off, 1 always, -1 automatic
   const bool use_mma = int8_kv && !cache_indir && (mma_env == 1 || (mma_env != 0 && len_cap >= 512));
-  if (use_mma) {
+  static const bool nofit = getenv("TB_MMHA_NOFIT") && atoi(getenv("TB_MMHA_NOFIT")) != 0;   // A/B switch
+  if (use_mma && !nofit) {
     const int fit = (2 * kNumSMs) / (batch * num_heads);
     if (nsplit > fit) nsplit = fit < 1 ? 1 : fit;
   }
