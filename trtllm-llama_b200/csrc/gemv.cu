@@ -525,13 +525,14 @@ extern "C" int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, con
   if ((prologue >= kProRmsQuant) != (kind == kA8W8) && prologue != kProNone && prologue != kProRms) return -1;
   if (prologue == kProRms && kind == kA8W8) return -1;
   if (swiglu && residual) return -1;
-  // Which kernel: measured on LLaMA-7B decode steps (B200, CUDA-graph replay, tools/mma_minm_ab.sh).  M <= 4: the FMA
-  // kernel's one-warp-per-row stream wins at STEP level for fp16 (2.595 vs 2.624 ms — although the tensor-core kernel is the
-  // faster one timed alone, 16.4 vs 18.5 us per launch: with one 214 KB CTA per SM it cannot overlap its neighbours in the
-  // step the way four small CTAs do) and W8A8 (1.65 vs 2.01 ms); weight-only int8 and int4 are conversion-bound on FMAs and
-  // win on tensor cores (W8: 1.87 vs 2.35 ms, int4: 1.66 vs 2.26 ms).  5..8 rows: tensor-core kernel only.
-  static const int mma_min_m_env = getenv("TB_GEMV_MMA_MIN_M") ? atoi(getenv("TB_GEMV_MMA_MIN_M")) : 0;   // A/B switch
-  const int mma_min_m = mma_min_m_env > 0 ? mma_min_m_env : ((kind == kW4 || kind == kW8) ? 1 : 5);
+  // Which kernel: measured on LLaMA-7B decode steps (B200, CUDA-graph replay, tools/mma_minm_ab.sh, same-run A/B).  The
+  // tensor-core kernel (per-lane cp.async weight ring) takes every 5..8-row problem, and at 1..4 rows: weight-only int8 and
+  // int4, which are conversion-bound on FMAs (W8: 1.87 vs 2.35 ms per step, int4: 1.66 vs 2.26), and fp16 (16.5 vs 18.6 us per
+  // launch timed alone = 0.93 vs 0.83 of the HBM peak; 2.573 vs 2.592 ms per step once the attention kernel triggers its
+  // dependents at entry — before that the one-CTA-per-SM kernel lost the step, 2.62 vs 2.60, to the ramp behind attention).
+  // W8A8 at 1..4 rows stays on the FMA (dp4a) kernel: 1.657 vs 1.687 ms per step.
+  static const int mma_min_m_env = getenv("TB_GEMV_MMA_MIN_M") ? atoi(getenv("TB_GEMV_MMA_MIN_M")) : 0;   // A/B switch (5: FMA at <= 4 rows)
+  const int mma_min_m = mma_min_m_env > 0 ? mma_min_m_env : (kind == kA8W8 ? 5 : 1);
   if (M >= mma_min_m && gemv_mma_eligible(kind, M, K)) {
     // the next-weights window measured slower on this kernel's workloads (cfg3 int8-KV 3.32 -> 3.40 ms, int4 2.10 -> 2.26 ms)
     static const bool mma_pf = getenv("TB_MMA_PF") && atoi(getenv("TB_MMA_PF")) != 0;
