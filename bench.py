@@ -206,7 +206,7 @@ def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which, rows=1, tp=1)
     ms = e0.elapsed_time(e1) / reps
     n_launch = len(calls)
     achieved = bytes_total / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": f"decode projection GEMV ({'gemv_mma_kernel' if rows > 4 or mode == 'w4' else 'gemv_kernel'}, "
+    return {"bound": "hbm", "kernel": f"decode projection GEMV ({'gemv_mma_kernel' if ops.lib.tb_gemv_on_tensor_cores(kind, rows, hid) else 'gemv_kernel'}, "
                                       f"{rows} token row{'s' if rows > 1 else ''})",
             "achieved": round(achieved, 1), "peak": hbm_peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
             "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "bytes_per_launch": bytes_total // n_launch,

@@ -54,6 +54,9 @@ int tb_quantize_tensor(int8_t* dst, const void* src, int64_t size, const float* 
  * swiglu != 0: w holds [N = 2*inter, K] (gate rows then up rows), y is [M, inter] = silu(gate)*up.
  * y_f32 != NULL writes fp32 instead of fp16 (lm_head logits).                                   */
 int tb_gemv_max_rows(int kind, int K);
+/* 1: this (kind, rows, K) runs on the tensor-core GEMV (gemv_mma_kernel), 0: on the FMA GEMV (gemv_kernel) — the reference
+ * picks between weight_only_gemv_launcher and the CUTLASS runner the same way (weightOnlyQuantMatmulPlugin.cpp:236-262) */
+int tb_gemv_on_tensor_cores(int kind, int M, int K);
 int tb_gemv(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
             const float* sr, int sc_per_channel, int sr_per_token, const void* residual, int M, int N, int K,
             int swiglu, tb_stream_t stream);

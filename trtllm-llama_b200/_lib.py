@@ -31,6 +31,7 @@ SIGNATURES = {
     "tb_quantize_tensor": (i32, [vp, vp, i64, vp, i32, vp]),
     "tb_gemv": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, vp]),
     "tb_gemv_max_rows": (i32, [i32, i32]),
+    "tb_gemv_on_tensor_cores": (i32, [i32, i32, i32]),
     "tb_gemv_hint_next": (i32, [vp, sz, vp, sz]),
     "tb_gemv_fused": (i32, [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp, f32, vp]),
     "tb_gemm_tc_workspace_bytes": (sz, [i32, i32, i32]),

@@ -501,6 +501,13 @@ extern "C" int tb_gemv_hint_next(const void* a, size_t a_bytes, const void* b, s
 // rows the decode-shape path accepts for this weight kind and K: 8 on the tensor-core kernel, 4 on the FMA kernel
 extern "C" int tb_gemv_max_rows(int kind, int K) { return gemv_mma_eligible(kind, 8, K) ? 8 : 4; }
 
+// 1: tb_gemv / tb_gemv_fused run this problem on the tensor-core kernel (gemv_mma.cu), 0: on the FMA kernel of this file
+extern "C" int tb_gemv_on_tensor_cores(int kind, int M, int K) {
+  static const int mma_min_m_env = getenv("TB_GEMV_MMA_MIN_M") ? atoi(getenv("TB_GEMV_MMA_MIN_M")) : 0;   // A/B switch (5: FMA at <= 4 rows)
+  const int mma_min_m = mma_min_m_env > 0 ? mma_min_m_env : (kind == kA8W8 ? 5 : 1);
+  return M >= mma_min_m && gemv_mma_eligible(kind, M, K) ? 1 : 0;
+}
+
 extern "C" int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale,
                              const float* sc, const float* sr, int sc_per_channel, int sr_per_token, const void* residual,
                              int M, int N, int K, int swiglu, int prologue, const void* gamma, float eps,
@@ -531,9 +538,7 @@ extern "C" int tb_gemv_fused(int kind, void* y, float* y_f32, const void* x, con
   // launch timed alone = 0.93 vs 0.83 of the HBM peak; 2.573 vs 2.592 ms per step once the attention kernel triggers its
   // dependents at entry — before that the one-CTA-per-SM kernel lost the step, 2.62 vs 2.60, to the ramp behind attention).
   // W8A8 at 1..4 rows stays on the FMA (dp4a) kernel: 1.657 vs 1.687 ms per step.
-  static const int mma_min_m_env = getenv("TB_GEMV_MMA_MIN_M") ? atoi(getenv("TB_GEMV_MMA_MIN_M")) : 0;   // A/B switch (5: FMA at <= 4 rows)
-  const int mma_min_m = mma_min_m_env > 0 ? mma_min_m_env : (kind == kA8W8 ? 5 : 1);
-  if (M >= mma_min_m && gemv_mma_eligible(kind, M, K)) {
+  if (tb_gemv_on_tensor_cores(kind, M, K)) {
     // the next-weights window measured slower on this kernel's workloads (cfg3 int8-KV 3.32 -> 3.40 ms, int4 2.10 -> 2.26 ms)
     static const bool mma_pf = getenv("TB_MMA_PF") && atoi(getenv("TB_MMA_PF")) != 0;
     if (!mma_pf) p.pf_lines[0] = p.pf_lines[1] = 0;
