@@ -127,7 +127,7 @@ __device__ __forceinline__ void pair_coords(const GemmTc2Params& p, int it, int&
   mt = b * p.band + (r - np * bw);
 }
 
-__device__ __forceinline__ float tc2_silu(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float tc2_silu(float v) { return silu_fast(v); }   // same definition as tb_swiglu: bit-identical
 
 template <int KIND, bool SWIGLU = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)

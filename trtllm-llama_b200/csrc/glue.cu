@@ -35,7 +35,7 @@ __global__ void swiglu_kernel(__half* out, const __half* gate, const __half* up,
     for (int j = 0; j < 4; ++j) {
       float2 gf = __half22float2(g[j]), uf = __half22float2(u[j]);
       // act output rounded to fp16 (TRT fp16 activation layer), then fp16 multiply
-      __half2 a = __floats2half2_rn(gf.x / (1.f + __expf(-gf.x)), gf.y / (1.f + __expf(-gf.y)));
+      __half2 a = __floats2half2_rn(silu_fast(gf.x), silu_fast(gf.y));
       float2 af = __half22float2(a);
       o[j] = __floats2half2_rn(af.x * uf.x, af.y * uf.y);
     }

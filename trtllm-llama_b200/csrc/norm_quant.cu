@@ -174,6 +174,47 @@ static int launch_norm(const NormParams& p, int rows, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // per-token quantiser (fp16 / fp32 in)
 // ---------------------------------------------------------------------------------------------
+// fp16 rows of up to ITER * 4096 columns: read ONCE with 16-byte loads and kept in registers between the amax and the
+// quantise phase.  One row per CTA is latency-bound (load -> block reduce -> store), so what counts is resident CTAs: ITER
+// is a template parameter and the bound below keeps the kernel at 32 registers = 4 CTAs per SM (a first version with a
+// 4-deep register array for every width ran at 3 CTAs per SM and was slower than the two-pass kernel, 90 vs 65 us).
+template <int ITER>
+__global__ void __launch_bounds__(kNormThreads, ITER == 1 ? 4 : 2) per_token_quant_half_kernel(int8_t* dst, const __half* src,
+                                                                                              int cols, float* scales) {
+  __shared__ float red[32];
+  const __half* s = src + (size_t) blockIdx.x * cols;
+  int8_t* d = dst + (size_t) blockIdx.x * cols;
+  uint4 v[ITER];
+  float amax = 0.f;
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int i = (it * kNormThreads + threadIdx.x) * 8;
+    v[it] = make_uint4(0, 0, 0, 0);
+    if (i < cols) v[it] = *reinterpret_cast<const uint4*>(s + i);
+    const __half2* h = reinterpret_cast<const __half2*>(&v[it]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  amax = fmaxf(block_reduce(amax, red, true), __half2float(__float2half_rn(1e-6f)));   // localMax = T(1e-6f) in the reference
+  if (threadIdx.x == 0) scales[blockIdx.x] = amax / 127.f;
+  const float qs = 127.f / amax;
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int i = (it * kNormThreads + threadIdx.x) * 8;
+    if (i < cols) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[it]);
+      const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), e = __half22float2(h[3]);
+      uint2 q;
+      q.x = pack4_i8(a.x * qs, a.y * qs, b.x * qs, b.y * qs);
+      q.y = pack4_i8(c.x * qs, c.y * qs, e.x * qs, e.y * qs);
+      *reinterpret_cast<uint2*>(d + i) = q;
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads) per_token_quant_kernel(int8_t* dst, const T* src, int cols,
                                                                        float* scales) {
@@ -234,7 +275,7 @@ __global__ void __launch_bounds__(kNormThreads) swiglu_quant_kernel(int8_t* dst,
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 gf = __half22float2(g[j]), uf = __half22float2(u[j]);
-        const __half2 a = __floats2half2_rn(gf.x / (1.f + __expf(-gf.x)), gf.y / (1.f + __expf(-gf.y)));
+        const __half2 a = __floats2half2_rn(silu_fast(gf.x), silu_fast(gf.y));
         const float2 af = __half22float2(a);
         o[j] = __floats2half2_rn(af.x * uf.x, af.y * uf.y);
         const float2 of = __half22float2(o[j]);
@@ -306,6 +347,10 @@ int tb_quantize_per_token(int8_t* dst, float* scales, const void* src, int rows,
                           cudaStream_t stream) {
   if (cols % 4 != 0 || rows <= 0) return -1;
   if (src_is_fp32) per_token_quant_kernel<float><<<rows, kNormThreads, 0, stream>>>(dst, (const float*) src, cols, scales);
+  else if (cols % 8 == 0 && cols <= kNormThreads * 8)
+    per_token_quant_half_kernel<1><<<rows, kNormThreads, 0, stream>>>(dst, (const __half*) src, cols, scales);
+  else if (cols % 8 == 0 && cols <= kNormThreads * 8 * 3)
+    per_token_quant_half_kernel<3><<<rows, kNormThreads, 0, stream>>>(dst, (const __half*) src, cols, scales);
   else per_token_quant_kernel<__half><<<rows, kNormThreads, 0, stream>>>(dst, (const __half*) src, cols, scales);
   return (int) cudaGetLastError();
 }
