@@ -257,14 +257,15 @@ __global__ void __launch_bounds__(kNormThreads) per_token_quant_kernel(int8_t* d
 // the fp16 activation, 540 MB per layer at 16384 rows).  Same arithmetic as swiglu_kernel followed by
 // per_token_quant_kernel<__half>: act = fp16(fp16(silu(g)) * u), amax over the row, q = rni_sat(act * (127 / amax)).
 constexpr int kSqMaxIter = 4;   // row chunks of 8 held in registers per thread: inter <= 4 * 512 * 8
-__global__ void __launch_bounds__(kNormThreads) swiglu_quant_kernel(int8_t* dst, float* scales, const __half* gate,
+template <int kSqIter>
+__global__ void __launch_bounds__(kNormThreads, kSqIter <= 3 ? 4 : 3) swiglu_quant_kernel(int8_t* dst, float* scales, const __half* gate,
                                                                     const __half* up, int inter, int in_stride) {
   __shared__ float red[32];
   const size_t row = blockIdx.x;
-  uint4 act[kSqMaxIter];
+  uint4 act[kSqIter];
   float amax = 0.f;
 #pragma unroll
-  for (int it = 0; it < kSqMaxIter; ++it) {
+  for (int it = 0; it < kSqIter; ++it) {
     const int i = (it * kNormThreads + threadIdx.x) * 8;
     if (i < inter) {
       const uint4 g4 = *reinterpret_cast<const uint4*>(gate + row * in_stride + i);
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(kNormThreads) swiglu_quant_kernel(int8_t* dst,
   if (threadIdx.x == 0) scales[row] = amax / 127.f;
   const float qs = 127.f / amax;
 #pragma unroll
-  for (int it = 0; it < kSqMaxIter; ++it) {
+  for (int it = 0; it < kSqIter; ++it) {
     const int i = (it * kNormThreads + threadIdx.x) * 8;
     if (i < inter) {
       const __half2* o = reinterpret_cast<const __half2*>(&act[it]);
@@ -358,7 +359,11 @@ int tb_quantize_per_token(int8_t* dst, float* scales, const void* src, int rows,
 int tb_swiglu_quant(int8_t* dst, float* scales, const void* gate, const void* up, int rows, int inter, int in_stride,
                     cudaStream_t stream) {
   if (inter % 8 || in_stride % 8 || rows <= 0 || inter > kSqMaxIter * kNormThreads * 8) return -1;
-  swiglu_quant_kernel<<<rows, kNormThreads, 0, stream>>>(dst, scales, (const __half*) gate, (const __half*) up, inter,
+  if (inter <= 3 * kNormThreads * 8)
+    swiglu_quant_kernel<3><<<rows, kNormThreads, 0, stream>>>(dst, scales, (const __half*) gate, (const __half*) up, inter,
+                                                         in_stride);
+  else
+    swiglu_quant_kernel<kSqMaxIter><<<rows, kNormThreads, 0, stream>>>(dst, scales, (const __half*) gate, (const __half*) up, inter,
                                                          in_stride);
   return (int) cudaGetLastError();
 }
