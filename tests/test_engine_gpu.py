@@ -204,3 +204,37 @@ def test_packed_input_equals_the_padded_batch(mode, int8_kv):
         np.testing.assert_array_equal(b_kv[b, :, :, S:S + new - 1], a_kv[b, :, :, S:S + new - 1])
     out = packed.decode(torch.from_numpy(ids), torch.from_numpy(lens), max_new_tokens=new)
     np.testing.assert_array_equal(out.numpy(), a_ids)
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_force_ids_teacher_forcing(fused):
+    """tbrt_force_ids (the hook bench.py --gpus N uses to step a tp = N and a tp = 1 engine along one token path): forcing
+    the token the engine chose itself changes nothing; forcing another token gives the logits of a request whose step-0
+    output was that token — checked against the oracle run on the forced path — and lands in output_ids."""
+    cfg = RM.LlamaCfg.tiny(layers=2, hidden=256, inter=384, vocab=512)
+    w = RM.random_weights(cfg, seed=9, std=0.05)
+    B, S, new = 2, 10, 4
+    rng = np.random.default_rng(21)
+    ids, lens = _prompts(rng, cfg, B, S, [S, S - 3])
+    sess, _ = _session(cfg, w, "fp16", True, B, S, new, fused=fused)
+    sess.setup(B, S, new)
+    t_ids, t_lens = torch.from_numpy(ids), torch.from_numpy(lens)
+    lg0 = sess.context(t_ids, t_lens)
+    own = lg0.argmax(-1).to(torch.int32)
+    sess.force_ids(own)                                  # a no-op by construction
+    lg1 = sess.step().clone()
+    sess.context(t_ids, t_lens)
+    lg1_plain = sess.step().clone()
+    assert torch.equal(lg1, lg1_plain)
+    # another path: token 7 / 11 instead of the arg-max
+    forced = torch.tensor([7, 11], dtype=torch.int32)
+    sess.context(t_ids, t_lens)
+    sess.force_ids(forced)
+    got = sess.step().cpu().numpy()
+    assert sess.output_ids(1)[:, 0].cpu().tolist() == [7, 11]
+    # oracle on the forced path (same padded-batch protocol: context, then one step fed with the forced tokens)
+    om = RM.OracleLlama(cfg, w, "fp16", True, kv_scale=4.0 / 127.0, max_seq_len=S + new)
+    om.context(ids, lens)
+    ref = om.step(forced.numpy())
+    tol = 1e-2 * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(got - ref).max() <= tol
