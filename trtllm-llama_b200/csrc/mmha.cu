@@ -95,6 +95,12 @@ __device__ __forceinline__ void mmha_mma_f16(float (&c)[4], uint32_t a0, uint32_
 __device__ __forceinline__ uint32_t mmha_h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ uint32_t mmha_pack_h2(float a, float b) { return mmha_h2u(__floats2half2_rn(a, b)); }
 
+// Measured and rejected (round 2): feeding the tensor-core loops from a per-lane cp.async ring (the K blocks, then the V blocks
+// of a warp as one flat sequence, 4 blocks = 8 KB per warp ahead, started above the RoPE prologue and running through the
+// softmax) — the form that took the tensor-core GEMV from 3.5 to 4.3 TB/s — made this kernel SLOWER at B = 8, L = 2047, int8:
+// 29.9 -> 37.8 us.  One 16-key block per iteration leaves a warp 16 MMAs of work per wait, against two blocks' worth with
+// the register-resident loads below, and the extra shared-memory round trip is not free at two CTAs per SM.
+//
 // Launch bounds.  fp16 caches: capped at 64 registers so that four CTAs share an SM (76 registers = three CTAs: the 512
 // CTAs of cfg3 no longer fit one wave, 1332 -> 1428 tokens/s); the int8 FMA variant is at 64 already and loses with an
 // explicit bound.
