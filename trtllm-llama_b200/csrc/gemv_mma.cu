@@ -667,11 +667,18 @@ static int launch_gemv_mma(GemvMmaParams p, cudaStream_t stream) {
   return launch_gemv_mma_r<KIND, SWIGLU, kMmaRingSmall>(p, xs_bytes, stream);
 }
 
-// true when the tensor-core GEMV handles this problem (else gemv.cu's FMA kernel, M <= 4)
+// true when the tensor-core GEMV handles this problem (else gemv.cu's FMA kernel, M <= 4): K a whole number of k-steps, and
+// the staged activations of the deepest K split (4 CTAs) fit beside the shallowest weight ring
 bool gemv_mma_eligible(int kind, int M, int K) {
   if (M < 1 || M > 8) return false;
   const int step = kind == kMF16 ? 32 : (kind == kMW4 ? 128 : 64);
-  return K % step == 0 && K / step >= kMmaMinSteps;
+  if (K % step != 0 || K / step < kMmaMinSteps) return false;
+  const int xstep = step * (kind == kMA8W8 ? 1 : 2);
+  const int ksteps = K / step;
+  const int s_max = ksteps / (kMmaWarps * 2) >= 2 ? 4 : (ksteps / (kMmaWarps * 2) >= 1 ? 2 : 1);   // launch_gemv_mma's cap on S
+  const int per = s_max == 1 ? ksteps : (ksteps + s_max - 1) / s_max + 1;
+  const size_t xs = (size_t) M * (((size_t) per * xstep + 127) / 128 * 128);
+  return kMmaFixedSmem + (size_t) kMmaWarps * kMmaRingSmall * kMmaChunk + xs <= kMmaSmemMax;
 }
 
 int gemv_mma_launch(int kind, void* y, float* y_f32, const void* x, const void* w, const void* w_scale, const float* sc,
