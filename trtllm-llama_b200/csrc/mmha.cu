@@ -642,6 +642,8 @@ static int mmha_launch(void* out, const void* qkv, void* kv_cache, const long lo
   // The projection that follows is launched with programmatic stream serialisation and requests its first weights before it
   // waits for this kernel: triggering at entry lets its CTAs become resident on the SMs this grid leaves free (same-run A/B,
   // step ms off -> on: int4 B=1 1.692 -> 1.627, W8 B=1 1.878 -> 1.801, cfg3 int8-KV 3.03 -> 2.95, cfg2 2.62 -> 2.60).
+  // (Launching THIS kernel with programmatic serialisation too — rotary angles above a griddepcontrol.wait — measured slower
+  // again with the ring GEMV in front of it: cfg2 2.50 -> 2.53 ms, SmoothQuant 1.66 -> 1.72, int4 1.63 -> 1.68.)
   static const int pdl_env = getenv("TB_MMHA_PDL") ? atoi(getenv("TB_MMHA_PDL")) : 1;   // A/B switch
   p.pdl_trigger = pdl_env;
   p.tpb_log2 = 0;
