@@ -233,7 +233,7 @@ def test_force_ids_teacher_forcing(fused):
     got = sess.step().cpu().numpy()
     assert sess.output_ids(1)[:, 0].cpu().tolist() == [7, 11]
     # oracle on the forced path (same padded-batch protocol: context, then one step fed with the forced tokens)
-    om = RM.OracleLlama(cfg, w, "fp16", True, kv_scale=4.0 / 127.0, max_seq_len=S + new)
+    om = RM.OracleLlama(cfg, RM.quantize_model(w, "fp16"), "fp16", True, kv_scale=4.0 / 127.0, max_seq_len=S + new)
     om.context(ids, lens)
     ref = om.step(forced.numpy())
     tol = 1e-2 * max(1.0, float(np.abs(ref).max()))
