@@ -160,9 +160,6 @@ def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which, rows=1, tp=1)
     kind = {"fp16": ops.KIND_F16, "w8": ops.KIND_W8, "w4": ops.KIND_W4, "sq": ops.KIND_A8W8}[mode]
     bpw = BPW[mode]
     hid = cfg["hidden"]
-    x16 = (torch.randn(rows, max(hid, cfg["inter"]), device="cuda") * 0.1).half()
-    x8 = torch.randint(-127, 127, (rows, max(hid, cfg["inter"])), device="cuda", dtype=torch.int8)
-    st = torch.ones(rows, 1, device="cuda", dtype=torch.float32)
     calls, bytes_total = [], 0
     for i in range(cfg["layers"]):
         for name in ("attention.qkv", "attention.dense", "mlp.fc_gate", "mlp.proj"):
@@ -172,6 +169,15 @@ def gemv_roofline(torch, sess_tensors, cfg, mode, hbm_peak, which, rows=1, tp=1)
             K = int(round(wt.numel() * wt.element_size() / bpw / N))
             calls.append((wt, sc, N, K, name == "mlp.fc_gate"))
             bytes_total += int(N * K * bpw)
+    not_gemv = sorted({c[3] for c in calls if rows > ops.lib.tb_gemv_max_rows(kind, c[3])})
+    if not_gemv:
+        return {"bound": "hbm", "kernel": f"projections with K in {not_gemv} at {rows} rows are outside the decode-shape GEMV (K not a whole "
+                                          "number of its k-steps at this tensor-parallel shard size): the engine runs this step's "
+                                          "projections on the tcgen05 GEMM (gemm_tc_kernel); no GEMV class to time",
+                "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None}
+    x16 = (torch.randn(rows, max(hid, cfg["inter"]), device="cuda") * 0.1).half()
+    x8 = torch.randint(-127, 127, (rows, max(hid, cfg["inter"])), device="cuda", dtype=torch.int8)
+    st = torch.ones(rows, 1, device="cuda", dtype=torch.float32)
     xs16 = {K: x16[:, :K].contiguous() for K in {c[3] for c in calls}}
     xs8 = {K: x8[:, :K].contiguous() for K in {c[3] for c in calls}}
 
@@ -385,7 +391,12 @@ def run_decode_workload(cx, name, steps, warmup, with_e2e=True, with_roofline=Tr
     step_bytes = step_bytes_of(mode, int8_kv, B, in_len, out_len, tp)
     roof = None
     if with_roofline and rank == 0:
-        roof = gemv_roofline(torch, tensors, LLAMA7B, mode, cx.hbm, cx.which, rows=min(B, 8), tp=tp)
+        # rank 0 only and no collective inside: a failure here must not leave this function on one rank alone (the other
+        # ranks are already on their way to the next collective)
+        try:
+            roof = gemv_roofline(torch, tensors, LLAMA7B, mode, cx.hbm, cx.which, rows=min(B, 8), tp=tp)
+        except Exception as ex:  # noqa: BLE001
+            roof = {"error": f"{type(ex).__name__}: {ex}"}
     res = None
     if rank == 0:
         hbm_ms = step_bytes / (cx.hbm * 1e9) * 1e3
@@ -470,35 +481,50 @@ def tp_parity_forced(cx, name, n_steps=32):
     n_steps = min(n_steps, out_len - 1)
     sess, tensors = build_session(cx, mode, int8_kv, B, in_len, out_len, cx.world, cx.rank, graph=not cx.args.no_graph,
                                   peer_ar=not cx.args.nccl_only)
+    # Every rank runs the SAME sequence of collectives whatever happens to rank 0's private tp = 1 engine: a failure there is
+    # recorded (the check then reports ok = false) and the tensor-parallel engine is stepped along its own arg-max path.
     one = one_t = None
-    if cx.rank == 0:
-        one, one_t = build_session(cx, mode, int8_kv, B, in_len, out_len, 1, 0, graph=True, peer_ar=False)
+    one_error = None
     g = torch.Generator().manual_seed(1234)
     ids = torch.randint(3, LLAMA7B["vocab"], (B, in_len), generator=g, dtype=torch.int32)
     lens = torch.full((B,), in_len, dtype=torch.int32)
+    lg_1 = None
+    if cx.rank == 0:
+        try:
+            one, one_t = build_session(cx, mode, int8_kv, B, in_len, out_len, 1, 0, graph=True, peer_ar=False)
+            lg_1 = one.context(ids, lens)
+        except Exception as ex:  # noqa: BLE001
+            one, lg_1, one_error = None, None, f"{type(ex).__name__}: {ex}"
     lg_tp = sess.context(ids, lens)
-    lg_1 = one.context(ids, lens) if one is not None else None
     worst, scale, argmax_equal = 0.0, 1.0, 0
     for s in range(n_steps + 1):
         tok = torch.zeros(B, dtype=torch.int32, device="cuda")
         if cx.rank == 0:
-            worst = max(worst, float((lg_tp - lg_1).abs().max()))
-            scale = max(scale, float(lg_1.abs().max()))
-            argmax_equal += int(torch.equal(lg_tp.argmax(-1), lg_1.argmax(-1)))
-            tok = lg_1.argmax(-1).to(torch.int32)
+            if lg_1 is not None:
+                worst = max(worst, float((lg_tp - lg_1).abs().max()))
+                scale = max(scale, float(lg_1.abs().max()))
+                argmax_equal += int(torch.equal(lg_tp.argmax(-1), lg_1.argmax(-1)))
+                tok = lg_1.argmax(-1).to(torch.int32)
+            else:
+                tok = lg_tp.argmax(-1).to(torch.int32)
         dist.broadcast(tok, 0)
         if s == n_steps:
             break
         sess.force_ids(tok)
         lg_tp = sess.step()
         if one is not None:
-            one.force_ids(tok)
-            lg_1 = one.step()
+            try:
+                one.force_ids(tok)
+                lg_1 = one.step()
+            except Exception as ex:  # noqa: BLE001
+                one, lg_1, one_error = None, None, f"{type(ex).__name__}: {ex}"
     path = "fused step kernel" if cx.lib.tbrt_last_launches(sess._e) == 1 else "per-operator plugin schedule"
     del sess, tensors, one, one_t
     gc.collect()
     torch.cuda.empty_cache()
     tol = 2e-2 * scale
+    if one_error is not None:
+        return {"ok": False, "error": "tp = 1 engine on rank 0: " + one_error, "decode_path": path}
     return {"ok": worst <= tol, "steps_compared": n_steps + 1, "max_abs_logit_diff": round(worst, 5), "tolerance": round(tol, 5),
 "argmax_equal_steps": argmax_equal, "decode_path": path, "rule": "teacher-forced: both engines follow the tp=1 arg-max path; fp32 logits "
             "compared after the context phase and after every generation step"}
@@ -677,7 +703,10 @@ def main():
     parity = None
     if world > 1 and not args.no_tp_parity:
         if rank == 0:
-            parity = tp_parity(cx, name, ids)
+            try:
+                parity = tp_parity(cx, name, ids)
+            except Exception as ex:  # noqa: BLE001  (rank 0 only: must reach the barrier below like every other rank)
+                parity = {"ok": False, "error": f"{type(ex).__name__}: {ex}"}
         cx.barrier()
         forced = tp_parity_forced(cx, name)
         cx.barrier()
@@ -695,7 +724,6 @@ def main():
                 r, _ = run_decode_workload(cx, nm, steps=max(3, min(args.steps, 5)), warmup=3, with_e2e=False)
             except Exception as ex:  # noqa: BLE001  (one side workload must not take the headline down)
                 r = {"error": f"{type(ex).__name__}: {ex}"}
-                cx.barrier()
             if rank == 0:
                 side[nm] = r
         if world == 1 and (args.side is None or "cfg4_prefill" in args.side):
@@ -709,41 +737,49 @@ def main():
             cx.dist.barrier()
             cx.dist.destroy_process_group()
         return
-    line = {"metric": "decode_tokens_per_sec", "value": head["value"], "unit": "tokens/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_request"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE[mode], "data": "synthetic",
-            "config": {"workload": desc, "batch": B, "in_len": in_len, "out_len": out_len, "parallelism": f"tp{world}",
-                       "l2": "inputs larger than L2: every step streams %.1f GB of weights (L2 = 126 MB)"
-                             % (head["decode_step"]["algorithmic_bytes"] / 1e9),
-                       "step_definition": "one request = context phase + out_len-1 generation steps (CUDA-graph replays)"},
-            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "decode_step": head["decode_step"],
-            "context_ms": head["context_ms"], "roofline": head["roofline"], "clocks": head["clocks"]}
-    if "decode_paths" in head:
-        line["decode_paths"] = head["decode_paths"]
-    if "limits" in head:
-        line["limits"] = head["limits"]
-    if parity is not None:
-        line["tp_parity"] = parity["ok"]
-        line["tp_parity_detail"] = parity
-    if side:
-        line["workloads"] = side
-    if not args.only_headline and world == 1:
-        try:
-            from tools.ref_kernel_bench import reference_kernels
-            line["reference_kernels"] = reference_kernels()
-        except Exception as ex:  # noqa: BLE001
-            line["reference_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
-    if not args.no_cpu_baseline and world == 1:
-        try:
-            from oracle.hf_baseline import time_hf_cpu
-            r = time_hf_cpu(batch=B, in_len=in_len, out_len=out_len, new_tokens=6,
-                            **{k: LLAMA7B[k] for k in ("hidden", "inter", "layers", "heads", "vocab")})
-            line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tokens/s", "cores": r["cores"], "kind": "port",
-                                    "sample": r["sample"], "in_len": in_len, "t_prefill_s": round(r["t_prefill_s"], 2),
-                                    "t_step_s": round(r["t_step_s"], 3)}
-        except Exception as ex:  # noqa: BLE001
-            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"failed: {type(ex).__name__}: {ex}"}
+    # rank 0 alone from here to the final barrier: whatever happens while the line is assembled, the barrier is reached (the other
+    # ranks are waiting in it) and a line is printed
+    line = None
+    try:
+        line = {"metric": "decode_tokens_per_sec", "value": head["value"], "unit": "tokens/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_request"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE[mode], "data": "synthetic",
+                "config": {"workload": desc, "batch": B, "in_len": in_len, "out_len": out_len, "parallelism": f"tp{world}",
+                           "l2": "inputs larger than L2: every step streams %.1f GB of weights (L2 = 126 MB)"
+                                 % (head["decode_step"]["algorithmic_bytes"] / 1e9),
+                           "step_definition": "one request = context phase + out_len-1 generation steps (CUDA-graph replays)"},
+                "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "decode_step": head["decode_step"],
+                "context_ms": head["context_ms"], "roofline": head["roofline"], "clocks": head["clocks"]}
+        if "decode_paths" in head:
+            line["decode_paths"] = head["decode_paths"]
+        if "limits" in head:
+            line["limits"] = head["limits"]
+        if parity is not None:
+            line["tp_parity"] = parity["ok"]
+            line["tp_parity_detail"] = parity
+        if side:
+            line["workloads"] = side
+        if not args.only_headline and world == 1:
+            try:
+                from tools.ref_kernel_bench import reference_kernels
+                line["reference_kernels"] = reference_kernels()
+            except Exception as ex:  # noqa: BLE001
+                line["reference_kernels"] = {"error": f"{type(ex).__name__}: {ex}"}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                from oracle.hf_baseline import time_hf_cpu
+                r = time_hf_cpu(batch=B, in_len=in_len, out_len=out_len, new_tokens=6,
+                                **{k: LLAMA7B[k] for k in ("hidden", "inter", "layers", "heads", "vocab")})
+                line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tokens/s", "cores": r["cores"], "kind": "port",
+                                        "sample": r["sample"], "in_len": in_len, "t_prefill_s": round(r["t_prefill_s"], 2),
+                                        "t_step_s": round(r["t_step_s"], 3)}
+            except Exception as ex:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {type(ex).__name__}: {ex}"}
+    except Exception as ex:  # noqa: BLE001
+        if line is None:
+            line = {"metric": "decode_tokens_per_sec", "value": head["value"], "unit": "tokens/s", "n_gpus": world}
+        line["assembly_error"] = f"{type(ex).__name__}: {ex}"
     print(json.dumps(line), flush=True)
     if world > 1:
         cx.dist.barrier()

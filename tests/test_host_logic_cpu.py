@@ -59,3 +59,103 @@ def test_sampling_restatement_distributions():
     # temperature -> 0 sharpens to greedy
     ids, _ = R.sample_top_k_top_p(np.tile(base, (50, 1)), 6, 1.0, 1e-3, u[:50])
     assert (ids == 3).all()
+
+
+def test_bench_roofline_reports_shards_outside_the_decode_gemv():
+    """bench.py times the decode GEMV class on rank 0 only; at tp = 4 / 8 the int4 down projection's K (2752 / 1376) is not a
+    whole number of the GEMV's k-steps, 8 rows are then outside the decode-shape GEMV (the engine uses the tcgen05 GEMM) and the
+    timing function must say so instead of raising on one rank (which once left rank 0 alone in a barrier: a hung N = 4 run)."""
+    torch = pytest.importorskip("torch")
+    import bench
+    from trtllm_llama_b200 import _lib
+    _lib.load_library()
+    cfg = dict(bench.LLAMA7B)
+    cfg["layers"] = 1
+    tp = 4
+    hid, inter = cfg["hidden"], cfg["inter"]
+    shapes = {"attention.qkv": (3 * hid // tp, hid), "attention.dense": (hid, hid // tp),
+              "mlp.fc_gate": (2 * inter // tp, hid), "mlp.proj": (hid, inter // tp)}
+    tensors = {}
+    for name, (N, K) in shapes.items():
+        tensors[f"layers.0.{name}.weight"] = torch.zeros((N, K // 2), dtype=torch.int8)          # int4: two weights per byte
+        tensors[f"layers.0.{name}.per_channel_scale"] = torch.ones(N, dtype=torch.float16)
+    r = bench.gemv_roofline(torch, tensors, cfg, "w4", 6500.0, "measured", rows=8, tp=tp)
+    assert r["achieved"] is None and "2752" in r["kernel"] and "gemm_tc_kernel" in r["kernel"]
+
+
+def _run_bench_main_mocked(monkeypatch, capsys, rank, world, fail_parity=False, fail_side=False):
+    """bench.main() with the GPU work mocked out: returns (printed line or None, the sequence of collectives this rank entered)."""
+    import json
+    import sys
+    import types
+    torch = pytest.importorskip("torch")
+    import bench
+    ops_log = []
+
+    class FakeDist:
+        def barrier(self): ops_log.append("barrier")
+        def destroy_process_group(self): ops_log.append("destroy")
+
+    class FakeCtx:
+        def __init__(self, args):
+            self.args, self.rank, self.world, self.local = args, rank, world, rank
+            self.torch, self.lib, self.hbm, self.which = torch, None, 6500.0, "measured"
+            self.dist = FakeDist() if world > 1 else None
+        def barrier(self):
+            if self.dist is not None:
+                self.dist.barrier()
+
+    def fake_workload(cx, name, steps, warmup, with_e2e=True, with_roofline=True, return_ids=False):
+        ops_log.append("workload:" + name)
+        if fail_side and name == "cfg5_b8" and cx.rank == 0:
+            raise RuntimeError("rank-0-only failure inside a side workload")
+        if cx.rank != 0:
+            return None, None
+        head = {"value": 1.0, "ms_per_request": 1.0, "e2e": {}, "gpu_launches": 1, "context_ms": 1.0, "roofline": {}, "clocks": {},
+                "decode_step": {"algorithmic_bytes": 1e9}}
+        return head, [[1, 2, 3]]
+
+    def fake_parity(cx, name, ids):
+        if fail_parity:
+            raise RuntimeError("tp = 1 engine could not be built")
+        return {"ok": True}
+
+    def fake_forced(cx, name, n_steps=32):
+        ops_log.append("forced")
+        return {"ok": True}
+
+    monkeypatch.setattr(bench, "Ctx", FakeCtx)
+    monkeypatch.setattr(bench, "run_decode_workload", fake_workload)
+    monkeypatch.setattr(bench, "run_prefill_workload", lambda cx, steps, warmup: {"prefill_ms": 1.0})
+    monkeypatch.setattr(bench, "tp_parity", fake_parity)
+    monkeypatch.setattr(bench, "tp_parity_forced", fake_forced)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    fake_ref = types.ModuleType("tools.ref_kernel_bench")
+    fake_ref.reference_kernels = lambda: {"rows": []}
+    monkeypatch.setitem(sys.modules, "tools.ref_kernel_bench", fake_ref)
+    fake_hf = types.ModuleType("oracle.hf_baseline")
+    fake_hf.time_hf_cpu = lambda **kw: {"value": 1.0, "cores": 1, "sample": "mock", "t_prefill_s": 1.0, "t_step_s": 1.0}
+    monkeypatch.setitem(sys.modules, "oracle.hf_baseline", fake_hf)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", str(world), "--steps", "3", "--warmup", "3"])
+    bench.main()
+    out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    return (json.loads(out[-1]) if out else None), ops_log
+
+
+def test_bench_main_single_gpu_line_has_the_contract_keys(monkeypatch, capsys):
+    line, _ = _run_bench_main_mocked(monkeypatch, capsys, rank=0, world=1)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks", "workloads", "reference_kernels", "cpu_baseline"):
+        assert k in line, k
+    assert "assembly_error" not in line and "cfg4_prefill" in line["workloads"]
+
+
+@pytest.mark.parametrize("fail_parity", [False, True])
+def test_bench_main_every_rank_enters_the_same_collectives(monkeypatch, capsys, fail_parity):
+    """torchrun ranks must agree on the sequence of collectives even when a rank-0-only part fails (the tp = 1 comparison
+    engine): otherwise rank 0 pairs a barrier with a later one of its peers and the job hangs at exit."""
+    line0, ops0 = _run_bench_main_mocked(monkeypatch, capsys, rank=0, world=4, fail_parity=fail_parity)
+    line1, ops1 = _run_bench_main_mocked(monkeypatch, capsys, rank=1, world=4, fail_parity=fail_parity)
+    assert ops0 == ops1 and ops0[-2:] == ["barrier", "destroy"]
+    assert line1 is None and line0["n_gpus"] == 4 and line0["tp_parity"] is (not fail_parity)
+    assert set(line0["workloads"]) == {"cfg5", "cfg5_b8"}
