@@ -674,6 +674,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _final_rendezvous(cx, seconds=120.0):
+    """Last barrier + process-group teardown of a torchrun job.  The result line is already printed: if a peer never arrives
+    (it died, or an earlier mismatch left it elsewhere) this process exits cleanly after `seconds` instead of hanging the job."""
+    import threading
+    watchdog = threading.Timer(seconds, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    cx.dist.barrier()
+    cx.dist.destroy_process_group()
+    watchdog.cancel()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -734,8 +746,7 @@ def main():
 
     if rank != 0:
         if world > 1:
-            cx.dist.barrier()
-            cx.dist.destroy_process_group()
+            _final_rendezvous(cx)
         return
     # rank 0 alone from here to the final barrier: whatever happens while the line is assembled, the barrier is reached (the other
     # ranks are waiting in it) and a line is printed
@@ -782,8 +793,7 @@ def main():
         line["assembly_error"] = f"{type(ex).__name__}: {ex}"
     print(json.dumps(line), flush=True)
     if world > 1:
-        cx.dist.barrier()
-        cx.dist.destroy_process_group()
+        _final_rendezvous(cx)
 
 
 if __name__ == "__main__":
