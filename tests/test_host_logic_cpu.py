@@ -159,3 +159,54 @@ def test_bench_main_every_rank_enters_the_same_collectives(monkeypatch, capsys, 
     assert ops0 == ops1 and ops0[-2:] == ["barrier", "destroy"]
     assert line1 is None and line0["n_gpus"] == 4 and line0["tp_parity"] is (not fail_parity)
     assert set(line0["workloads"]) == {"cfg5", "cfg5_b8"}
+
+
+@pytest.mark.parametrize("fail", [None, "build", "step"])
+def test_tp_parity_forced_keeps_ranks_in_step_when_the_tp1_engine_fails(monkeypatch, fail):
+    """bench.tp_parity_forced is a collective: rank 0's private tp = 1 engine may fail to build or to step without changing the
+    sequence of broadcasts / engine steps rank 0 runs (else the peers wait in a broadcast forever)."""
+    torch = pytest.importorskip("torch")
+    import types
+    import bench
+
+    def run(rank):
+        log = []
+
+        class FakeSess:
+            def __init__(self, tp):
+                self.tp, self._e, self.n = tp, None, 0
+            def context(self, ids, lens):
+                log.append(f"context tp{self.tp}")
+                return torch.zeros(1, 8)
+            def step(self):
+                self.n += 1
+                if self.tp == 1 and fail == "step" and self.n == 3:
+                    raise RuntimeError("boom")
+                log.append(f"step tp{self.tp}")
+                return torch.zeros(1, 8)
+            def force_ids(self, tok):
+                pass
+
+        def fake_build(cx, mode, int8_kv, B, in_len, out_len, tp, rank_, graph=True, peer_ar=True):
+            if tp == 1 and fail == "build":
+                raise RuntimeError("no memory for the tp = 1 engine")
+            return FakeSess(tp), {}
+
+        class FakeDist:
+            def broadcast(self, t, src):
+                log.append("broadcast")
+
+        cx = types.SimpleNamespace(torch=torch, dist=FakeDist(), world=4, rank=rank, args=types.SimpleNamespace(no_graph=False, nccl_only=False),
+                                   lib=types.SimpleNamespace(tbrt_last_launches=lambda e: 1))
+        monkeypatch.setattr(bench, "build_session", fake_build)
+        monkeypatch.setattr(torch, "zeros", lambda *a, **k: torch.ones(*a, **{kk: v for kk, v in k.items() if kk != "device"}) * 0)
+        monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+        r = bench.tp_parity_forced(cx, "cfg2", n_steps=5)
+        return r, [x for x in log if "tp1" not in x]
+
+    r0, ops0 = run(0)
+    r1, ops1 = run(1)
+    assert ops0 == ops1 and ops0.count("broadcast") == 6 and ops0.count("step tp4") == 5
+    assert r0["ok"] is (fail is None)
+    if fail:
+        assert "tp = 1 engine" in r0["error"]
