@@ -664,7 +664,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "decode_tokens_per_sec", "value": round(value, 3), "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 1),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": desc, "batch": B, "in_len": in_len, "out_len": out_len},
+            # the same `config` object as the b200 arm prints for this N (the driver compares the two)
+            "config": {"workload": desc, "batch": B, "in_len": in_len, "out_len": out_len, "parallelism": f"tp{args.gpus}",
+                       "l2": "inputs larger than L2: every step streams %.1f GB of weights (L2 = 126 MB)"
+                             % (int(step_bytes_of(mode, int8_kv, B, in_len, out_len, args.gpus)) / 1e9),
+                       "step_definition": "one request = context phase + out_len-1 generation steps (CUDA-graph replays)"},
             "cpu_baseline": {"value": round(value, 3), "unit": "tokens/s", "cores": cores, "kind": "port",
                              "sample": f"run_hf.py path (HF LlamaForCausalLM.forward greedy, fp32, random-init 7B) on {cores} host "
                                        f"threads: {in_len}-token prefill + {new_tokens} greedy steps per step, rate extrapolated "
